@@ -1,0 +1,183 @@
+/* lorads_b200.h -- C ABI of the B200-native LoRADS low-rank kernel layer.
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  All host matrices are
+ * the reference's own formats:
+ *   - a factor matrix (U, V, R, Grad, ...) is column-major n x r, exactly
+ *     lorads_sdp_dense.matElem (reference src_semi/data/def_lorads_elements.h:29-33);
+ *   - cone data are the SDPA reader's output arrays coneMatBeg / coneMatIdx /
+ *     coneMatElem (CSC over the packed lower-triangular index, column 0 = C,
+ *     column i = A_i; reference src_semi/io/lorads_file_io.c:325-340,
+ *     src_semi/data/lorads_sdp_conic.c:160-168);
+ *   - m-vectors (b, lambda, constrValSum, ...) are plain double[m].
+ * Indices are 64-bit (lb2_int) regardless of the reference's lorads_int width.
+ *
+ * Every entry point returns 0 on success and a negative lb2 error code
+ * otherwise (lb2_last_error() gives the text).  There is NO CPU fallback: when
+ * no CUDA device is usable lb2_create() fails with LB2_ERR_CUDA.
+ *
+ * Each function names the reference function(s) it replaces.
+ */
+#ifndef LORADS_B200_H
+#define LORADS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int64_t lb2_int;
+typedef struct lb2_solver lb2_solver;
+
+#define LB2_OK            0
+#define LB2_ERR_ARG      -1
+#define LB2_ERR_CUDA     -2
+#define LB2_ERR_STATE    -3
+#define LB2_ERR_UNSUPPORTED -4
+#define LB2_ERR_NUMERIC  -5
+
+/* return codes of the phase functions, reference src_semi/lorads.h:62-65 */
+#define LB2_RET_OK        0
+#define LB2_RET_TIME_OUT  1
+#define LB2_RET_NUM_ERR   4
+#define LB2_RET_BAD_ITER  8
+
+/* solver status, reference src_semi/lorads.h:45-51 */
+#define LB2_STATUS_UNKNOWN             0
+#define LB2_STATUS_PRIMAL_DUAL_OPTIMAL 1
+#define LB2_STATUS_PRIMAL_OPTIMAL      2
+#define LB2_STATUS_MAXITER             3
+#define LB2_STATUS_TIME_LIMIT          4
+
+/* Same fields and defaults as lorads_params (reference src_semi/lorads.h:82-105,
+ * defaults src_semi/main.c:19-43,236); fname is not part of the kernel layer. */
+typedef struct {
+    double  initRho;
+    double  rhoMax;
+    double  rhoCellingALM;
+    double  rhoCellingADMM;
+    lb2_int maxALMIter;
+    lb2_int maxADMMIter;
+    double  timesLogRank;
+    lb2_int rhoFreq;
+    double  rhoFactor;
+    double  ALMRhoFactor;
+    double  phase1Tol;
+    double  phase2Tol;
+    double  timeSecLimit;
+    double  heuristicFactor;
+    lb2_int lbfgsListLength;
+    double  endTauTol;
+    double  endALMSubTol;
+    int     l2Rescaling;
+    lb2_int reoptLevel;
+    lb2_int dyrankLevel;
+    int     highAccMode;
+    int     verbose;          /* 0 silent, 1 reference-style log lines */
+} lb2_params;
+
+/* What main.c reads back after a solve (reference src_semi/main.c:404-410,478-504
+ * and printRes, src_semi/data/lorads_solver.c:908-922). */
+typedef struct {
+    double  pObj, dObj;
+    double  pInfeasL1, dInfeasL1, pdGap;   /* DIMACS errors 1, 2, 3 */
+    double  pInfeasInf, dInfeasInf;        /* DIMACS errors 5, 6   */
+    lb2_int almOuterIter, almInnerIter, admmIter, cgIter;
+    double  almRho, admmRho;
+    double  solveSeconds;                  /* host wall clock of lb2_solve      */
+    double  almSeconds, admmSeconds;
+    int     status;                        /* LB2_STATUS_*                       */
+    lb2_int finalRank0;                    /* rank of cone 0 at exit             */
+    lb2_int kernelLaunches;                /* kernels launched by this library   */
+} lb2_result;
+
+const char *lb2_last_error(void);
+const char *lb2_version(void);
+void lb2_default_params(lb2_params *p);                       /* main.c:19-43 initCommandLineArgs */
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+
+/* LORADSInitSolver + LORADSSetDualObjective (lorads_solver.c:17,125).  `device` is the CUDA ordinal. */
+int lb2_create(lb2_solver **out, lb2_int nRows, lb2_int nCones, const lb2_int *blkDims,
+               const double *rowRHS, int device);
+/* LORADSInitConeData (lorads_solver.c:130) for one PSD block; arrays are borrowed during the call only. */
+int lb2_set_cone_data(lb2_solver *s, lb2_int iCone, const lb2_int *coneMatBeg,
+                      const lb2_int *coneMatIdx, const double *coneMatElem);
+/* LORADSPreprocess (lorads_solver.c:189): AConeProcData + AConePresolveData (lorads_sdp_conic.c:758,868):
+ * coefficient classification, union pattern, index maps; then the device layouts are built and uploaded. */
+int lb2_preprocess(lb2_solver *s);
+/* LORADSDetermineRank (lorads_solver.c:290). */
+int lb2_determine_rank(lb2_solver *s, double timesLogRank);
+/* LORADSInitALMVars + LORADSInitADMMVars + initial_solver_state (lorads_solver.c:406,580,1148); the libc
+ * rand() draw order of the reference (srand(925), R, then U, V per cone) is reproduced. */
+int lb2_init_vars(lb2_solver *s, lb2_int lbfgsListLength, double initRho);
+/* LORADSDestroy* (lorads_solver.c:81,265,280,500,677). */
+void lb2_destroy(lb2_solver *s);
+
+/* Multi-GPU: factor columns are sharded over `world` ranks (one process per GPU); `ncclUniqueId` is the
+ * 128-byte NCCL id produced on rank 0 and broadcast by the caller (e.g. torch.distributed over gloo/nccl).
+ * Call between lb2_determine_rank and lb2_init_vars. */
+int lb2_comm_unique_id(void *id128);
+int lb2_comm_init(lb2_solver *s, const void *id128, int rank, int world);
+
+/* ---- queries ------------------------------------------------------------------------------ */
+/* what: 0 nRows, 1 nCones, 2 blkDim, 3 rank, 4 |P| (pattern entries; n(n+1)/2 on the dense path),
+ *       5 1 if the cone is a "dense-constraint cone" (> 30% of rows touch it, lorads_user_data.c:68-70)
+ *       6 1 if the cone uses the dense scratch path, 7 nnz of the cone, 8 active constraints of the cone,
+ *       9 rank_max, 10 local rank (column shard) , 11 kernel launches so far, 12 nnzA, 13 nnzC */
+lb2_int lb2_info(const lb2_solver *s, int what, lb2_int iCone);
+/* what: 0 cObjNrm1, 1 cObjNrm2, 2 cObjNrmInf, 3 bNrm1, 4 bNrm2, 5 bNrmInf, 6 rho0, 7 pObj, 8 dObj,
+ *       9 pinf(1), 10 gap, 11 dinf(1), 12 scaleObjHis */
+double  lb2_dinfo(const lb2_solver *s, int what);
+/* union pattern P of a sparse-path cone (row >= col, sorted by (col,row)), AConePresolveData :974-1005 */
+int lb2_get_pattern(const lb2_solver *s, lb2_int iCone, lb2_int *rows, lb2_int *cols);
+
+/* ---- state transfer (host column-major <-> device layout) ----------------------------------- */
+/* which: 'R' 'U' 'V' 'G'(rad) 'M'(2temp) 'B'(bLinSys) */
+int lb2_set_factor(lb2_solver *s, char which, lb2_int iCone, const double *colMajor);
+int lb2_get_factor(const lb2_solver *s, char which, lb2_int iCone, double *colMajor);
+/* which: 'l' dualVar, 's' constrValSum, 'b' rowRHS, 'm' M1temp, 'q' ARDSum, 'Q' ADDSum, 'v' constrVio */
+int lb2_set_vec(lb2_solver *s, char which, const double *v);
+int lb2_get_vec(const lb2_solver *s, char which, double *v);
+
+/* ---- hot-path operators (host buffers in/out; the parity tests call these) ------------------- */
+/* constrVal = A(sym(U V^T)) of one cone, expanded to length nRows; if obj != NULL also <C, sym(U V^T)>.
+ * Replaces LORADSUVt + coneAUV (+ objAUV): lorads_alg_common.c:21-76,97-103; lorads_sdp_conic.c:285,294,498,507;
+ * lorads_sdp_data.c:524-587,698-715. */
+int lb2_auv(lb2_solver *s, lb2_int iCone, char u, char v, double *constrVal, double *obj);
+/* out (n x r col-major) = ([C] + sum_i w_i A_i) X.  Replaces zeros + addObjCoeff + sdpDataWSum + mul_rk:
+ * lorads_alm.c:29-34; lorads_sdp_conic.c:327,437,539,633; lorads_sdp_data.c:491-504,589-671. */
+int lb2_wsum_mulrk(lb2_solver *s, lb2_int iCone, const double *w, int addC, char x, double *out);
+/* ALMCalGrad (lorads_alm.c:41) with the current dualVar / constrValSum; Grad stays on device ('G'). */
+int lb2_alm_cal_grad(lb2_solver *s, double rho, double *lagNormSquare);
+/* res = x + (sum_i A(sym(x V^T))_i A_i) V : ADMMUpdateUVMvec / linSysProduct (lorads_admm.c:376-426). */
+int lb2_cg_matvec(lb2_solver *s, lb2_int iCone, char noUpdate, const double *x, double *res);
+/* LORADSUpdateSDPVarOne (lorads_admm.c:428) = RHS build + CGSolve (lorads_cgs.c:81), all on device. */
+int lb2_update_sdp_var_one(lb2_solver *s, lb2_int iCone, char upd, char noupd, double rho,
+                           double cgTol, lb2_int cgMaxIter, lb2_int *cgIters);
+/* state at ALG_START of LORADS_ALMOptimize (lorads_alm.c:1004-1014); returns sum ||Grad||^2 */
+int lb2_alm_prepare(lb2_solver *s, double rho, double *lagNormSquare);
+/* one ALM inner iteration, the loop body lorads_alm.c:1073-1146.
+ * out[0]=tau out[1]=lagNormSquare out[2]=pinf(1) out[3]=p1 out[4]=p2 ; *rootNum = 0 on numerical failure */
+int lb2_alm_inner_iter(lb2_solver *s, double rho, lb2_int lbfgsCounter, double *out, lb2_int *rootNum);
+/* `iters` inner iterations back to back, device resident; seconds = CUDA-event time of the loop. */
+int lb2_time_alm_inner_iters(lb2_solver *s, double rho, lb2_int iters, double *out, double *seconds);
+
+/* ---- phases (host control flow feeding on device-computed scalars) --------------------------- */
+/* LORADS_ALMOptimize (lorads_alm.c:991) */
+int lb2_alm_optimize(lb2_solver *s, lb2_params *p, double timeSolveStart);
+/* LORADS_ALMtoADMM (lorads_solver.c:968) */
+int lb2_alm_to_admm(lb2_solver *s, lb2_params *p);
+/* LORADSADMMOptimize (lorads_admm.c:33); returns LB2_RET_* */
+int lb2_admm_optimize(lb2_solver *s, lb2_params *p, lb2_int iterCelling, double timeSolveStart);
+/* calculate_dual_infeasibility_solver (lorads_solver.c:1007) */
+int lb2_dual_infeasibility(lb2_solver *s);
+/* The whole driver sequence of main.c:321-487 (ALM, ALM->ADMM, ADMM, reopt rounds, dual infeasibility). */
+int lb2_solve(lb2_solver *s, lb2_params *p, lb2_result *res);
+/* copies the current primal factor R (n x r col-major) and the dual vector to the host */
+int lb2_get_solution(const lb2_solver *s, lb2_int iCone, double *R, double *dualVar);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LORADS_B200_H */

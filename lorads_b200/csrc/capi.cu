@@ -1,0 +1,337 @@
+// capi.cu -- the extern "C" boundary declared in include/lorads_b200.h, plus the NCCL plumbing.
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "solver.hpp"
+
+using namespace lb2;
+
+static thread_local std::string g_err;
+
+struct lb2_solver {
+    Solver impl;
+};
+
+#define LB2_TRY try {
+#define LB2_CATCH                                                       \
+    }                                                                   \
+    catch (const CudaError &e) { g_err = e.what(); return LB2_ERR_CUDA; }        \
+    catch (const std::invalid_argument &e) { g_err = e.what(); return LB2_ERR_ARG; } \
+    catch (const std::logic_error &e) { g_err = e.what(); return LB2_ERR_STATE; }    \
+    catch (const std::exception &e) { g_err = e.what(); return LB2_ERR_UNSUPPORTED; } \
+    return LB2_OK;
+
+// ---------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily so that the library has no link-time dependency on it
+// ---------------------------------------------------------------------------------------------------
+namespace {
+typedef struct { char internal[128]; } nccl_uid;
+typedef int (*fn_get_uid)(nccl_uid *);
+typedef int (*fn_init_rank)(void **, int, nccl_uid, int);
+typedef int (*fn_allreduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_destroy)(void *);
+typedef const char *(*fn_errstr)(int);
+struct NcclApi {
+    void *h = nullptr;
+    fn_get_uid get_uid = nullptr;
+    fn_init_rank init_rank = nullptr;
+    fn_allreduce allreduce = nullptr;
+    fn_destroy destroy = nullptr;
+    fn_errstr errstr = nullptr;
+    bool load() {
+        if (h) return true;
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return false;
+        get_uid = (fn_get_uid)dlsym(h, "ncclGetUniqueId");
+        init_rank = (fn_init_rank)dlsym(h, "ncclCommInitRank");
+        allreduce = (fn_allreduce)dlsym(h, "ncclAllReduce");
+        destroy = (fn_destroy)dlsym(h, "ncclCommDestroy");
+        errstr = (fn_errstr)dlsym(h, "ncclGetErrorString");
+        return get_uid && init_rank && allreduce;
+    }
+} g_nccl;
+}  // namespace
+
+void Solver::allreduce(double *p, long long count) {
+    if (world <= 1 || count <= 0) return;
+    // ncclDouble = 8, ncclSum = 0
+    int rc = g_nccl.allreduce(p, p, (size_t)count, 8, 0, nccl, ctx.stream);
+    if (rc != 0) throw CudaError(std::string("ncclAllReduce failed: ") + (g_nccl.errstr ? g_nccl.errstr(rc) : "?"));
+}
+
+extern "C" {
+
+const char *lb2_last_error(void) { return g_err.c_str(); }
+const char *lb2_version(void) { return "lorads_b200 0.1 (sm_100a)"; }
+
+void lb2_default_params(lb2_params *p) {
+    std::memset(p, 0, sizeof(*p));
+    p->initRho = 0.0; p->rhoMax = 5000.0; p->rhoCellingALM = 1e+8; p->rhoCellingADMM = p->rhoMax * 200;
+    p->maxALMIter = 200; p->maxADMMIter = 10000; p->timesLogRank = 2.0; p->rhoFreq = 5; p->rhoFactor = 1.2;
+    p->ALMRhoFactor = 2.0; p->phase1Tol = 1e-3; p->phase2Tol = 1e-5; p->timeSecLimit = 3600.0;
+    p->heuristicFactor = 1.0; p->lbfgsListLength = 2; p->endTauTol = 1e-16; p->endALMSubTol = 1e-10;
+    p->l2Rescaling = 0; p->reoptLevel = 2; p->dyrankLevel = 2; p->highAccMode = 0; p->verbose = 0;
+}
+
+int lb2_create(lb2_solver **out, lb2_int nRows, lb2_int nCones, const lb2_int *blkDims, const double *rowRHS, int device) {
+    if (!out || !blkDims || !rowRHS || nRows <= 0 || nCones <= 0) { g_err = "lb2_create: bad argument"; return LB2_ERR_ARG; }
+    *out = nullptr;
+    lb2_solver *s = nullptr;
+    LB2_TRY
+    s = new lb2_solver();
+    try {
+        s->impl.create(nRows, nCones, blkDims, rowRHS, device);
+    } catch (...) {
+        delete s;
+        throw;
+    }
+    *out = s;
+    LB2_CATCH
+}
+
+int lb2_set_cone_data(lb2_solver *s, lb2_int iCone, const lb2_int *beg, const lb2_int *idx, const double *elem) {
+    if (!s || !beg) { g_err = "null argument"; return LB2_ERR_ARG; }
+    LB2_TRY s->impl.set_cone(iCone, beg, idx, elem); LB2_CATCH
+}
+int lb2_preprocess(lb2_solver *s) { if (!s) return LB2_ERR_ARG; LB2_TRY s->impl.preprocess(); LB2_CATCH }
+int lb2_determine_rank(lb2_solver *s, double t) { if (!s) return LB2_ERR_ARG; LB2_TRY s->impl.determine_rank(t); LB2_CATCH }
+int lb2_init_vars(lb2_solver *s, lb2_int L, double initRho) { if (!s) return LB2_ERR_ARG; LB2_TRY s->impl.init_vars(L, initRho); LB2_CATCH }
+void lb2_destroy(lb2_solver *s) {
+    if (!s) return;
+    if (s->impl.nccl && g_nccl.destroy) g_nccl.destroy(s->impl.nccl);
+    cudaSetDevice(s->impl.device);
+    delete s;
+}
+
+int lb2_comm_unique_id(void *id128) {
+    if (!g_nccl.load()) { g_err = "NCCL library not found"; return LB2_ERR_UNSUPPORTED; }
+    return g_nccl.get_uid((nccl_uid *)id128) == 0 ? LB2_OK : LB2_ERR_CUDA;
+}
+
+int lb2_comm_init(lb2_solver *s, const void *id128, int rank, int world) {
+    if (!s || world < 1 || rank < 0 || rank >= world) { g_err = "lb2_comm_init: bad argument"; return LB2_ERR_ARG; }
+    if (world == 1) return LB2_OK;
+    if (!g_nccl.load()) { g_err = "NCCL library not found"; return LB2_ERR_UNSUPPORTED; }
+    LB2_TRY
+    LB2_CUDA(cudaSetDevice(s->impl.device));
+    nccl_uid id;
+    std::memcpy(&id, id128, sizeof(id));
+    int rc = g_nccl.init_rank(&s->impl.nccl, world, id, rank);
+    if (rc != 0) throw CudaError("ncclCommInitRank failed");
+    s->impl.world = world; s->impl.myrank = rank;
+    LB2_CATCH
+}
+
+lb2_int lb2_info(const lb2_solver *s, int what, lb2_int c) {
+    if (!s) return -1;
+    const Solver &S = s->impl;
+    if (what == 0) return S.m;
+    if (what == 1) return S.nCones;
+    if (what == 11) return S.ctx.launches;
+    if (c < 0 || c >= S.nCones) return -1;
+    switch (what) {
+    case 2: return S.blkDims[c];
+    case 3: return S.rank.empty() ? 0 : S.rank[c];
+    case 9: return S.rank_max.empty() ? 0 : S.rank_max[c];
+    }
+    if (!S.preprocessed) return -1;
+    const ConeDev &K = S.cones[c];
+    switch (what) {
+    case 4: return K.np;
+    case 5: return K.dense_cone ? 1 : 0;
+    case 6: return K.dense_path ? 1 : 0;
+    case 7: return K.nnzA + K.nnzC;
+    case 8: return K.n_act;
+    case 10: return K.r;
+    case 12: return K.nnzA;
+    case 13: return K.nnzC;
+    }
+    return -1;
+}
+
+double lb2_dinfo(const lb2_solver *s, int what) {
+    if (!s) return NAN;
+    const Solver &S = s->impl;
+    switch (what) {
+    case 0: return S.cObjNrm1; case 1: return S.cObjNrm2; case 2: return S.cObjNrmInf;
+    case 3: return S.bNrm1; case 4: return S.bNrm2; case 5: return S.bNrmInf;
+    case 6: return S.alm.rho; case 7: return S.pObj; case 8: return S.dObj;
+    case 9: return S.dimac_pinf; case 10: return S.dimac_gap; case 11: return S.dimac_dinf; case 12: return S.scaleObjHis;
+    }
+    return NAN;
+}
+
+int lb2_get_pattern(const lb2_solver *s, lb2_int c, lb2_int *rows, lb2_int *cols) {
+    if (!s || c < 0 || c >= s->impl.nCones || !s->impl.preprocessed) { g_err = "bad cone / not preprocessed"; return LB2_ERR_ARG; }
+    const ConeDev &K = s->impl.cones[c];
+    if (K.dense_path) { g_err = "dense-path cone has no explicit pattern"; return LB2_ERR_UNSUPPORTED; }
+    for (size_t p = 0; p < K.P_row_h.size(); ++p) { rows[p] = K.P_row_h[p]; cols[p] = K.P_col_h[p]; }
+    return LB2_OK;
+}
+
+int lb2_set_factor(lb2_solver *s, char which, lb2_int c, const double *cm) {
+    if (!s || !cm) return LB2_ERR_ARG;
+    LB2_TRY if (!s->impl.vars_ready) throw std::logic_error("variables not initialised"); s->impl.set_factor(which, c, cm); LB2_CATCH
+}
+int lb2_get_factor(const lb2_solver *s, char which, lb2_int c, double *cm) {
+    if (!s || !cm) return LB2_ERR_ARG;
+    LB2_TRY if (!s->impl.vars_ready) throw std::logic_error("variables not initialised"); s->impl.get_factor(which, c, cm); LB2_CATCH
+}
+int lb2_set_vec(lb2_solver *s, char which, const double *v) {
+    if (!s || !v) return LB2_ERR_ARG;
+    LB2_TRY
+    Solver &S = s->impl;
+    LB2_CUDA(cudaMemcpyAsync(S.vec_ptr(which), v, sizeof(double) * S.m, cudaMemcpyHostToDevice, S.ctx.stream));
+    S.sync();
+    LB2_CATCH
+}
+int lb2_get_vec(const lb2_solver *s, char which, double *v) {
+    if (!s || !v) return LB2_ERR_ARG;
+    LB2_TRY
+    Solver &S = const_cast<Solver &>(s->impl);
+    LB2_CUDA(cudaMemcpyAsync(v, S.vec_ptr(which), sizeof(double) * S.m, cudaMemcpyDeviceToHost, S.ctx.stream));
+    S.sync();
+    LB2_CATCH
+}
+
+int lb2_auv(lb2_solver *s, lb2_int c, char u, char v, double *constrVal, double *obj) {
+    if (!s || !constrVal) return LB2_ERR_ARG;
+    LB2_TRY
+    Solver &S = s->impl;
+    ConeDev &K = S.cones.at(c);
+    const bool same = (u == v);
+    S.cone_auv(K, obj != nullptr, S.factor_ptr(u), S.factor_ptr(v), same, 1.0, K.t1.p);
+    S.expand_cv_from(K, K.t1.p, S.cvfull.p);
+    LB2_CUDA(cudaMemcpyAsync(constrVal, S.cvfull.p, sizeof(double) * S.m, cudaMemcpyDeviceToHost, S.ctx.stream));
+    if (obj) LB2_CUDA(cudaMemcpyAsync(obj, K.t1.p + K.n_act, sizeof(double), cudaMemcpyDeviceToHost, S.ctx.stream));
+    S.sync();
+    LB2_CATCH
+}
+
+int lb2_wsum_mulrk(lb2_solver *s, lb2_int c, const double *w, int addC, char x, double *out) {
+    if (!s || !w || !out) return LB2_ERR_ARG;
+    LB2_TRY
+    Solver &S = s->impl;
+    ConeDev &K = S.cones.at(c);
+    LB2_CUDA(cudaMemcpyAsync(S.M1.p, w, sizeof(double) * S.m, cudaMemcpyHostToDevice, S.ctx.stream));
+    S.cone_wsum(K, S.M1.p, false, addC != 0);
+    S.cone_mul(K, S.factor_ptr(x), 1.0, 0.0, nullptr, nullptr, S.M2.p, nullptr);
+    S.get_factor('M', c, out);
+    LB2_CATCH
+}
+
+int lb2_alm_cal_grad(lb2_solver *s, double rho, double *lag) {
+    if (!s || !lag) return LB2_ERR_ARG;
+    LB2_TRY *lag = s->impl.cal_grad(rho); LB2_CATCH
+}
+
+int lb2_cg_matvec(lb2_solver *s, lb2_int c, char noUpdate, const double *x, double *res) {
+    if (!s || !x || !res) return LB2_ERR_ARG;
+    LB2_TRY
+    Solver &S = s->impl;
+    ConeDev &K = S.cones.at(c);
+    S.upload_factor(S.cg_p.p, K, x);
+    S.cg_matvec(K, S.cg_p.p, S.factor_ptr(noUpdate), S.cg_Q.p, nullptr, nullptr);
+    S.download_factor(S.cg_Q.p, K, res);
+    LB2_CATCH
+}
+
+int lb2_update_sdp_var_one(lb2_solver *s, lb2_int c, char upd, char noupd, double rho, double tol, lb2_int maxit, lb2_int *iters) {
+    if (!s) return LB2_ERR_ARG;
+    LB2_TRY
+    Solver &S = s->impl;
+    S.cones.at(c);
+    S.update_sdp_var_one(c, S.factor_ptr(upd), S.factor_ptr(noupd), rho, tol, maxit);
+    S.sync();
+    if (iters) *iters = S.cones[c].cg_iter_last;
+    LB2_CATCH
+}
+
+int lb2_alm_prepare(lb2_solver *s, double rho, double *lag) {
+    if (!s) return LB2_ERR_ARG;
+    LB2_TRY
+    Solver &S = s->impl;
+    S.init_constr_val_all(S.R.p, S.R.p, true);
+    S.constr_val_sum();
+    double l = S.cal_grad(rho);
+    if (lag) *lag = l;
+    LB2_CATCH
+}
+
+int lb2_alm_inner_iter(lb2_solver *s, double rho, lb2_int counter, double *out, lb2_int *rootNum) {
+    if (!s || !out) return LB2_ERR_ARG;
+    LB2_TRY
+    Solver &S = s->impl;
+    double tau = 0.0, p12[2], lag = 0, pinf = 0;
+    long long rn = 0;
+    S.alm_inner_front(rho, counter, &tau, p12, &rn);
+    out[0] = tau; out[3] = p12[0]; out[4] = p12[1];
+    if (rootNum) *rootNum = rn;
+    if (rn != 0) {
+        S.alm_inner_back(rho, tau, &lag, &pinf);
+        out[1] = lag; out[2] = pinf;
+    }
+    LB2_CATCH
+}
+
+int lb2_time_alm_inner_iters(lb2_solver *s, double rho, lb2_int iters, double *out, double *seconds) {
+    if (!s || !out || !seconds) return LB2_ERR_ARG;
+    LB2_TRY
+    Solver &S = s->impl;
+    cudaEvent_t e0, e1;
+    LB2_CUDA(cudaEventCreate(&e0)); LB2_CUDA(cudaEventCreate(&e1));
+    LB2_CUDA(cudaEventRecord(e0, S.ctx.stream));
+    double tau = 0.0, p12[2], lag = 0, pinf = 0;
+    for (lb2_int k = 0; k < iters; ++k) {
+        long long rn = 0;
+        S.alm_inner_front(rho, k, &tau, p12, &rn);
+        if (rn == 0) break;
+        S.alm_inner_back(rho, tau, &lag, &pinf);
+    }
+    LB2_CUDA(cudaEventRecord(e1, S.ctx.stream));
+    LB2_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    LB2_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    out[0] = tau; out[1] = lag; out[2] = pinf; out[3] = p12[0]; out[4] = p12[1];
+    *seconds = ms * 1e-3;
+    LB2_CATCH
+}
+
+int lb2_alm_optimize(lb2_solver *s, lb2_params *p, double timeSolveStart) {
+    if (!s || !p) return LB2_ERR_ARG;
+    int rc = 0;
+    LB2_TRY rc = s->impl.alm_optimize(p, 0.0, timeSolveStart, false, false, 0.0); (void)rc; LB2_CATCH
+}
+int lb2_alm_to_admm(lb2_solver *s, lb2_params *p) { if (!s || !p) return LB2_ERR_ARG; LB2_TRY s->impl.alm_to_admm(p); LB2_CATCH }
+int lb2_admm_optimize(lb2_solver *s, lb2_params *p, lb2_int iterCelling, double timeSolveStart) {
+    if (!s || !p) return LB2_ERR_ARG;
+    try {
+        return s->impl.admm_optimize(p, iterCelling, timeSolveStart, false);
+    } catch (const std::exception &e) { g_err = e.what(); return LB2_ERR_CUDA; }
+}
+int lb2_dual_infeasibility(lb2_solver *s) { if (!s) return LB2_ERR_ARG; LB2_TRY s->impl.dual_infeasibility(); LB2_CATCH }
+int lb2_solve(lb2_solver *s, lb2_params *p, lb2_result *res) {
+    if (!s || !p) return LB2_ERR_ARG;
+    LB2_TRY
+    if (!s->impl.vars_ready) throw std::logic_error("call lb2_init_vars before lb2_solve");
+    s->impl.solve(p, res);
+    LB2_CATCH
+}
+int lb2_get_solution(const lb2_solver *s, lb2_int c, double *R, double *dualVar) {
+    if (!s) return LB2_ERR_ARG;
+    LB2_TRY
+    if (R) s->impl.get_factor('R', c, R);
+    if (dualVar) {
+        Solver &S = const_cast<Solver &>(s->impl);
+        LB2_CUDA(cudaMemcpyAsync(dualVar, S.lam.p, sizeof(double) * S.m, cudaMemcpyDeviceToHost, S.ctx.stream));
+        S.sync();
+    }
+    LB2_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,851 @@
+// kernels.cu -- hand-written sm_100a kernels of the LoRADS low-rank hot path.
+//
+// All kernels are FP64 and HBM/L2-bandwidth bound (0.1-0.5 flop/B), so the design rules are: row-major
+// r-padded factor rows (every gather is whole 32 B sectors), 16 B vector loads, a small lane group per
+// gathered row so a warp keeps 8 independent row gathers in flight, warp-shuffle segmented reductions,
+// and deterministic grid reductions (fixed summation order, no floating-point atomics).
+//
+// Reference loops replaced (src_semi/...):
+//   auv_items_kernel   LORADSUVt lorads_alg_common.c:21-68 fused with coneAUV/objAUV
+//                      lorads_sdp_conic.c:285-301,498-513 -> sparseAUV/denseAUV lorads_sdp_data.c:524-587
+//   wsum_kernel        zeros + addObjCoeff + sdpDataWSum lorads_sdp_conic.c:327,437,539,633;
+//                      dataMatSparseAddSparseSDPCoeff lorads_sdp_data.c:618-634
+//   spmm_sym_kernel    dataMatSparseMultiRkMat lorads_sdp_data.c:491-504 (+ the scal/axpy/nrm2 that follow it
+//                      in ALMSetGrad lorads_alm.c:34-37,51 and linSysProduct lorads_admm.c:386-390)
+//   dense_*            fds_syr2k + repack lorads_alg_common.c:50-67; dataMatDenseMultiRkMat lorads_sdp_data.c:646-671
+//   BLAS-1 kernels     lorads_vec_opts.c:116-329 call sites in lorads_alm.c / lorads_cgs.c / lorads_alg_common.c
+#include "kernels.cuh"
+#include "layout.hpp"
+
+namespace lb2 {
+
+static inline int grid_for(long long n, int per_thread, const Ctx &c) {
+    long long b = (n + (long long)kBlock * per_thread - 1) / ((long long)kBlock * per_thread);
+    long long cap = (long long)c.num_sms * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+#define LB2_LAUNCH_CHECK(c)            \
+    do {                               \
+        (c).launches++;                \
+        LB2_CUDA(cudaGetLastError());  \
+    } while (0)
+
+// =================================================================================================
+// A(UV^T)
+// =================================================================================================
+constexpr int kTile = kAuvTileItems;
+
+__device__ __forceinline__ int upper_row(const int *__restrict__ ptr, int n_rows, int item) {
+    // largest row r with ptr[r] <= item (rows are non-empty except possibly trailing/isolated empties)
+    int lo = 0, hi = n_rows;   // invariant: ptr[lo] <= item < ptr[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (ptr[mid] <= item) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <int MODE, int G>
+__global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const double *__restrict__ U,
+                                                           const double *__restrict__ V, int ld, double scale1,
+                                                           double scale2, double *__restrict__ out1,
+                                                           double *__restrict__ out2, double *__restrict__ carry1,
+                                                           double *__restrict__ carry2) {
+    constexpr bool DUAL = (MODE == AUV_DUAL);
+    __shared__ double sp1[kTile];
+    __shared__ double sp2[DUAL ? kTile : 1];
+    __shared__ int s_rows[2];
+    __shared__ double sred[8];
+
+    const int tile = blockIdx.x;
+    const int t0 = tile * kTile;
+    const int t1 = min(t0 + kTile, (int)L.n_items);
+    const int tid = threadIdx.x;
+
+    if (tid == 0) s_rows[0] = upper_row(L.ptr, (int)L.n_rows, t0);
+    if (tid == 32) s_rows[1] = upper_row(L.ptr, (int)L.n_rows, t1 - 1);
+
+    if constexpr (MODE == AUV_FROMZ) {
+        for (int k = t0 + tid; k < t1; k += kBlock) sp1[k - t0] = scale1 * L.coef[k] * U[L.irow[k]];
+    } else {
+        constexpr int NG = kBlock / G;          // groups per block
+        const int g = tid / G, gl = tid % G;
+        for (int k = t0 + g; k < t1; k += NG) {
+            const int i = L.irow[k], j = L.icol[k];
+            const double cf = L.coef[k];
+            const double *ui = U + (size_t)i * ld, *uj = U + (size_t)j * ld;
+            double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            if constexpr (MODE == AUV_SAME) {
+                if (i == j) {
+                    for (int col = 2 * gl; col < ld; col += 2 * G) {
+                        double2 x = ld2(ui + col);
+                        a1 = fma(x.x, x.x, a1); a1 = fma(x.y, x.y, a1);
+                    }
+                } else {
+                    for (int col = 2 * gl; col < ld; col += 2 * G) {
+                        double2 x = ld2(ui + col), y = ld2(uj + col);
+                        a1 = fma(x.x, y.x, a1); a1 = fma(x.y, y.y, a1);
+                    }
+                }
+                a1 = group_sum<G>(a1);
+                if (gl == 0) sp1[k - t0] = scale1 * cf * a1;
+            } else {
+                const double *vi = V + (size_t)i * ld, *vj = V + (size_t)j * ld;
+                if (i == j) {
+                    for (int col = 2 * gl; col < ld; col += 2 * G) {
+                        double2 x = ld2(ui + col), y = ld2(vi + col);
+                        a1 = fma(x.x, y.x, a1); a1 = fma(x.y, y.y, a1);
+                        if constexpr (DUAL) { a3 = fma(y.x, y.x, a3); a3 = fma(y.y, y.y, a3); }
+                    }
+                    a1 = group_sum<G>(a1);
+                    if constexpr (DUAL) a3 = group_sum<G>(a3);
+                    if (gl == 0) {
+                        sp1[k - t0] = scale1 * cf * a1;
+                        if constexpr (DUAL) sp2[k - t0] = scale2 * cf * a3;
+                    }
+                } else {
+                    for (int col = 2 * gl; col < ld; col += 2 * G) {
+                        double2 x = ld2(ui + col), y = ld2(vj + col), p = ld2(uj + col), q = ld2(vi + col);
+                        a1 = fma(x.x, y.x, a1); a1 = fma(x.y, y.y, a1);
+                        a2 = fma(p.x, q.x, a2); a2 = fma(p.y, q.y, a2);
+                        if constexpr (DUAL) { a3 = fma(q.x, y.x, a3); a3 = fma(q.y, y.y, a3); }
+                    }
+                    a1 = group_sum<G>(a1); a2 = group_sum<G>(a2);
+                    if constexpr (DUAL) a3 = group_sum<G>(a3);
+                    if (gl == 0) {
+                        sp1[k - t0] = scale1 * cf * (0.5 * a1 + 0.5 * a2);
+                        if constexpr (DUAL) sp2[k - t0] = scale2 * cf * a3;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const int row_lo = s_rows[0], row_hi = s_rows[1];
+    const int nrows = row_hi - row_lo + 1;
+    const int nit = t1 - t0;
+
+    if (nrows == 1) {
+        // the whole tile belongs to one row: block reduction in a fixed order
+        double v1 = 0.0, v2 = 0.0;
+        for (int k = tid; k < nit; k += kBlock) {
+            v1 += sp1[k];
+            if constexpr (DUAL) v2 += sp2[k];
+        }
+        v1 = block_sum(v1, sred);
+        if constexpr (DUAL) v2 = block_sum(v2, sred);
+        if (tid == 0) {
+            const bool complete = (L.ptr[row_lo] >= t0) && (L.ptr[row_lo + 1] <= t1);
+            if (complete) {
+                out1[row_lo] = v1;
+                if constexpr (DUAL) out2[row_lo] = v2;
+            } else {
+                carry1[2 * tile] = v1;
+                if constexpr (DUAL) carry2[2 * tile] = v2;
+            }
+        }
+        return;
+    }
+
+    if (nrows * 8 >= nit) {
+        // short rows: one thread per row, sequential (deterministic) sum
+        for (int r = row_lo + tid; r <= row_hi; r += kBlock) {
+            const int pa = L.ptr[r], pb = L.ptr[r + 1];
+            const int a = max(pa, t0) - t0, b = min(pb, t1) - t0;
+            double v1 = 0.0, v2 = 0.0;
+            for (int k = a; k < b; ++k) {
+                v1 += sp1[k];
+                if constexpr (DUAL) v2 += sp2[k];
+            }
+            if (pa >= t0 && pb <= t1) {
+                out1[r] = v1;
+                if constexpr (DUAL) out2[r] = v2;
+            } else {
+                const int slot = (r == row_lo) ? 2 * tile : 2 * tile + 1;
+                carry1[slot] = v1;
+                if constexpr (DUAL) carry2[slot] = v2;
+            }
+        }
+    } else {
+        // longer rows: one warp per row
+        const int w = tid >> 5, lane = tid & 31;
+        for (int r = row_lo + w; r <= row_hi; r += kBlock / 32) {
+            const int pa = L.ptr[r], pb = L.ptr[r + 1];
+            const int a = max(pa, t0) - t0, b = min(pb, t1) - t0;
+            double v1 = 0.0, v2 = 0.0;
+            for (int k = a + lane; k < b; k += 32) {
+                v1 += sp1[k];
+                if constexpr (DUAL) v2 += sp2[k];
+            }
+            v1 = warp_sum(v1);
+            if constexpr (DUAL) v2 = warp_sum(v2);
+            if (lane == 0) {
+                if (pa >= t0 && pb <= t1) {
+                    out1[r] = v1;
+                    if constexpr (DUAL) out2[r] = v2;
+                } else {
+                    const int slot = (r == row_lo) ? 2 * tile : 2 * tile + 1;
+                    carry1[slot] = v1;
+                    if constexpr (DUAL) carry2[slot] = v2;
+                }
+            }
+        }
+    }
+}
+
+// rows split over several tiles: out[row] = sum of their tile partials, one warp per row, fixed order
+__global__ void __launch_bounds__(kBlock) auv_fixup_kernel(ItemListDev L, const double *__restrict__ carry1,
+                                                           const double *__restrict__ carry2,
+                                                           double *__restrict__ out1, double *__restrict__ out2) {
+    const int w = (blockIdx.x * kBlock + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= L.n_split) return;
+    const int row = L.split_row[w], fs = L.split_first_slot[w], ta = L.split_tile_a[w], tb = L.split_tile_b[w];
+    const int ne = tb - ta + 1;
+    double v1 = 0.0, v2 = 0.0;
+    for (int e = lane; e < ne; e += 32) {
+        const int slot = (e == 0) ? fs : 2 * (ta + e);
+        v1 += carry1[slot];
+        if (carry2) v2 += carry2[slot];
+    }
+    v1 = warp_sum(v1);
+    v2 = warp_sum(v2);
+    if (lane == 0) {
+        out1[row] = v1;
+        if (carry2) out2[row] = v2;
+    }
+}
+
+template <int MODE>
+static void launch_auv_mode(Ctx &c, const ItemListDev &L, const double *U, const double *V, int ld, double s1,
+                            double s2, double *o1, double *o2, double *c1, double *c2) {
+    const int grid = (int)L.n_tiles;
+    if (MODE == AUV_FROMZ) {
+        auv_items_kernel<MODE, 4><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, c1, c2);
+    } else if (ld <= 32) {
+        auv_items_kernel<MODE, 4><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, c1, c2);
+    } else if (ld <= 64) {
+        auv_items_kernel<MODE, 8><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, c1, c2);
+    } else if (ld <= 128) {
+        auv_items_kernel<MODE, 16><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, c1, c2);
+    } else {
+        auv_items_kernel<MODE, 32><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, c1, c2);
+    }
+    LB2_LAUNCH_CHECK(c);
+}
+
+void launch_auv(Ctx &c, AuvMode mode, const ItemListDev &L, const double *U, const double *V, int ld, double scale1,
+                double scale2, double *out1, double *out2, double *carry1, double *carry2) {
+    if (L.has_empty_rows) {
+        LB2_CUDA(cudaMemsetAsync(out1, 0, sizeof(double) * L.n_rows, c.stream));
+        if (mode == AUV_DUAL) LB2_CUDA(cudaMemsetAsync(out2, 0, sizeof(double) * L.n_rows, c.stream));
+    }
+    if (L.n_items == 0) return;
+    switch (mode) {
+    case AUV_SAME: launch_auv_mode<AUV_SAME>(c, L, U, V, ld, scale1, scale2, out1, out2, carry1, carry2); break;
+    case AUV_PAIR: launch_auv_mode<AUV_PAIR>(c, L, U, V, ld, scale1, scale2, out1, out2, carry1, carry2); break;
+    case AUV_DUAL: launch_auv_mode<AUV_DUAL>(c, L, U, V, ld, scale1, scale2, out1, out2, carry1, carry2); break;
+    case AUV_FROMZ: launch_auv_mode<AUV_FROMZ>(c, L, U, V, ld, scale1, scale2, out1, out2, carry1, carry2); break;
+    }
+    if (L.n_split > 0) {
+        const int grid = (int)((L.n_split * 32 + kBlock - 1) / kBlock);
+        auv_fixup_kernel<<<grid, kBlock, 0, c.stream>>>(L, carry1, mode == AUV_DUAL ? carry2 : nullptr, out1, out2);
+        LB2_LAUNCH_CHECK(c);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) scatter_add_kernel(double *__restrict__ dst, const double *__restrict__ src,
+                                                             const int *__restrict__ idx, long long n, double alpha,
+                                                             bool accumulate, double *obj_dst) {
+    for (long long a = blockIdx.x * (long long)kBlock + threadIdx.x; a < n; a += (long long)gridDim.x * kBlock) {
+        const long long d = idx ? idx[a] : a;
+        const double v = alpha * src[a];
+        dst[d] = accumulate ? dst[d] + v : v;
+    }
+    if (obj_dst && blockIdx.x == 0 && threadIdx.x == 0) *obj_dst += alpha * src[n];
+}
+
+void launch_scatter_add(Ctx &c, double *dst, const double *src, const int *idx, long long n, double alpha,
+                        bool accumulate, double *obj_dst) {
+    scatter_add_kernel<<<grid_for(n, 4, c), kBlock, 0, c.stream>>>(dst, src, idx, n, alpha, accumulate, obj_dst);
+    LB2_LAUNCH_CHECK(c);
+}
+
+// =================================================================================================
+// S = C + A^*(w) on the pattern ; Y = S X
+// =================================================================================================
+__global__ void __launch_bounds__(kBlock) wsum_kernel(double *__restrict__ S, long long np,
+                                                      const double *__restrict__ C_onP, const int *__restrict__ T_ptr,
+                                                      const int *__restrict__ T_con, const double *__restrict__ T_val,
+                                                      const double *__restrict__ w, const int *__restrict__ act_idx,
+                                                      bool addC) {
+    for (long long p = blockIdx.x * (long long)kBlock + threadIdx.x; p < np; p += (long long)gridDim.x * kBlock) {
+        double s = addC ? C_onP[p] : 0.0;
+        const int a = T_ptr[p], b = T_ptr[p + 1];
+        for (int k = a; k < b; ++k) {
+            const int cidx = act_idx ? act_idx[T_con[k]] : T_con[k];
+            s += w[cidx] * T_val[k];
+        }
+        S[p] = s;
+    }
+}
+
+void launch_wsum(Ctx &c, double *S, long long np, const double *C_onP, const int *T_ptr, const int *T_con,
+                 const double *T_val, const double *w, const int *act_idx, bool w_is_compact, bool addC) {
+    if (np == 0) return;
+    wsum_kernel<<<grid_for(np, 2, c), kBlock, 0, c.stream>>>(S, np, C_onP, T_ptr, T_con, T_val, w,
+                                                             w_is_compact ? nullptr : act_idx, addC);
+    LB2_LAUNCH_CHECK(c);
+}
+
+template <int G, int NP>
+__global__ void __launch_bounds__(kBlock) spmm_sym_kernel(long long n, int ld, const int *__restrict__ adj_ptr,
+                                                          const int *__restrict__ adj_col,
+                                                          const int *__restrict__ adj_pos, const double *__restrict__ S,
+                                                          const double *__restrict__ X, double a, double b,
+                                                          const double *__restrict__ Z, const double *__restrict__ Z2,
+                                                          double *__restrict__ Y, ReduceScratch rs, double *red) {
+    constexpr int NG = kBlock / G;
+    const int g = threadIdx.x / G, gl = threadIdx.x % G;
+    double ryy = 0.0, ryz = 0.0;
+    for (long long i = (long long)blockIdx.x * NG + g; i < n; i += (long long)gridDim.x * NG) {
+        double2 acc[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) acc[q] = make_double2(0.0, 0.0);
+        const int ea = adj_ptr[i], eb = adj_ptr[i + 1];
+        int e = ea;
+        for (; e + 1 < eb; e += 2) {   // two neighbours in flight
+            const int j0 = adj_col[e], j1 = adj_col[e + 1];
+            const double s0 = S[adj_pos[e]], s1 = S[adj_pos[e + 1]];
+            const double *x0 = X + (size_t)j0 * ld, *x1 = X + (size_t)j1 * ld;
+            double2 v0[NP], v1[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int col = 2 * gl + 2 * G * q;
+                if (col < ld) { v0[q] = ld2(x0 + col); v1[q] = ld2(x1 + col); }
+                else { v0[q] = make_double2(0.0, 0.0); v1[q] = v0[q]; }
+            }
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                acc[q].x = fma(s0, v0[q].x, acc[q].x); acc[q].y = fma(s0, v0[q].y, acc[q].y);
+                acc[q].x = fma(s1, v1[q].x, acc[q].x); acc[q].y = fma(s1, v1[q].y, acc[q].y);
+            }
+        }
+        if (e < eb) {
+            const int j0 = adj_col[e];
+            const double s0 = S[adj_pos[e]];
+            const double *x0 = X + (size_t)j0 * ld;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int col = 2 * gl + 2 * G * q;
+                if (col < ld) {
+                    double2 v = ld2(x0 + col);
+                    acc[q].x = fma(s0, v.x, acc[q].x); acc[q].y = fma(s0, v.y, acc[q].y);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int col = 2 * gl + 2 * G * q;
+            if (col < ld) {
+                double2 y = make_double2(a * acc[q].x, a * acc[q].y);
+                if (Z) {
+                    double2 z = ld2(Z + (size_t)i * ld + col);
+                    y.x = fma(b, z.x, y.x); y.y = fma(b, z.y, y.y);
+                }
+                st2(Y + (size_t)i * ld + col, y);
+                ryy = fma(y.x, y.x, ryy); ryy = fma(y.y, y.y, ryy);
+                if (Z2) {
+                    double2 z2 = ld2(Z2 + (size_t)i * ld + col);
+                    ryz = fma(y.x, z2.x, ryz); ryz = fma(y.y, z2.y, ryz);
+                }
+            }
+        }
+    }
+    if (red) {
+        double v[2] = {ryy, ryz};
+        if (grid_reduce<2>(v, rs) && threadIdx.x == 0) { red[0] = v[0]; red[1] = v[1]; }
+    }
+}
+
+template <int G>
+static void launch_spmm_g(Ctx &c, int np, long long n, int ld, const int *ap, const int *ac, const int *apos,
+                          const double *S, const double *X, double a, double b, const double *Z, const double *Z2,
+                          double *Y, double *red) {
+    constexpr int NG = kBlock / G;
+    long long blocks = (n + NG - 1) / NG;
+    long long cap = (long long)c.num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    const int grid = (int)blocks;
+    switch (np) {
+    case 1: spmm_sym_kernel<G, 1><<<grid, kBlock, 0, c.stream>>>(n, ld, ap, ac, apos, S, X, a, b, Z, Z2, Y, c.rs, red); break;
+    case 2: spmm_sym_kernel<G, 2><<<grid, kBlock, 0, c.stream>>>(n, ld, ap, ac, apos, S, X, a, b, Z, Z2, Y, c.rs, red); break;
+    case 3: spmm_sym_kernel<G, 3><<<grid, kBlock, 0, c.stream>>>(n, ld, ap, ac, apos, S, X, a, b, Z, Z2, Y, c.rs, red); break;
+    default: spmm_sym_kernel<G, 4><<<grid, kBlock, 0, c.stream>>>(n, ld, ap, ac, apos, S, X, a, b, Z, Z2, Y, c.rs, red); break;
+    }
+    LB2_LAUNCH_CHECK(c);
+}
+
+void launch_spmm(Ctx &c, long long n, int ld, const int *adj_ptr, const int *adj_col, const int *adj_pos,
+                 const double *S, const double *X, double a, double b, const double *Z, const double *Z2, double *Y,
+                 double *red) {
+    if (ld > 256) throw std::runtime_error("rank above 256 is not supported by the SpMM kernel yet");
+    int G = ld <= 32 ? 4 : (ld <= 64 ? 8 : (ld <= 128 ? 16 : 32));
+    int np = (ld + 2 * G - 1) / (2 * G);
+    switch (G) {
+    case 4: launch_spmm_g<4>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red); break;
+    case 8: launch_spmm_g<8>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red); break;
+    case 16: launch_spmm_g<16>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red); break;
+    default: launch_spmm_g<32>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red); break;
+    }
+}
+
+// =================================================================================================
+// dense path (straightforward shared-memory tiled FP64 kernels; see DESIGN.md for the DMMA plan)
+// =================================================================================================
+constexpr int kDT = 32;   // tile edge
+
+__device__ __forceinline__ long long packed_col_start(long long n, long long j) { return j * n - j * (j - 1) / 2; }
+
+// One CTA per lower tile (bi >= bj): Z[i,j] = (U_i.V_j + U_j.V_i)/2 ; optional second output D_i.D_j
+template <bool SAME, bool DUAL>
+__global__ void __launch_bounds__(kBlock) dense_uvt_kernel(long long n, int r, int ld, const double *__restrict__ U,
+                                                           const double *__restrict__ V, double *__restrict__ Z1,
+                                                           double *__restrict__ Z2, int nb) {
+    // linear tile id -> (bi, bj) with bi >= bj
+    long long t = blockIdx.x;
+    int bi = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) / 2.0);
+    while ((long long)(bi + 1) * (bi + 2) / 2 <= t) ++bi;
+    while ((long long)bi * (bi + 1) / 2 > t) --bi;
+    const int bj = (int)(t - (long long)bi * (bi + 1) / 2);
+    extern __shared__ double sm[];
+    const int lds = ld + 1;
+    double *Ui = sm, *Uj = Ui + kDT * lds, *Vi = Uj + kDT * lds, *Vj = Vi + kDT * lds;
+    const long long i0 = (long long)bi * kDT, j0 = (long long)bj * kDT;
+    for (int q = threadIdx.x; q < kDT * ld; q += kBlock) {
+        const int rr = q / ld, cc = q % ld;
+        const long long gi = i0 + rr, gj = j0 + rr;
+        Ui[rr * lds + cc] = gi < n ? U[gi * ld + cc] : 0.0;
+        Uj[rr * lds + cc] = gj < n ? U[gj * ld + cc] : 0.0;
+        if (!SAME) {
+            Vi[rr * lds + cc] = gi < n ? V[gi * ld + cc] : 0.0;
+            Vj[rr * lds + cc] = gj < n ? V[gj * ld + cc] : 0.0;
+        }
+    }
+    __syncthreads();
+    // thread -> 4 entries of the 32x32 tile; consecutive threads walk i (contiguous in packed storage)
+    const int li = threadIdx.x % kDT;
+    for (int q = 0; q < kDT * kDT / kBlock; ++q) {
+        const int lj = threadIdx.x / kDT + q * (kBlock / kDT);
+        const long long gi = i0 + li, gj = j0 + lj;
+        if (gi >= n || gj >= n || gi < gj) continue;
+        double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if (SAME) {
+            for (int k = 0; k < r; ++k) a1 = fma(Ui[li * lds + k], Uj[lj * lds + k], a1);
+            Z1[packed_col_start(n, gj) + (gi - gj)] = a1;
+        } else {
+            for (int k = 0; k < r; ++k) {
+                a1 = fma(Ui[li * lds + k], Vj[lj * lds + k], a1);
+                a2 = fma(Uj[lj * lds + k], Vi[li * lds + k], a2);
+                if (DUAL) a3 = fma(Vi[li * lds + k], Vj[lj * lds + k], a3);
+            }
+            const long long pos = packed_col_start(n, gj) + (gi - gj);
+            Z1[pos] = (gi == gj) ? a1 : (0.5 * a1 + 0.5 * a2);
+            if (DUAL) Z2[pos] = a3;
+        }
+    }
+}
+
+void launch_dense_uvt(Ctx &c, long long n, int r, int ld, const double *U, const double *V, double *Zp, bool same) {
+    const int nb = (int)((n + kDT - 1) / kDT);
+    const long long tiles = (long long)nb * (nb + 1) / 2;
+    const size_t smem = sizeof(double) * 4 * kDT * (ld + 1);
+    if (same) {
+        LB2_CUDA(cudaFuncSetAttribute(dense_uvt_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dense_uvt_kernel<true, false><<<(unsigned)tiles, kBlock, smem, c.stream>>>(n, r, ld, U, V, Zp, nullptr, nb);
+    } else {
+        LB2_CUDA(cudaFuncSetAttribute(dense_uvt_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dense_uvt_kernel<false, false><<<(unsigned)tiles, kBlock, smem, c.stream>>>(n, r, ld, U, V, Zp, nullptr, nb);
+    }
+    LB2_LAUNCH_CHECK(c);
+}
+
+void launch_dense_uvt_dual(Ctx &c, long long n, int r, int ld, const double *R, const double *D, double *Z1, double *Z2) {
+    const int nb = (int)((n + kDT - 1) / kDT);
+    const long long tiles = (long long)nb * (nb + 1) / 2;
+    const size_t smem = sizeof(double) * 4 * kDT * (ld + 1);
+    LB2_CUDA(cudaFuncSetAttribute(dense_uvt_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dense_uvt_kernel<false, true><<<(unsigned)tiles, kBlock, smem, c.stream>>>(n, r, ld, R, D, Z1, Z2, nb);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) dense_wsum_kernel(double *__restrict__ Sp, const long long *__restrict__ D_pos,
+                                                            long long n_pos, const int *__restrict__ T_ptr,
+                                                            const int *__restrict__ T_con, const double *__restrict__ T_val,
+                                                            const double *__restrict__ w, const int *__restrict__ act_idx) {
+    for (long long u = blockIdx.x * (long long)kBlock + threadIdx.x; u < n_pos; u += (long long)gridDim.x * kBlock) {
+        double s = Sp[D_pos[u]];
+        for (int k = T_ptr[u]; k < T_ptr[u + 1]; ++k) {
+            const int cidx = act_idx ? act_idx[T_con[k]] : T_con[k];
+            s += w[cidx] * T_val[k];
+        }
+        Sp[D_pos[u]] = s;
+    }
+}
+
+void launch_dense_wsum(Ctx &c, double *Sp, long long psize, const double *Cp, const long long *D_pos, long long n_pos,
+                       const int *T_ptr, const int *T_con, const double *T_val, const double *w, const int *act_idx,
+                       bool w_is_compact, bool addC) {
+    if (addC) LB2_CUDA(cudaMemcpyAsync(Sp, Cp, sizeof(double) * psize, cudaMemcpyDeviceToDevice, c.stream));
+    else LB2_CUDA(cudaMemsetAsync(Sp, 0, sizeof(double) * psize, c.stream));
+    if (n_pos == 0) return;
+    dense_wsum_kernel<<<grid_for(n_pos, 1, c), kBlock, 0, c.stream>>>(Sp, D_pos, n_pos, T_ptr, T_con, T_val, w,
+                                                                      w_is_compact ? nullptr : act_idx);
+    LB2_LAUNCH_CHECK(c);
+}
+
+// Y[I,:] = a * sum_J S[I,J] X[J,:] + b Z[I,:], S symmetric packed lower column-major. One CTA per row block I.
+__global__ void __launch_bounds__(kBlock) dense_symm_kernel(long long n, int r, int ld, const double *__restrict__ Sp,
+                                                            const double *__restrict__ X, double a, double b,
+                                                            const double *__restrict__ Z, const double *__restrict__ Z2,
+                                                            double *__restrict__ Y, ReduceScratch rs, double *red) {
+    extern __shared__ double sm[];
+    double *St = sm;                       // kDT x (kDT+1): St[li][lj] = S[i0+li][j0+lj]
+    double *Xt = sm + kDT * (kDT + 1);     // kDT x ld
+    const long long i0 = (long long)blockIdx.x * kDT;
+    const int nb = (int)((n + kDT - 1) / kDT);
+    // thread -> (row li, column chunk); kBlock/kDT = 8 threads per row, each owns columns cq, cq+8, ...
+    const int li = threadIdx.x / 8, cq = threadIdx.x % 8;
+    constexpr int MAXC = 32;               // supports ld <= 256
+    double acc[MAXC];
+#pragma unroll
+    for (int q = 0; q < MAXC; ++q) acc[q] = 0.0;
+    for (int bj = 0; bj < nb; ++bj) {
+        const long long j0 = (long long)bj * kDT;
+        __syncthreads();
+        for (int q = threadIdx.x; q < kDT * kDT; q += kBlock) {
+            int x = q % kDT, y = q / kDT;
+            double v = 0.0;
+            if (j0 < i0 || (j0 == i0)) {
+                // lower (or diagonal) tile: rows i (fast index x), column j = j0 + y
+                const long long gi = i0 + x, gj = j0 + y;
+                if (gi < n && gj < n) {
+                    if (gi >= gj) v = Sp[packed_col_start(n, gj) + (gi - gj)];
+                    else v = Sp[packed_col_start(n, gi) + (gj - gi)];
+                }
+                St[x * (kDT + 1) + y] = v;
+            } else {
+                // upper tile: S[i][j] = lower(j, i): column i = i0 + y, rows j (fast index x)
+                const long long gi = i0 + y, gj = j0 + x;
+                if (gi < n && gj < n) v = Sp[packed_col_start(n, gi) + (gj - gi)];
+                St[y * (kDT + 1) + x] = v;
+            }
+        }
+        for (int q = threadIdx.x; q < kDT * ld; q += kBlock) {
+            const int rr = q / ld, cc = q % ld;
+            Xt[rr * ld + cc] = (j0 + rr) < n ? X[(j0 + rr) * ld + cc] : 0.0;
+        }
+        __syncthreads();
+        for (int lj = 0; lj < kDT; ++lj) {
+            const double s = St[li * (kDT + 1) + lj];
+#pragma unroll
+            for (int q = 0; q < MAXC; ++q) {
+                const int col = cq + 8 * q;
+                if (col < ld) acc[q] = fma(s, Xt[lj * ld + col], acc[q]);
+            }
+        }
+    }
+    double ryy = 0.0, ryz = 0.0;
+    const long long gi = i0 + li;
+    if (gi < n) {
+#pragma unroll
+        for (int q = 0; q < MAXC; ++q) {
+            const int col = cq + 8 * q;
+            if (col < ld) {
+                double y = a * acc[q];
+                if (Z) y = fma(b, Z[gi * ld + col], y);
+                if (col >= r) y = 0.0;
+                Y[gi * ld + col] = y;
+                ryy = fma(y, y, ryy);
+                if (Z2) ryz = fma(y, Z2[gi * ld + col], ryz);
+            }
+        }
+    }
+    if (red) {
+        double v[2] = {ryy, ryz};
+        if (grid_reduce<2>(v, rs) && threadIdx.x == 0) { red[0] = v[0]; red[1] = v[1]; }
+    }
+}
+
+void launch_dense_symm(Ctx &c, long long n, int r, int ld, const double *Sp, const double *X, double a, double b,
+                       const double *Z, const double *Z2, double *Y, double *red) {
+    if (ld > 256) throw std::runtime_error("rank above 256 is not supported by the dense symm kernel yet");
+    const int nb = (int)((n + kDT - 1) / kDT);
+    const size_t smem = sizeof(double) * (kDT * (kDT + 1) + kDT * ld);
+    LB2_CUDA(cudaFuncSetAttribute(dense_symm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dense_symm_kernel<<<nb, kBlock, smem, c.stream>>>(n, r, ld, Sp, X, a, b, Z, Z2, Y, c.rs, red);
+    LB2_LAUNCH_CHECK(c);
+}
+
+// =================================================================================================
+// fused BLAS-1
+// =================================================================================================
+__device__ __forceinline__ double eval_coef(const Coef &k, double *S) {
+    double v = k.k0 * S[k.i0];
+    if (k.k1 != 0.0) v = fma(k.k1 * S[k.i1], S[k.i2], v);
+    return v;
+}
+
+__global__ void scalar_prologue_kernel(Coef ca, Coef cb, double *S) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (ca.store >= 0) S[ca.store] = eval_coef(ca, S);
+        if (cb.store >= 0) S[cb.store] = eval_coef(cb, S);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) axpby_dot2_kernel(long long n, double *out, Coef ca, const double *x, Coef cb,
+                                                            const double *y, const double *z, double *S, int dot_slot,
+                                                            bool recip, ReduceScratch rs) {
+    const double a = eval_coef(ca, S), b = eval_coef(cb, S);
+    double acc = 0.0;
+    const long long n2 = n >> 1;
+    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n2; q += (long long)gridDim.x * kBlock) {
+        double2 xv = ld2(x + 2 * q);
+        double2 o = make_double2(a * xv.x, a * xv.y);
+        if (y) {
+            double2 yv = ld2(y + 2 * q);
+            o.x = fma(b, yv.x, o.x); o.y = fma(b, yv.y, o.y);
+        }
+        st2(out + 2 * q, o);
+        if (z) {
+            double2 zv = (z == out) ? o : ld2(z + 2 * q);
+            acc = fma(o.x, zv.x, acc); acc = fma(o.y, zv.y, acc);
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        double o = a * x[n - 1];
+        if (y) o = fma(b, y[n - 1], o);
+        out[n - 1] = o;
+        if (z) acc = fma(o, (z == out) ? o : z[n - 1], acc);
+    }
+    if (z) {
+        double v[1] = {acc};
+        if (grid_reduce<1>(v, rs) && threadIdx.x == 0) S[dot_slot] = recip ? 1.0 / v[0] : v[0];
+    }
+}
+
+void launch_axpby_dot(Ctx &c, long long n, double *out, Coef a, const double *x, Coef b, const double *y,
+                      const double *z, double *S, int dot_slot, bool recip) {
+    if (a.store >= 0 || b.store >= 0) {
+        // remembered coefficients are written by a one-thread kernel that runs before (same stream), and the
+        // main kernel then reads them back from their slots -> no intra-kernel race on S
+        scalar_prologue_kernel<<<1, 32, 0, c.stream>>>(a, b, S);
+        LB2_LAUNCH_CHECK(c);
+        if (a.store >= 0) a = coef_slot(a.store);
+        if (b.store >= 0) b = coef_slot(b.store);
+    }
+    axpby_dot2_kernel<<<grid_for(n, 8, c), kBlock, 0, c.stream>>>(n, out, a, x, b, y, z, S, dot_slot, recip, c.rs);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) dot_kernel(long long n, const double *__restrict__ x,
+                                                     const double *__restrict__ y, double *S, int slot, bool absx,
+                                                     ReduceScratch rs) {
+    double acc = 0.0;
+    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n; q += (long long)gridDim.x * kBlock)
+        acc += absx ? fabs(x[q]) : x[q] * y[q];
+    double v[1] = {acc};
+    if (grid_reduce<1>(v, rs) && threadIdx.x == 0) S[slot] = v[0];
+}
+
+void launch_dot(Ctx &c, long long n, const double *x, const double *y, double *S, int slot) {
+    dot_kernel<<<grid_for(n, 8, c), kBlock, 0, c.stream>>>(n, x, y, S, slot, false, c.rs);
+    LB2_LAUNCH_CHECK(c);
+}
+
+void launch_asum(Ctx &c, long long n, const double *x, double *S, int slot) {
+    dot_kernel<<<grid_for(n, 8, c), kBlock, 0, c.stream>>>(n, x, x, S, slot, true, c.rs);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) neg_if_nonneg_kernel(long long n, double *__restrict__ D,
+                                                               const double *__restrict__ G, const double *S, int slot) {
+    if (!(S[slot] >= 0.0)) return;
+    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n; q += (long long)gridDim.x * kBlock)
+        D[q] = -G[q];
+}
+
+void launch_neg_if_nonneg(Ctx &c, long long n, double *D, const double *G, const double *S, int cond_slot) {
+    neg_if_nonneg_kernel<<<grid_for(n, 4, c), kBlock, 0, c.stream>>>(n, D, G, S, cond_slot);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) alm_step_kernel(long long n, double tau, const double *__restrict__ G,
+                                                          const double *__restrict__ D, double *__restrict__ R,
+                                                          double *__restrict__ y, double *__restrict__ s) {
+    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n; q += (long long)gridDim.x * kBlock) {
+        const double d = D[q];
+        y[q] = -G[q];
+        s[q] = tau * d;
+        R[q] = fma(tau, d, R[q]);
+    }
+}
+
+void launch_alm_step(Ctx &c, long long n, double tau, const double *G, const double *D, double *R, double *y, double *s) {
+    alm_step_kernel<<<grid_for(n, 4, c), kBlock, 0, c.stream>>>(n, tau, G, D, R, y, s);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) cg_update_kernel(long long n, double *__restrict__ x, double *__restrict__ r,
+                                                           const double *__restrict__ p, const double *__restrict__ Q,
+                                                           double *S, int slot_num, int slot_den, int slot_rr,
+                                                           ReduceScratch rs) {
+    const double alpha = S[slot_num] / S[slot_den];
+    double acc = 0.0;
+    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n; q += (long long)gridDim.x * kBlock) {
+        x[q] = fma(alpha, p[q], x[q]);
+        const double rv = fma(-alpha, Q[q], r[q]);
+        r[q] = rv;
+        acc = fma(rv, rv, acc);
+    }
+    double v[1] = {acc};
+    if (grid_reduce<1>(v, rs) && threadIdx.x == 0) S[slot_rr] = v[0];
+}
+
+void launch_cg_update(Ctx &c, long long n, double *x, double *r, const double *p, const double *Q, double *S,
+                      int slot_num, int slot_den, int slot_rr) {
+    cg_update_kernel<<<grid_for(n, 8, c), kBlock, 0, c.stream>>>(n, x, r, p, Q, S, slot_num, slot_den, slot_rr, c.rs);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) linesearch_dots_kernel(long long m, const double *__restrict__ b,
+                                                                 const double *__restrict__ s,
+                                                                 const double *__restrict__ lam, double rhoInv,
+                                                                 const double *__restrict__ q1,
+                                                                 const double *__restrict__ q2, double *S, int slot,
+                                                                 ReduceScratch rs) {
+    double v[5] = {0, 0, 0, 0, 0};
+    for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < m; i += (long long)gridDim.x * kBlock) {
+        const double q0 = fma(rhoInv, lam[i], b[i] - s[i]);
+        const double a = q1[i], c2 = q2[i];
+        v[0] = fma(c2, c2, v[0]);
+        v[1] = fma(a, c2, v[1]);
+        v[2] = fma(q0, c2, v[2]);
+        v[3] = fma(a, a, v[3]);
+        v[4] = fma(q0, a, v[4]);
+    }
+    if (grid_reduce<5>(v, rs) && threadIdx.x == 0)
+        for (int k = 0; k < 5; ++k) S[slot + k] = v[k];
+}
+
+void launch_linesearch_dots(Ctx &c, long long m, const double *b, const double *s, const double *lam, double rho,
+                            const double *q1, const double *q2, double *S, int slot) {
+    linesearch_dots_kernel<<<grid_for(m, 4, c), kBlock, 0, c.stream>>>(m, b, s, lam, 1.0 / rho, q1, q2, S, slot, c.rs);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) alm_m_update_kernel(long long m, double tau, const double *__restrict__ q1,
+                                                              const double *__restrict__ q2, double *__restrict__ s,
+                                                              const double *__restrict__ lam,
+                                                              const double *__restrict__ b, double rho,
+                                                              double *__restrict__ M1) {
+    const double t2 = tau * tau;
+    for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < m; i += (long long)gridDim.x * kBlock) {
+        double sv = s[i];
+        if (q1) {
+            sv = fma(tau, q1[i], sv);
+            sv = fma(t2, q2[i], sv);
+            s[i] = sv;
+        }
+        M1[i] = fma(rho, sv, fma(-rho, b[i], -lam[i]));
+    }
+}
+
+void launch_alm_m_update(Ctx &c, long long m, double tau, const double *q1, const double *q2, double *s,
+                         const double *lam, const double *b, double rho, double *M1) {
+    alm_m_update_kernel<<<grid_for(m, 4, c), kBlock, 0, c.stream>>>(m, tau, q1, q2, s, lam, b, rho, M1);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) resid_sq_kernel(long long m, const double *__restrict__ b,
+                                                          const double *__restrict__ s, double *S, int slot,
+                                                          ReduceScratch rs) {
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < m; i += (long long)gridDim.x * kBlock) {
+        const double d = b[i] - s[i];
+        acc = fma(d, d, acc);
+    }
+    double v[1] = {acc};
+    if (grid_reduce<1>(v, rs) && threadIdx.x == 0) S[slot] = v[0];
+}
+
+void launch_resid_sq(Ctx &c, long long m, const double *b, const double *s, double *S, int slot) {
+    resid_sq_kernel<<<grid_for(m, 4, c), kBlock, 0, c.stream>>>(m, b, s, S, slot, c.rs);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) dual_update_kernel(long long m, double rho, const double *__restrict__ b,
+                                                             const double *__restrict__ s, double *__restrict__ lam) {
+    for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < m; i += (long long)gridDim.x * kBlock)
+        lam[i] = fma(-rho, s[i], fma(rho, b[i], lam[i]));
+}
+
+void launch_dual_update(Ctx &c, long long m, double rho, const double *b, const double *s, double *lam) {
+    dual_update_kernel<<<grid_for(m, 4, c), kBlock, 0, c.stream>>>(m, rho, b, s, lam);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) admm_m1_kernel(long long m, const double *__restrict__ b,
+                                                         const double *__restrict__ s, const double *__restrict__ cv,
+                                                         const double *__restrict__ lam, double rho,
+                                                         double *__restrict__ M1) {
+    for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < m; i += (long long)gridDim.x * kBlock) {
+        double t = s[i] - b[i];
+        if (cv) t -= cv[i];
+        M1[i] = fma(t, rho, -lam[i]);
+    }
+}
+
+void launch_admm_m1(Ctx &c, long long m, const double *b, const double *s, const double *cv, const double *lam,
+                    double rho, double *M1) {
+    admm_m1_kernel<<<grid_for(m, 4, c), kBlock, 0, c.stream>>>(m, b, s, cv, lam, rho, M1);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void recip_kernel(double *S, int slot) { S[slot] = 1.0 / S[slot]; }
+
+void launch_recip(Ctx &c, double *S, int slot) {
+    recip_kernel<<<1, 1, 0, c.stream>>>(S, slot);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void set_scalar_kernel(double *S, int slot, double v) { S[slot] = v; }
+
+void launch_set_scalar(Ctx &c, double *S, int slot, double v) {
+    set_scalar_kernel<<<1, 1, 0, c.stream>>>(S, slot, v);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) fill_kernel(double *__restrict__ x, long long n, double v) {
+    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n; q += (long long)gridDim.x * kBlock) x[q] = v;
+}
+
+__global__ void __launch_bounds__(kBlock) scale_kernel(double *__restrict__ x, long long n, double f) {
+    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n; q += (long long)gridDim.x * kBlock) x[q] *= f;
+}
+
+void launch_scale(Ctx &c, double *x, long long n, double f) {
+    if (n <= 0) return;
+    scale_kernel<<<grid_for(n, 4, c), kBlock, 0, c.stream>>>(x, n, f);
+    LB2_LAUNCH_CHECK(c);
+}
+
+void launch_fill(Ctx &c, double *x, long long n, double v) {
+    fill_kernel<<<grid_for(n, 4, c), kBlock, 0, c.stream>>>(x, n, v);
+    LB2_LAUNCH_CHECK(c);
+}
+
+}  // namespace lb2

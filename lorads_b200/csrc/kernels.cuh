@@ -1,0 +1,118 @@
+// kernels.cuh -- launch interface of the hand-written sm_100a kernels (definitions in kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace lb2 {
+
+// Launch context: one stream, one reduction scratch, a launch counter (reported as gpu_launches).
+struct Ctx {
+    cudaStream_t stream = nullptr;
+    ReduceScratch rs{nullptr, nullptr};
+    int num_sms = 148;
+    long long launches = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// A(UV^T): items = non-zeros of [A_1..A_m ; C] sorted by constraint (layout.hpp ItemList)
+// ------------------------------------------------------------------------------------------------
+struct ItemListDev {
+    long long n_items = 0, n_rows = 0, n_tiles = 0, n_split = 0;
+    const int *ptr = nullptr, *irow = nullptr, *icol = nullptr;
+    const double *coef = nullptr;
+    const int *split_row = nullptr, *split_first_slot = nullptr, *split_tile_a = nullptr, *split_tile_b = nullptr;
+    bool has_empty_rows = false;
+};
+
+enum AuvMode {
+    AUV_SAME = 0,   // U == V            : z = U_i . U_j
+    AUV_PAIR = 1,   // U != V            : z = (U_i.V_j + U_j.V_i)/2
+    AUV_DUAL = 2,   // (R,D) and (D,D)   : z1 = (R_i.D_j + R_j.D_i)/2 , z2 = D_i.D_j  (one gather pass)
+    AUV_FROMZ = 3   // dense path        : z is materialised (packed), item.irow is the packed position
+};
+
+// out1/out2: n_rows values each; carry: 2*n_tiles doubles per output.  U,V row-major n x ld (ld % 4 == 0).
+void launch_auv(Ctx &c, AuvMode mode, const ItemListDev &L, const double *U, const double *V, int ld,
+                double scale1, double scale2, double *out1, double *out2, double *carry1, double *carry2);
+
+// dst[idx ? idx[a] : a] (+)= alpha * src[a]  for a < n ; when obj_dst != nullptr: *obj_dst += alpha*src[n]
+void launch_scatter_add(Ctx &c, double *dst, const double *src, const int *idx, long long n, double alpha,
+                        bool accumulate, double *obj_dst);
+
+// ------------------------------------------------------------------------------------------------
+// (C + A^*(w)) X : weighted sum on the pattern, then symmetric SpMM in gather form
+// ------------------------------------------------------------------------------------------------
+// S[p] = (addC ? C_onP[p] : 0) + sum_k w[map(T_con[k])] * T_val[k],  map = act_idx unless w is compact
+void launch_wsum(Ctx &c, double *S, long long np, const double *C_onP, const int *T_ptr, const int *T_con,
+                 const double *T_val, const double *w, const int *act_idx, bool w_is_compact, bool addC);
+
+// Y[i,:] = a * sum_{e in adj(i)} S[adj_pos[e]] * X[adj_col[e],:] + b * Z[i,:]   (Z may be null)
+// red[0] = sum Y.Y, red[1] = sum Y.Z2 (Z2 may be null) when red != nullptr.
+void launch_spmm(Ctx &c, long long n, int ld, const int *adj_ptr, const int *adj_col, const int *adj_pos,
+                 const double *S, const double *X, double a, double b, const double *Z, const double *Z2,
+                 double *Y, double *red);
+
+// ------------------------------------------------------------------------------------------------
+// dense path (cones whose scratch matrices are dense, lorads_sdp_conic.c:884-963)
+// ------------------------------------------------------------------------------------------------
+// Zp (packed lower, column-major as the reference) = sym(U V^T);  replaces dsyr2k + repack (lorads_alg_common.c:50-67)
+void launch_dense_uvt(Ctx &c, long long n, int r, int ld, const double *U, const double *V, double *Zp, bool same);
+// dual variant: Z1 = sym(R D^T), Z2 = D D^T
+void launch_dense_uvt_dual(Ctx &c, long long n, int r, int ld, const double *R, const double *D, double *Z1, double *Z2);
+// Sp = (addC ? Cp : 0) then Sp[D_pos[u]] += sum_k w[..] T_val[k]
+void launch_dense_wsum(Ctx &c, double *Sp, long long psize, const double *Cp, const long long *D_pos, long long n_pos,
+                       const int *T_ptr, const int *T_con, const double *T_val, const double *w, const int *act_idx,
+                       bool w_is_compact, bool addC);
+// Y = a * Sp(sym, packed) * X + b * Z ; reductions as launch_spmm
+void launch_dense_symm(Ctx &c, long long n, int r, int ld, const double *Sp, const double *X, double a, double b,
+                       const double *Z, const double *Z2, double *Y, double *red);
+
+// ------------------------------------------------------------------------------------------------
+// fused BLAS-1 on the concatenated factor vectors (length N) and on m-vectors
+// ------------------------------------------------------------------------------------------------
+// A coefficient evaluated on the device from scalar slots: value = k0*S[i0] + k1*S[i1]*S[i2];
+// if store >= 0 thread 0 writes it to S[store].  Slot 0 holds 1.0.
+struct Coef {
+    double k0; int i0; double k1; int i1, i2; int store;
+};
+inline Coef coef_const(double v) { return Coef{v, 0, 0.0, 0, 0, -1}; }
+inline Coef coef_slot(int i, double k = 1.0) { return Coef{k, i, 0.0, 0, 0, -1}; }
+inline Coef coef_prod(int i1, int i2, double k = 1.0, int store = -1) { return Coef{0.0, 0, k, i1, i2, store}; }
+inline Coef coef_affine(int i0, double k1, int i1, int i2, int store = -1) { return Coef{1.0, i0, k1, i1, i2, store}; }
+
+// out = a*x + b*y ; if z != nullptr: S[dot_slot] = sum out*z ; if recip: S[dot_slot] = 1/sum
+// out may alias x or y.  y may be nullptr (treated as 0).
+void launch_axpby_dot(Ctx &c, long long n, double *out, Coef a, const double *x, Coef b, const double *y,
+                      const double *z, double *S, int dot_slot, bool recip);
+// S[slot] = sum x*y
+void launch_dot(Ctx &c, long long n, const double *x, const double *y, double *S, int slot);
+// S[slot] = sum |x|
+void launch_asum(Ctx &c, long long n, const double *x, double *S, int slot);
+// if (S[cond_slot] >= 0) D = -G           (LBFGSDirectionUseGrad, lorads_alm.c:469-489)
+void launch_neg_if_nonneg(Ctx &c, long long n, double *D, const double *G, const double *S, int cond_slot);
+// y = -G ; s = tau*D ; R += tau*D         (SetyAsNegGrad :583, ALMupdateVar :619, first half of setlbfgsHisTwo :657)
+void launch_alm_step(Ctx &c, long long n, double tau, const double *G, const double *D, double *R, double *y, double *s);
+// x += alpha*p ; r -= alpha*Q ; S[slot_rr] = sum r*r  with alpha = S[slot_num]/S[slot_den]  (lorads_cgs.c:183-189)
+void launch_cg_update(Ctx &c, long long n, double *x, double *r, const double *p, const double *Q, double *S,
+                      int slot_num, int slot_den, int slot_rr);
+
+// line-search sums over m (ALMLineSearch, lorads_alm.c:161-172): q0 = b - s + lambda/rho
+// S[slot+0]=|q2|^2  S[slot+1]=q1.q2  S[slot+2]=q0.q2  S[slot+3]=|q1|^2  S[slot+4]=q0.q1
+void launch_linesearch_dots(Ctx &c, long long m, const double *b, const double *s, const double *lam, double rho,
+                            const double *q1, const double *q2, double *S, int slot);
+// s += tau*q1 + tau^2*q2 (when q1 != nullptr) ; M1 = -lambda - rho*b + rho*s   (lorads_alm.c:1123-1124, 15-27)
+void launch_alm_m_update(Ctx &c, long long m, double tau, const double *q1, const double *q2, double *s,
+                         const double *lam, const double *b, double rho, double *M1);
+// S[slot] = sum (b - s)^2  (primalInfeasibility, lorads_alg_common.c:255-257)
+void launch_resid_sq(Ctx &c, long long m, const double *b, const double *s, double *S, int slot);
+// lambda = (lambda + rho*b) - rho*s  (LORADSUpdateDualVar, lorads_alg_common.c:319-332)
+void launch_dual_update(Ctx &c, long long m, double rho, const double *b, const double *s, double *lam);
+// M1 = ((s - b) - cv) * rho - lambda  (LORADSUpdateSDPVarOne, lorads_admm.c:432-445); cv is the cone's
+// constraint vector expanded to length m (may be null)
+void launch_admm_m1(Ctx &c, long long m, const double *b, const double *s, const double *cv, const double *lam,
+                    double rho, double *M1);
+void launch_set_scalar(Ctx &c, double *S, int slot, double v);
+void launch_recip(Ctx &c, double *S, int slot);   // S[slot] = 1/S[slot]
+void launch_fill(Ctx &c, double *x, long long n, double v);
+void launch_scale(Ctx &c, double *x, long long n, double f);   // x *= f
+
+}  // namespace lb2

@@ -1,0 +1,300 @@
+// layout.hpp -- host-side pre-solve of one PSD cone: from the SDPA reader's CSC arrays to the index
+// structures the device kernels consume.
+//
+// Replaces (reference, all under src_semi/data/): sdpDataMatSetData lorads_sdp_data.c:811-828 (coefficient
+// classification), sdp{Dense,Sparse}ConeProcDataImpl lorads_sdp_conic.c:144-227 (constraint rows, compact
+// row list), AConePresolveData lorads_sdp_conic.c:868-1076 (union pattern P, dense/sparse scratch decision,
+// nnzIdx2ResIdx maps -- here by sort + binary search instead of the chained hash of lorads_sdp_data.c:31-45).
+//
+// The reference keeps one heap object + vtable per constraint; here every structure is a flat array:
+//   P            union pattern (row >= col), sorted by (col, row)
+//   item lists   the non-zeros of [A_1..A_m ; C] stacked, sorted by constraint, each item carrying its
+//                pattern coordinates and its inner-product weight (2a off the diagonal, a on it)
+//   T            the same non-zeros transposed: CSC by pattern position (for S = C + sum_i w_i A_i)
+//   adj          the symmetric adjacency of P in CSR by row (for Y = S X without scatter)
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <numeric>
+#include <stdexcept>
+#include <vector>
+
+namespace lb2 {
+
+constexpr int kAuvTileItems = 512;   // items per CTA tile of the A(UV^T) kernel (must match kernels.cu)
+
+struct ItemList {
+    // rows 0..n_rows-1; when has_obj the last row is the objective C
+    int64_t n_rows = 0;
+    bool has_obj = false;
+    std::vector<int32_t> ptr;     // n_rows + 1
+    std::vector<int32_t> irow;    // pattern row  (sparse path)  | packed position (dense path)
+    std::vector<int32_t> icol;    // pattern col  (sparse path)  | unused (dense path)
+    std::vector<double> coef;     // 2a off-diagonal, a on the diagonal (lorads_sdp_data.c:545-549)
+    // rows that straddle tile boundaries: their tile partials are summed by the fix-up kernel
+    std::vector<int32_t> split_row, split_first_slot, split_tile_a, split_tile_b;
+    int64_t n_items() const { return (int64_t)irow.size(); }
+    int64_t n_tiles() const { return (n_items() + kAuvTileItems - 1) / kAuvTileItems; }
+};
+
+struct ConeLayout {
+    int64_t n = 0;          // block dimension
+    int64_t m = 0;          // global number of constraints
+    bool dense_path = false;        // dense scratch matrices (lorads_sdp_conic.c:884,969-973,988-989)
+    bool dense_cone = true;         // > 30 % of the constraints touch the block (lorads_user_data.c:68-70)
+    int64_t n_act = 0;              // constraints with at least one entry in this block
+    std::vector<int32_t> act_idx;   // compact row -> global constraint index
+    int64_t nnzA = 0, nnzC = 0;
+    int64_t n_nonzero_coeff = 0;    // "nnzStat": number of non-zero constraint matrices (lorads_sdp_data.c:190)
+    bool c_is_dense_type = false, any_dense_coeff = false;
+    double cNrm1 = 0, cNrm2Sq = 0, cNrmInf = 0;
+
+    // sparse path
+    std::vector<int32_t> P_row, P_col;
+    int64_t n_diag = 0;
+    std::vector<double> C_onP;                      // C expanded on P (dense path: packed C)
+    ItemList listA, listAC;
+    std::vector<int32_t> T_ptr, T_con; std::vector<double> T_val;   // CSC by pattern position
+    std::vector<int32_t> adj_ptr, adj_col, adj_pos;                 // symmetric adjacency CSR
+    // dense path: positions touched by any constraint, CSR over those positions
+    std::vector<long long> D_pos;                   // unique packed positions with constraint entries
+    int64_t psize() const { return dense_path ? n * (n + 1) / 2 : (int64_t)P_row.size(); }
+};
+
+inline void unpack_lower(int64_t n, int64_t packed, int64_t &row, int64_t &col) {
+    // inverse of PACK_IDX (lorads_utils.h:45); column j starts at j*n - j*(j-1)/2
+    double nn = (double)n;
+    int64_t j = (int64_t)std::floor(((2 * nn + 1) - std::sqrt((2 * nn + 1) * (2 * nn + 1) - 8.0 * (double)packed)) / 2.0);
+    if (j < 0) j = 0;
+    if (j > n - 1) j = n - 1;
+    while (j > 0 && j * n - j * (j - 1) / 2 > packed) --j;
+    while (j + 1 < n && (j + 1) * n - (j + 1) * j / 2 <= packed) ++j;
+    col = j;
+    row = packed - (j * n - j * (j - 1) / 2) + j;
+}
+
+inline void finish_item_list(ItemList &L) {
+    // static table of the rows whose items straddle tile boundaries
+    const int64_t T = kAuvTileItems;
+    L.split_row.clear(); L.split_first_slot.clear(); L.split_tile_a.clear(); L.split_tile_b.clear();
+    for (int64_t r = 0; r < L.n_rows; ++r) {
+        int64_t a = L.ptr[r], b = L.ptr[r + 1];
+        if (b <= a) continue;
+        int64_t ta = a / T, tb = (b - 1) / T;
+        if (ta == tb) continue;
+        // in tile ta the row is the LAST row of the tile: slot 2*ta+1, unless it starts exactly at the tile
+        // start (then it is also the first row: slot 2*ta)
+        int64_t first_slot = (a == ta * T) ? 2 * ta : 2 * ta + 1;
+        L.split_row.push_back((int32_t)r);
+        L.split_first_slot.push_back((int32_t)first_slot);
+        L.split_tile_a.push_back((int32_t)ta);
+        L.split_tile_b.push_back((int32_t)tb);
+    }
+}
+
+// Build the layout of one cone from the reader's arrays (column 0 = C, column i = A_i).
+inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg, const int64_t *idx, const double *elem) {
+    ConeLayout L;
+    L.n = n; L.m = m;
+    const double packedSize = (double)(n * (n + 1) / 2);
+    const int64_t nnz_all = beg[m + 1];
+    if (nnz_all > (int64_t)2000000000) throw std::runtime_error("cone has more than 2^31 non-zeros");
+
+    // --- per-column sorted copies (dataMatCreateSparseImpl sorts when needed, lorads_sdp_data.c:106-108)
+    std::vector<int64_t> sidx(idx, idx + nnz_all);
+    std::vector<double> sval(elem, elem + nnz_all);
+    {
+        std::vector<int64_t> perm;
+        for (int64_t c = 0; c <= m; ++c) {
+            int64_t a = beg[c], b = beg[c + 1];
+            if (b - a < 2 || std::is_sorted(sidx.begin() + a, sidx.begin() + b)) continue;
+            perm.resize(b - a);
+            std::iota(perm.begin(), perm.end(), (int64_t)0);
+            std::stable_sort(perm.begin(), perm.end(), [&](int64_t x, int64_t y) { return idx[a + x] < idx[a + y]; });
+            for (int64_t k = 0; k < b - a; ++k) { sidx[a + k] = idx[a + perm[k]]; sval[a + k] = elem[a + perm[k]]; }
+        }
+    }
+
+    // --- classification (lorads_sdp_data.c:818-824) and statistics
+    auto is_dense_type = [&](int64_t nnz) { return (double)nnz > 0.1 * packedSize; };
+    L.nnzC = beg[1] - beg[0];
+    L.c_is_dense_type = L.nnzC > 0 && is_dense_type(L.nnzC);
+    L.any_dense_coeff = L.c_is_dense_type;
+    L.n_act = 0; L.nnzA = 0; L.n_nonzero_coeff = 0;
+    for (int64_t i = 0; i < m; ++i) {
+        int64_t k = beg[i + 2] - beg[i + 1];
+        if (k > 0) {
+            L.act_idx.push_back((int32_t)i);
+            L.n_act++; L.nnzA += k; L.n_nonzero_coeff++;
+            if (is_dense_type(k)) L.any_dense_coeff = true;
+        }
+    }
+    L.dense_cone = (double)L.n_act > 0.3 * (double)m;   // LUserDataChooseCone, lorads_user_data.c:68-70
+
+    // rows / cols of every entry
+    std::vector<int32_t> erow(nnz_all), ecol(nnz_all);
+    {
+        // entries inside a column are sorted by packed index => columns of the matrix ascend; walk instead
+        // of calling the closed form for every entry
+        for (int64_t c = 0; c <= m; ++c) {
+            int64_t j = 0, start = 0, next = n;   // packed range of matrix column j is [start, next)
+            for (int64_t k = beg[c]; k < beg[c + 1]; ++k) {
+                int64_t p = sidx[k];
+                if (p < start) { j = 0; start = 0; next = n; }
+                if (p - next > 8 * n) {           // far jump: use the closed form
+                    int64_t r_, c_; unpack_lower(n, p, r_, c_);
+                    j = c_; start = j * n - j * (j - 1) / 2; next = start + (n - j);
+                }
+                while (p >= next) { start = next; ++j; next = start + (n - j); }
+                erow[k] = (int32_t)(p - start + j);
+                ecol[k] = (int32_t)j;
+            }
+        }
+    }
+
+    // objective norms (dataMatSparseNrm1/Nrm2Square/NrmInf lorads_sdp_data.c:148-183; dense variants :227-272)
+    for (int64_t k = beg[0]; k < beg[1]; ++k) {
+        double v = sval[k], a = std::fabs(v);
+        bool diag = erow[k] == ecol[k];
+        L.cNrm1 += diag ? a : 2 * a;
+        L.cNrm2Sq += diag ? v * v : 2 * v * v;
+        L.cNrmInf = std::max(L.cNrmInf, a);
+    }
+
+    // --- scratch type decision (AConePresolveData, lorads_sdp_conic.c:884-989)
+    std::vector<int64_t> keys;     // (col, row) keys of the union pattern
+    bool dense = (n < 20) || L.any_dense_coeff;
+    if (!dense) {
+        keys.resize(nnz_all);
+        for (int64_t k = 0; k < nnz_all; ++k) keys[k] = (int64_t)ecol[k] * n + erow[k];
+        std::sort(keys.begin(), keys.end());
+        keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+        double spRatio = (double)keys.size() / packedSize;
+        if (spRatio >= 0.1) dense = true;
+    }
+    L.dense_path = dense;
+
+    auto fill_items = [&](ItemList &IL, bool with_obj) {
+        IL.has_obj = with_obj;
+        IL.n_rows = L.n_act + (with_obj ? 1 : 0);
+        IL.ptr.assign(IL.n_rows + 1, 0);
+        int64_t total = L.nnzA + (with_obj ? L.nnzC : 0);
+        IL.irow.resize(total); IL.icol.resize(total); IL.coef.resize(total);
+        int64_t w = 0;
+        auto push = [&](int64_t k) {
+            bool diag = erow[k] == ecol[k];
+            if (dense) {
+                IL.irow[w] = (int32_t)sidx[k];   // packed position == nnzIdx2ResIdx on the dense path
+                IL.icol[w] = diag ? 1 : 0;
+            } else {
+                IL.irow[w] = erow[k]; IL.icol[w] = ecol[k];
+            }
+            IL.coef[w] = diag ? sval[k] : 2.0 * sval[k];
+            ++w;
+        };
+        for (int64_t a = 0; a < L.n_act; ++a) {
+            int64_t i = L.act_idx[a];
+            for (int64_t k = beg[i + 1]; k < beg[i + 2]; ++k) push(k);
+            IL.ptr[a + 1] = (int32_t)w;
+        }
+        if (with_obj) {
+            for (int64_t k = beg[0]; k < beg[1]; ++k) push(k);
+            IL.ptr[L.n_act + 1] = (int32_t)w;
+        }
+        finish_item_list(IL);
+    };
+
+    if (dense) {
+        if (n * (n + 1) / 2 > (int64_t)2000000000) throw std::runtime_error("dense path: packed size exceeds 2^31");
+        fill_items(L.listA, false);
+        fill_items(L.listAC, true);
+        // packed C
+        L.C_onP.assign((size_t)(n * (n + 1) / 2), 0.0);
+        for (int64_t k = beg[0]; k < beg[1]; ++k) L.C_onP[(size_t)sidx[k]] += sval[k];
+        // constraint entries transposed by packed position (only touched positions)
+        std::vector<int64_t> order(L.nnzA);
+        std::vector<int64_t> pos(L.nnzA); std::vector<int32_t> con(L.nnzA); std::vector<double> val(L.nnzA);
+        int64_t w = 0;
+        for (int64_t a = 0; a < L.n_act; ++a) {
+            int64_t i = L.act_idx[a];
+            for (int64_t k = beg[i + 1]; k < beg[i + 2]; ++k) { pos[w] = sidx[k]; con[w] = (int32_t)a; val[w] = sval[k]; ++w; }
+        }
+        std::iota(order.begin(), order.end(), (int64_t)0);
+        std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return pos[x] < pos[y]; });
+        L.T_ptr.clear(); L.T_con.resize(L.nnzA); L.T_val.resize(L.nnzA); L.D_pos.clear();
+        for (int64_t q = 0; q < L.nnzA; ++q) {
+            int64_t o = order[q];
+            if (q == 0 || pos[o] != L.D_pos.back()) { L.D_pos.push_back(pos[o]); L.T_ptr.push_back((int32_t)q); }
+            L.T_con[q] = con[o]; L.T_val[q] = val[o];
+        }
+        L.T_ptr.push_back((int32_t)L.nnzA);
+        return L;
+    }
+
+    // ----------------------------- sparse path -----------------------------
+    const int64_t np = (int64_t)keys.size();
+    L.P_row.resize(np); L.P_col.resize(np);
+    L.n_diag = 0;
+    for (int64_t p = 0; p < np; ++p) {
+        L.P_col[p] = (int32_t)(keys[p] / n); L.P_row[p] = (int32_t)(keys[p] % n);
+        if (L.P_col[p] == L.P_row[p]) L.n_diag++;
+    }
+    // pattern position of every entry (replaces the hash dictionary)
+    std::vector<int32_t> epos(nnz_all);
+    for (int64_t k = 0; k < nnz_all; ++k) {
+        int64_t key = (int64_t)ecol[k] * n + erow[k];
+        epos[k] = (int32_t)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin());
+    }
+    fill_items(L.listA, false);
+    fill_items(L.listAC, true);
+
+    L.C_onP.assign(np, 0.0);
+    for (int64_t k = beg[0]; k < beg[1]; ++k) L.C_onP[epos[k]] += sval[k];
+
+    // T: CSC by pattern position, constraint (compact index) ascending inside a position
+    L.T_ptr.assign(np + 1, 0);
+    for (int64_t a = 0; a < L.n_act; ++a) {
+        int64_t i = L.act_idx[a];
+        for (int64_t k = beg[i + 1]; k < beg[i + 2]; ++k) L.T_ptr[epos[k] + 1]++;
+    }
+    for (int64_t p = 0; p < np; ++p) L.T_ptr[p + 1] += L.T_ptr[p];
+    L.T_con.resize(L.nnzA); L.T_val.resize(L.nnzA);
+    {
+        std::vector<int32_t> cur(L.T_ptr.begin(), L.T_ptr.end() - 1);
+        for (int64_t a = 0; a < L.n_act; ++a) {
+            int64_t i = L.act_idx[a];
+            for (int64_t k = beg[i + 1]; k < beg[i + 2]; ++k) {
+                int32_t q = cur[epos[k]]++;
+                L.T_con[q] = (int32_t)a; L.T_val[q] = sval[k];
+            }
+        }
+    }
+
+    // symmetric adjacency CSR: row i lists (j, p) for every pattern entry (i,j) or (j,i)
+    L.adj_ptr.assign(n + 1, 0);
+    for (int64_t p = 0; p < np; ++p) {
+        L.adj_ptr[L.P_row[p] + 1]++;
+        if (L.P_row[p] != L.P_col[p]) L.adj_ptr[L.P_col[p] + 1]++;
+    }
+    for (int64_t i = 0; i < n; ++i) L.adj_ptr[i + 1] += L.adj_ptr[i];
+    const int64_t nadj = L.adj_ptr[n];
+    L.adj_col.resize(nadj); L.adj_pos.resize(nadj);
+    {
+        // emit in an order that leaves every row sorted by neighbour index: P is sorted by (col,row); the
+        // entries (i, j<i) of row i come from pattern columns j ascending, then (i,i), then (j>i, i) from
+        // pattern column i with rows ascending.  Two passes keep that order.
+        std::vector<int32_t> cur(L.adj_ptr.begin(), L.adj_ptr.end() - 1);
+        for (int64_t p = 0; p < np; ++p) {           // lower part seen from the row: (row, col<row)
+            int32_t r = L.P_row[p], c = L.P_col[p];
+            if (r != c) { int32_t q = cur[r]++; L.adj_col[q] = c; L.adj_pos[q] = (int32_t)p; }
+        }
+        for (int64_t p = 0; p < np; ++p) {           // diagonal and upper part: row c gets (r >= c)
+            int32_t r = L.P_row[p], c = L.P_col[p];
+            int32_t q = cur[c]++; L.adj_col[q] = r; L.adj_pos[q] = (int32_t)p;
+        }
+    }
+    return L;
+}
+
+}  // namespace lb2

@@ -1,0 +1,654 @@
+// solver.cu -- setup, state transfer and the hot-path operators of the device-resident solver.
+//
+// Host code here replaces src_semi/data/lorads_solver.c (allocation, rank choice, random start) and the glue of
+// src_semi/lorads_alg/lorads_alg_common.c; every numerical loop is a kernel from kernels.cu.
+#include "solver.hpp"
+
+#include <sys/time.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+namespace lb2 {
+
+double wall_time() {
+    struct timeval tv;
+    gettimeofday(&tv, nullptr);
+    return (double)tv.tv_sec + 1e-6 * (double)tv.tv_usec;
+}
+
+void ItemListBufs::upload(const ItemList &L) {
+    ptr.upload(L.ptr); irow.upload(L.irow); icol.upload(L.icol); coef.upload(L.coef);
+    split_row.upload(L.split_row); split_first_slot.upload(L.split_first_slot);
+    split_tile_a.upload(L.split_tile_a); split_tile_b.upload(L.split_tile_b);
+    dev.n_items = L.n_items(); dev.n_rows = L.n_rows; dev.n_tiles = L.n_tiles(); dev.n_split = (long long)L.split_row.size();
+    dev.ptr = ptr.p; dev.irow = irow.p; dev.icol = icol.p; dev.coef = coef.p;
+    dev.split_row = split_row.p; dev.split_first_slot = split_first_slot.p;
+    dev.split_tile_a = split_tile_a.p; dev.split_tile_b = split_tile_b.p;
+    dev.has_empty_rows = false;
+    for (int64_t r = 0; r < L.n_rows; ++r)
+        if (L.ptr[r + 1] == L.ptr[r]) dev.has_empty_rows = true;
+}
+
+Solver::~Solver() {
+    if (S_host) cudaFreeHost(S_host);
+    if (ctx.stream) cudaStreamDestroy(ctx.stream);
+}
+
+void Solver::create(long long nRows, long long nC, const lb2_int *dims, const double *rhs, int dev) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        throw CudaError("no usable CUDA device: the LoRADS B200 kernel layer has no CPU fallback");
+    if (dev < 0 || dev >= count) throw CudaError("CUDA device ordinal out of range");
+    device = dev;
+    LB2_CUDA(cudaSetDevice(dev));
+    LB2_CUDA(cudaStreamCreate(&ctx.stream));
+    cudaDeviceProp prop;
+    LB2_CUDA(cudaGetDeviceProperties(&prop, dev));
+    ctx.num_sms = prop.multiProcessorCount;
+    m = nRows; nCones = nC;
+    blkDims.assign(dims, dims + nC);
+    b_h.assign(rhs, rhs + nRows);
+    inputs.resize(nC);
+    red_partials.alloc(8192 * 8);
+    red_counter.alloc(4);
+    ctx.rs.partials = red_partials.p;
+    ctx.rs.counter = red_counter.p;
+    S.alloc(kNumSlots + 2 * nC);
+    LB2_CUDA(cudaMallocHost((void **)&S_host, sizeof(double) * (kNumSlots + 2 * nC)));
+    std::memset(S_host, 0, sizeof(double) * (kNumSlots + 2 * nC));
+    S_host[SL_ONE] = 1.0;
+    LB2_CUDA(cudaMemcpy(S.p, S_host, sizeof(double) * (kNumSlots + 2 * nC), cudaMemcpyHostToDevice));
+}
+
+void Solver::set_cone(long long i, const lb2_int *beg, const lb2_int *idx, const double *elem) {
+    if (i < 0 || i >= nCones) throw std::invalid_argument("cone index out of range");
+    ConeInput &in = inputs[i];
+    in.beg.assign(beg, beg + m + 2);
+    in.idx.assign(idx, idx + beg[m + 1]);
+    in.elem.assign(elem, elem + beg[m + 1]);
+    in.set = true;
+}
+
+void Solver::preprocess() {
+    LB2_CUDA(cudaSetDevice(device));
+    cones.clear();
+    cones.resize(nCones);
+    cObjNrm1 = 0; cObjNrmInf = 0;
+    double n2 = 0;
+    for (long long c = 0; c < nCones; ++c) {
+        if (!inputs[c].set) throw std::logic_error("cone data missing: call lb2_set_cone_data for every cone");
+        ConeLayout L = build_cone_layout(blkDims[c], m, inputs[c].beg.data(), inputs[c].idx.data(), inputs[c].elem.data());
+        ConeDev &K = cones[c];
+        K.n = L.n; K.dense_path = L.dense_path; K.dense_cone = L.dense_cone; K.n_act = L.n_act;
+        K.np = L.psize(); K.nnzA = L.nnzA; K.nnzC = L.nnzC; K.n_nonzero_coeff = L.n_nonzero_coeff;
+        K.cNrm1 = L.cNrm1; K.cNrm2Sq = L.cNrm2Sq; K.cNrmInf = L.cNrmInf;
+        K.act_idx_h = L.act_idx;
+        K.identity_act = (L.n_act == m);
+        K.act_idx.upload(L.act_idx);
+        K.listA.upload(L.listA);
+        K.listAC.upload(L.listAC);
+        K.obj_item_begin = L.listAC.ptr[L.n_act];
+        const size_t ntile = (size_t)std::max<long long>(1, K.listAC.dev.n_tiles);
+        K.carry1.alloc(2 * ntile); K.carry2.alloc(2 * ntile);
+        K.C_onP.upload(L.C_onP);
+        K.S.alloc((size_t)K.np);
+        K.T_ptr.upload(L.T_ptr); K.T_con.upload(L.T_con); K.T_val.upload(L.T_val);
+        if (K.dense_path) {
+            K.D_pos.upload(L.D_pos);
+            K.n_pos = (long long)L.D_pos.size();
+            K.Z1.alloc((size_t)K.np); K.Z2.alloc((size_t)K.np);
+        } else {
+            K.adj_ptr.upload(L.adj_ptr); K.adj_col.upload(L.adj_col); K.adj_pos.upload(L.adj_pos);
+            K.P_row_h = L.P_row; K.P_col_h = L.P_col;
+        }
+        K.cv.alloc((size_t)K.n_act + 1); K.t1.alloc((size_t)K.n_act + 1); K.t2.alloc((size_t)K.n_act + 1);
+        cObjNrm1 += K.cNrm1; n2 += K.cNrm2Sq; cObjNrmInf = std::max(cObjNrmInf, K.cNrmInf);
+        inputs[c] = ConeInput();   // the reader arrays are no longer needed
+    }
+    cObjNrm2 = std::sqrt(n2);
+    bNrm1 = 0; bNrmInf = 0; double b2 = 0;
+    for (double v : b_h) { bNrm1 += std::fabs(v); bNrmInf = std::max(bNrmInf, std::fabs(v)); b2 += v * v; }
+    bNrm2 = std::sqrt(b2);
+    single_identity = (nCones == 1 && cones[0].identity_act);
+    b.alloc((size_t)m + 1); lam.alloc((size_t)m + 1); s.alloc((size_t)m + 1); q1.alloc((size_t)m + 1);
+    q2.alloc((size_t)m + 1); M1.alloc((size_t)m + 1); cvfull.alloc((size_t)m + 1);
+    LB2_CUDA(cudaMemcpy(b.p, b_h.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
+    preprocessed = true;
+}
+
+void Solver::determine_rank(double timesRank) {
+    // LORADSDetermineRank, lorads_solver.c:290-319
+    if (!preprocessed) throw std::logic_error("preprocess first");
+    rank.assign(nCones, 1); rank_max.assign(nCones, 1);
+    for (long long c = 0; c < nCones; ++c) {
+        const long long nnzRows = cones[c].n_nonzero_coeff, n = blkDims[c];
+        const long long cap = std::min<long long>((long long)std::sqrt((double)(2 * nnzRows)) + 1, n);
+        long long r;
+        if (timesRank <= 1e-6) r = cap;
+        else if (nnzRows / n >= 20 && n <= 400 && nCones <= 3) r = cap;
+        else r = (long long)std::min<double>(std::ceil(timesRank * std::log((double)n)), (double)cap);
+        rank[c] = std::max<long long>(1, r);
+        rank_max[c] = cap;
+    }
+}
+
+void Solver::alloc_vars() {
+    N = 0;
+    for (long long c = 0; c < nCones; ++c) {
+        ConeDev &K = cones[c];
+        K.r = (int)my_cols[c].size();
+        K.ld = std::max(4, ((K.r + 3) / 4) * 4);
+        K.off = N;
+        N += K.n * K.ld;
+    }
+    for (DBuf<double> *v : {&R, &U, &V, &G, &M2, &Bls, &cg_r, &cg_p, &cg_Q, &Dtemp}) v->alloc((size_t)N);
+    lb_s.clear(); lb_y.clear();
+    lb_s.resize(lbfgs_len); lb_y.resize(lbfgs_len);
+    for (int k = 0; k < lbfgs_len; ++k) { lb_s[k].alloc((size_t)N); lb_y[k].alloc((size_t)N); }
+    lb_head = 0;
+}
+
+static void assign_columns(std::vector<int> &cols, long long r, int world, int myrank) {
+    cols.clear();
+    for (long long k = 0; k < r; ++k)
+        if ((int)(k % world) == myrank) cols.push_back((int)k);
+}
+
+void Solver::init_vars(long long lbfgsLen, double initRho) {
+    if (rank.empty()) throw std::logic_error("determine the rank first");
+    if (lbfgsLen < 1 || lbfgsLen > kMaxLbfgs) throw std::invalid_argument("lbfgsListLength must be in 1..16");
+    LB2_CUDA(cudaSetDevice(device));
+    lbfgs_len = (int)lbfgsLen;
+    my_cols.resize(nCones);
+    for (long long c = 0; c < nCones; ++c) assign_columns(my_cols[c], rank[c], world, myrank);
+    alloc_vars();
+    // the reference's libc draw order: srand(925); R of every cone (lorads_solver.c:415-446), later U then V of
+    // every cone (lorads_solver.c:631-658); each element is rand()/RAND_MAX - rand()/RAND_MAX (:361-370)
+    auto draw = [](std::vector<double> &x) {
+        for (double &v : x) {
+            v = (double)rand() / RAND_MAX;
+            v -= (double)rand() / RAND_MAX;
+        }
+    };
+    srand(925);
+    std::vector<double> tmp;
+    for (long long c = 0; c < nCones; ++c) {
+        tmp.resize((size_t)(blkDims[c] * rank[c]));
+        draw(tmp);
+        upload_factor(R.p, cones[c], tmp.data());
+    }
+    for (long long c = 0; c < nCones; ++c) {
+        tmp.resize((size_t)(blkDims[c] * rank[c]));
+        draw(tmp);
+        upload_factor(U.p, cones[c], tmp.data());
+        draw(tmp);
+        upload_factor(V.p, cones[c], tmp.data());
+    }
+    LB2_CUDA(cudaMemset(lam.p, 0, sizeof(double) * (m + 1)));
+    // initial_solver_state, lorads_solver.c:1148-1170
+    double rho;
+    if (initRho == 0) {
+        long long sum = 0;
+        for (long long c = 0; c < nCones; ++c) sum += blkDims[c];
+        rho = 1.0 / std::sqrt((double)sum);
+    } else rho = initRho;
+    alm = AlmState(); alm.rho = rho;
+    admm = AdmmState(); admm.rho = rho; admm.nBlks = nCones;
+    scaleObjHis = 1.0;
+    cgIter = 0;
+    vars_ready = true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// transfers
+// ---------------------------------------------------------------------------------------------------
+double *Solver::factor_ptr(char which) {
+    switch (which) {
+    case 'R': return R.p; case 'U': return U.p; case 'V': return V.p; case 'G': return G.p;
+    case 'M': return M2.p; case 'B': return Bls.p;
+    }
+    throw std::invalid_argument("unknown factor name");
+}
+
+double *Solver::vec_ptr(char which) {
+    switch (which) {
+    case 'l': return lam.p; case 's': return s.p; case 'b': return b.p; case 'm': return M1.p;
+    case 'q': return q1.p; case 'Q': return q2.p; case 'v': return cvfull.p;
+    }
+    throw std::invalid_argument("unknown vector name");
+}
+
+void Solver::upload_factor(double *dst, const ConeDev &K, const double *colMajor) {
+    std::vector<double> rm((size_t)(K.n * K.ld), 0.0);
+    const long long c = &K - cones.data();
+    const std::vector<int> &cols = my_cols[c];
+    for (int k = 0; k < K.r; ++k) {
+        const double *src = colMajor + (size_t)cols[k] * K.n;
+        for (long long i = 0; i < K.n; ++i) rm[(size_t)i * K.ld + k] = src[i];
+    }
+    LB2_CUDA(cudaMemcpyAsync(dst + K.off, rm.data(), sizeof(double) * rm.size(), cudaMemcpyHostToDevice, ctx.stream));
+    LB2_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+void Solver::download_factor(const double *src, const ConeDev &K, double *colMajor) const {
+    std::vector<double> rm((size_t)(K.n * K.ld));
+    LB2_CUDA(cudaMemcpyAsync(rm.data(), src + K.off, sizeof(double) * rm.size(), cudaMemcpyDeviceToHost, ctx.stream));
+    LB2_CUDA(cudaStreamSynchronize(ctx.stream));
+    const long long c = &K - cones.data();
+    const std::vector<int> &cols = my_cols[c];
+    std::memset(colMajor, 0, sizeof(double) * (size_t)(K.n * rank[c]));
+    for (int k = 0; k < K.r; ++k) {
+        double *dstc = colMajor + (size_t)cols[k] * K.n;
+        for (long long i = 0; i < K.n; ++i) dstc[i] = rm[(size_t)i * K.ld + k];
+    }
+}
+
+void Solver::set_factor(char which, long long c, const double *colMajor) { upload_factor(factor_ptr(which), cones.at(c), colMajor); }
+void Solver::get_factor(char which, long long c, double *colMajor) const {
+    download_factor(const_cast<Solver *>(this)->factor_ptr(which), cones.at(c), colMajor);
+}
+
+void Solver::sync() { LB2_CUDA(cudaStreamSynchronize(ctx.stream)); }
+
+void Solver::read_slots() {
+    LB2_CUDA(cudaMemcpyAsync(S_host, S.p, sizeof(double) * (kNumSlots + 2 * nCones), cudaMemcpyDeviceToHost, ctx.stream));
+    LB2_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// operators
+// ---------------------------------------------------------------------------------------------------
+void Solver::cone_auv(ConeDev &K, bool with_obj, const double *Um, const double *Vm, bool same, double scale, double *out) {
+    ItemListBufs &L = with_obj ? K.listAC : K.listA;
+    if (K.dense_path) {
+        launch_dense_uvt(ctx, K.n, K.r, K.ld, Um + K.off, Vm + K.off, K.Z1.p, same);
+        if (world > 1) allreduce(K.Z1.p, K.np);
+        launch_auv(ctx, AUV_FROMZ, L.dev, K.Z1.p, nullptr, K.ld, scale, 0.0, out, nullptr, K.carry1.p, nullptr);
+        return;
+    }
+    launch_auv(ctx, same ? AUV_SAME : AUV_PAIR, L.dev, Um + K.off, Vm + K.off, K.ld, scale, 0.0, out, nullptr,
+               K.carry1.p, nullptr);
+    if (world > 1) allreduce(out, L.dev.n_rows);
+}
+
+void Solver::cone_auv_dual(ConeDev &K, const double *Rm, const double *Dm, double *out1, double *out2) {
+    ItemListBufs &L = K.listAC;
+    if (K.dense_path) {
+        launch_dense_uvt_dual(ctx, K.n, K.r, K.ld, Rm + K.off, Dm + K.off, K.Z1.p, K.Z2.p);
+        if (world > 1) { allreduce(K.Z1.p, K.np); allreduce(K.Z2.p, K.np); }
+        launch_auv(ctx, AUV_FROMZ, L.dev, K.Z1.p, nullptr, K.ld, 2.0, 0.0, out1, nullptr, K.carry1.p, nullptr);
+        launch_auv(ctx, AUV_FROMZ, L.dev, K.Z2.p, nullptr, K.ld, 1.0, 0.0, out2, nullptr, K.carry1.p, nullptr);
+        return;
+    }
+    launch_auv(ctx, AUV_DUAL, L.dev, Rm + K.off, Dm + K.off, K.ld, 2.0, 1.0, out1, out2, K.carry1.p, K.carry2.p);
+    if (world > 1) { allreduce(out1, L.dev.n_rows); allreduce(out2, L.dev.n_rows); }
+}
+
+void Solver::cone_wsum(ConeDev &K, const double *w, bool w_compact, bool addC) {
+    const int *map = K.identity_act ? nullptr : K.act_idx.p;
+    if (K.dense_path)
+        launch_dense_wsum(ctx, K.S.p, K.np, K.C_onP.p, K.D_pos.p, K.n_pos, K.T_ptr.p, K.T_con.p, K.T_val.p, w, map,
+                          w_compact, addC);
+    else
+        launch_wsum(ctx, K.S.p, K.np, K.C_onP.p, K.T_ptr.p, K.T_con.p, K.T_val.p, w, map, w_compact, addC);
+}
+
+void Solver::cone_mul(ConeDev &K, const double *X, double a, double bcoef, const double *Z, const double *Z2, double *Y,
+                      double *red) {
+    if (K.dense_path)
+        launch_dense_symm(ctx, K.n, K.r, K.ld, K.S.p, X + K.off, a, bcoef, Z ? Z + K.off : nullptr,
+                          Z2 ? Z2 + K.off : nullptr, Y + K.off, red);
+    else
+        launch_spmm(ctx, K.n, K.ld, K.adj_ptr.p, K.adj_col.p, K.adj_pos.p, K.S.p, X + K.off, a, bcoef,
+                    Z ? Z + K.off : nullptr, Z2 ? Z2 + K.off : nullptr, Y + K.off, red);
+}
+
+void Solver::init_constr_val_all(const double *Um, const double *Vm, bool same) {
+    for (ConeDev &K : cones) cone_auv(K, false, Um, Vm, same, 1.0, K.cv.p);
+}
+
+void Solver::constr_val_sum() {
+    if (single_identity) {
+        LB2_CUDA(cudaMemcpyAsync(s.p, cones[0].cv.p, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx.stream));
+        return;
+    }
+    LB2_CUDA(cudaMemsetAsync(s.p, 0, sizeof(double) * m, ctx.stream));
+    for (ConeDev &K : cones)
+        launch_scatter_add(ctx, s.p, K.cv.p, K.identity_act ? nullptr : K.act_idx.p, K.n_act, 1.0, true, nullptr);
+}
+
+void Solver::update_constr_val(long long c, const double *Um, const double *Vm) {
+    cone_auv(cones[c], false, Um, Vm, false, 1.0, cones[c].cv.p);
+}
+
+void Solver::expand_cv_from(ConeDev &K, const double *src, double *full) {
+    if (K.identity_act) {
+        LB2_CUDA(cudaMemcpyAsync(full, src, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx.stream));
+        return;
+    }
+    LB2_CUDA(cudaMemsetAsync(full, 0, sizeof(double) * m, ctx.stream));
+    launch_scatter_add(ctx, full, src, K.act_idx.p, K.n_act, 1.0, false, nullptr);
+}
+
+void Solver::expand_cv(ConeDev &K, double *full) { expand_cv_from(K, K.cv.p, full); }
+
+// G = 2 (C + A^*(M1)) R per cone with M1 already on the device; per-cone sum G.G lands in S[kNumSlots + 2c]
+static void grad_from_M1(Solver &S_) {
+    for (long long c = 0; c < S_.nCones; ++c) {
+        ConeDev &K = S_.cones[c];
+        S_.cone_wsum(K, S_.M1.p, false, true);
+        S_.cone_mul(K, S_.R.p, 2.0, 0.0, nullptr, nullptr, S_.G.p, S_.S.p + kNumSlots + 2 * c);
+    }
+}
+
+static double sum_grad_sq(Solver &S_) {
+    double t = 0.0;
+    for (long long c = 0; c < S_.nCones; ++c) t += S_.S_host[kNumSlots + 2 * c];
+    return t;
+}
+
+double Solver::cal_grad(double rho) {
+    // ALMSetGrad / ALMCalGrad, lorads_alm.c:9-54
+    launch_alm_m_update(ctx, m, 0.0, nullptr, nullptr, s.p, lam.p, b.p, rho, M1.p);
+    grad_from_M1(*this);
+    if (world > 1) allreduce(S.p + kNumSlots, 2 * nCones);
+    read_slots();
+    return sum_grad_sq(*this);
+}
+
+void Solver::lbfgs_direction(long long counter) {
+    // LBFGSDirection, lorads_alm.c:230-391 (history ring of lbfgs_len nodes, lb_head = oldest) followed by
+    // LBFGSDirectionUseGrad, lorads_alm.c:469-489.  The search direction lives in U, as in the reference.
+    const int L = lbfgs_len;
+    double *D = U.p, *q = Dtemp.p;
+    if (counter == 0) {
+        // D = -G; the <D,G> >= 0 test of LBFGSDirectionUseGrad can only fire for G = 0, where it is a no-op
+        launch_axpby_dot(ctx, N, D, coef_const(-1.0), G.p, coef_const(0.0), nullptr, nullptr, S.p, SL_DG, false);
+        return;
+    }
+    const int K = (int)((counter <= L - 1) ? counter : L);
+    auto node = [&](int i) { return ((lb_head - i) % L + L) % L; };   // i = 1 newest ... K oldest used
+    launch_dot(ctx, N, lb_s[node(1)].p, G.p, S.p, SL_T0);
+    if (world > 1) allreduce(S.p + SL_T0, 1);
+    for (int i = 1; i <= K; ++i) {
+        const int nd = node(i);
+        const double *zvec = (i < K) ? lb_s[node(i + 1)].p : lb_y[nd].p;
+        // q = q - alpha*y, alpha = beta*<s,q>; -alpha is remembered for the second loop
+        launch_axpby_dot(ctx, N, q, coef_const(1.0), (i == 1) ? G.p : q,
+                         coef_prod(SL_BETA0 + nd, SL_T0, -1.0, SL_NEGALPHA0 + nd), lb_y[nd].p, zvec, S.p, SL_T0, false);
+        if (world > 1) allreduce(S.p + SL_T0, 1);
+    }
+    for (int i = K; i >= 1; --i) {
+        const int nd = node(i);
+        if (i > 1) {
+            // q = q + (alpha - beta*<y,q>) s
+            Coef w{-1.0, SL_NEGALPHA0 + nd, -1.0, SL_BETA0 + nd, SL_T0, -1};
+            launch_axpby_dot(ctx, N, q, coef_const(1.0), q, w, lb_s[nd].p, lb_y[node(i - 1)].p, S.p, SL_T0, false);
+            if (world > 1) allreduce(S.p + SL_T0, 1);
+        } else {
+            // D = -(q + w s)
+            Coef negw{1.0, SL_NEGALPHA0 + nd, 1.0, SL_BETA0 + nd, SL_T0, -1};
+            launch_axpby_dot(ctx, N, D, coef_const(-1.0), q, negw, lb_s[nd].p, G.p, S.p, SL_DG, false);
+            if (world > 1) allreduce(S.p + SL_DG, 1);
+        }
+    }
+    launch_neg_if_nonneg(ctx, N, D, G.p, S.p, SL_DG);
+}
+
+void Solver::q12p12() {
+    // ALMCalq12p12, lorads_alm.c:540-560: q1 = 2 A(sym(R D^T)), p1 = 2 <C, sym(R D^T)>, q2 = A(D D^T), p2 = <C, D D^T>
+    LB2_CUDA(cudaMemsetAsync(S.p + SL_P1, 0, 2 * sizeof(double), ctx.stream));
+    if (single_identity) {
+        ConeDev &K = cones[0];
+        cone_auv_dual(K, R.p, U.p, q1.p, q2.p);   // row m of the outputs is the objective row
+        launch_scatter_add(ctx, S.p + SL_P1, q1.p + m, nullptr, 0, 1.0, true, S.p + SL_P1);
+        launch_scatter_add(ctx, S.p + SL_P2, q2.p + m, nullptr, 0, 1.0, true, S.p + SL_P2);
+        return;
+    }
+    LB2_CUDA(cudaMemsetAsync(q1.p, 0, sizeof(double) * m, ctx.stream));
+    LB2_CUDA(cudaMemsetAsync(q2.p, 0, sizeof(double) * m, ctx.stream));
+    for (ConeDev &K : cones) {
+        cone_auv_dual(K, R.p, U.p, K.t1.p, K.t2.p);
+        const int *map = K.identity_act ? nullptr : K.act_idx.p;
+        launch_scatter_add(ctx, q1.p, K.t1.p, map, K.n_act, 1.0, true, S.p + SL_P1);
+        launch_scatter_add(ctx, q2.p, K.t2.p, map, K.n_act, 1.0, true, S.p + SL_P2);
+    }
+}
+
+void Solver::primal_infeasibility(const double *Rm) {
+    // primalInfeasibility, lorads_alg_common.c:250-258 (the caller reads S_host[SL_PINF] after read_slots())
+    init_constr_val_all(Rm, Rm, true);
+    constr_val_sum();
+    launch_resid_sq(ctx, m, b.p, s.p, S.p, SL_PINF);
+}
+
+double Solver::cal_obj(const double *Rm) {
+    // LORADSCalObjRR_ALM, lorads_alm.c:1259-1268
+    LB2_CUDA(cudaMemsetAsync(S.p + SL_OBJ, 0, sizeof(double), ctx.stream));
+    for (ConeDev &K : cones) {
+        cone_auv(K, true, Rm, Rm, true, 1.0, K.t1.p);
+        launch_scatter_add(ctx, S.p + SL_OBJ, K.t1.p + K.n_act, nullptr, 0, 1.0, true, S.p + SL_OBJ);
+    }
+    read_slots();
+    return S_host[SL_OBJ] / scaleObjHis;
+}
+
+double Solver::cal_dual_obj() {
+    // LORADSCalDualObj, lorads_alg_common.c:334-340
+    launch_dot(ctx, m, b.p, lam.p, S.p, SL_DOBJ);
+    read_slots();
+    return S_host[SL_DOBJ] / scaleObjHis;
+}
+
+void Solver::average_uv() {
+    // averageUV, lorads_admm.c:310-315
+    launch_axpby_dot(ctx, N, R.p, coef_const(0.5), U.p, coef_const(0.5), V.p, nullptr, S.p, SL_T1, false);
+}
+
+void Solver::update_dual_var(double rho) { launch_dual_update(ctx, m, rho, b.p, s.p, lam.p); }
+
+void Solver::update_dimacs_alm() {
+    // LORADSUpdateDimacsErrorALM, lorads_alg_common.c:270-274
+    primal_infeasibility(R.p);
+    read_slots();
+    dimac_pinf = std::sqrt(S_host[SL_PINF]) / (1 + bNrm1);
+    dimac_gap = std::fabs(pObj - dObj) / (1 + std::fabs(pObj) + std::fabs(dObj));
+}
+
+void Solver::update_dimacs_admm() {
+    // LORADSUpdateDimacsErrorADMM, lorads_alg_common.c:282-290: R = (U+V)/2, then the ALM formula; note that
+    // this overwrites constrVal / constrValSum with A(R R^T), which the dual update then uses
+    average_uv();
+    update_dimacs_alm();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ALM inner iteration, lorads_alm.c:1073-1146
+// ---------------------------------------------------------------------------------------------------
+static double nth_root3(double base) {
+    // LORADSnthroot(base, 3), lorads_alm.c:102-112
+    return base > 0 ? std::pow(base, 1.0 / 3) : -std::pow(-base, 1.0 / 3);
+}
+
+static long long cubic_roots(double a, double b, double c, double d, double *res) {
+    // Shengjin's formulas as used by LORADScubic_equation, lorads_alm.c:114-154
+    const double A = b * b - 3 * a * c, B = b * c - 9 * a * d, C = c * c - 3 * b * d;
+    const double delta = B * B - 4 * A * C;
+    res[0] = res[1] = res[2] = 0.0;
+    if (A == 0 && B == 0) {
+        res[0] = std::max(res[0], -c / b);
+        return 1;
+    }
+    if (delta > 0) {
+        const double sq = std::sqrt(delta);
+        const double Y1 = A * b + 1.5 * a * (-B + sq), Y2 = A * b + 1.5 * a * (-B - sq);
+        res[0] = std::max(res[0], (-b - nth_root3(Y1) - nth_root3(Y2)) / 3 / a);
+        return 1;
+    }
+    if (delta == 0 && A != 0 && B != 0) {
+        const double K = B / A;
+        res[0] = -b / a + K;
+        res[1] = -K / 2;
+        return 2;
+    }
+    if (delta < 0) {
+        const double sqA = std::sqrt(A);
+        const double T = (A * b - 1.5 * a * B) / (A * sqA);
+        const double theta = std::acos(T);
+        const double cs = std::cos(theta / 3), sn = std::sqrt(3.0) * std::sin(theta / 3);
+        res[0] = (-b - 2 * sqA * cs) / 3 / a;
+        res[1] = (-b + sqA * (cs + sn)) / 3 / a;
+        res[2] = (-b + sqA * (cs - sn)) / 3 / a;
+        return 3;
+    }
+    return 0;
+}
+
+long long line_search(double rho, const double *sums, double p1, double p2, double *tau) {
+    // ALMLineSearch, lorads_alm.c:161-228: exact minimiser over [0,1] of a t^4 + b t^3 + c t^2 + d t.
+    // sums = {|q2|^2, q1.q2, q0.q2, |q1|^2, q0.q1} with q0 = b - A(RR^T) + lambda/rho.
+    const double a = rho * sums[0] / 2;
+    const double b = rho * sums[1];
+    const double c = p2 - rho * sums[2] + rho * sums[3] / 2;
+    const double d = p1 - rho * sums[4];
+    double roots[3];
+    const long long rootNum = cubic_roots(4 * a, 3 * b, 2 * c, d, roots);
+    auto f = [&](double x) { return a * std::pow(x, 4) + b * std::pow(x, 3) + c * std::pow(x, 2) + d * x; };
+    const double f0 = 0.0, f1 = f(1.0);
+    double fr[3] = {1e+30, 1e+30, 1e+30};
+    for (int k = 0; k < 3; ++k)
+        if (rootNum >= k + 1 && (k < 2 || rootNum == 3) && roots[k] > 1e-20 && roots[k] <= 1.0) fr[k] = f(roots[k]);
+    const double mn = std::min(std::min(std::min(std::min(f0, f1), fr[0]), fr[1]), fr[2]);
+    if (std::fabs(mn - f0) < 1e-10) *tau = 0.0;
+    if (std::fabs(mn - f1) < 1e-10) *tau = 1.0;
+    for (int k = 0; k < 3; ++k)
+        if (std::fabs(mn - fr[k]) < 1e-10) *tau = roots[k];
+    return rootNum;
+}
+
+int Solver::alm_inner_front(double rho, long long counter, double *tau, double *p12, long long *rootNum) {
+    lbfgs_direction(counter);
+    q12p12();
+    if (world > 1) allreduce(S.p + SL_P1, 2);
+    launch_linesearch_dots(ctx, m, b.p, s.p, lam.p, rho, q1.p, q2.p, S.p, SL_LS);
+    read_slots();
+    p12[0] = S_host[SL_P1]; p12[1] = S_host[SL_P2];
+    *rootNum = line_search(rho, S_host + SL_LS, p12[0], p12[1], tau);
+    return 0;
+}
+
+void Solver::alm_inner_back(double rho, double tau, double *lagNormSq, double *pinf1) {
+    const int head = lb_head;
+    launch_alm_step(ctx, N, tau, G.p, U.p, R.p, lb_y[head].p, lb_s[head].p);
+    launch_alm_m_update(ctx, m, tau, q1.p, q2.p, s.p, lam.p, b.p, rho, M1.p);
+    grad_from_M1(*this);
+    if (world > 1) allreduce(S.p + kNumSlots, 2 * nCones);
+    // setlbfgsHisTwo, lorads_alm.c:657-678: y += G_new, beta = 1/<y,s>, advance the ring
+    launch_axpby_dot(ctx, N, lb_y[head].p, coef_const(1.0), lb_y[head].p, coef_const(1.0), G.p, lb_s[head].p, S.p,
+                     SL_BETA0 + head, world == 1);
+    if (world > 1) {
+        allreduce(S.p + SL_BETA0 + head, 1);
+        launch_recip(ctx, S.p, SL_BETA0 + head);
+    }
+    lb_head = (head + 1) % lbfgs_len;
+    primal_infeasibility(R.p);
+    read_slots();
+    *lagNormSq = sum_grad_sq(*this);
+    dimac_pinf = std::sqrt(S_host[SL_PINF]) / (1 + bNrm1);
+    dimac_gap = std::fabs(pObj - dObj) / (1 + std::fabs(pObj) + std::fabs(dObj));
+    *pinf1 = dimac_pinf;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ADMM block update: RHS + CG, lorads_admm.c:376-480 and lorads_cgs.c:81-240
+// ---------------------------------------------------------------------------------------------------
+void Solver::cg_matvec(ConeDev &K, const double *x, const double *Vn, double *res, const double *Z2, double *red) {
+    // linSysProduct: weight = A(sym(x V^T)); W = sum_i weight_i A_i; res = W V + x
+    cone_auv(K, false, x, Vn, false, 1.0, K.t1.p);
+    cone_wsum(K, K.t1.p, true, false);
+    cone_mul(K, Vn, 1.0, 1.0, x, Z2, res, red);
+}
+
+void Solver::update_sdp_var_one(long long c, double *upd, const double *noupd, double rho, double tol, long long maxit) {
+    ConeDev &K = cones[c];
+    const long long nk = K.n * K.ld, off = K.off;
+    // M1 = rho (constrValSum - constrVal[c] - b) - lambda
+    const double *cvf = nullptr;
+    if (K.identity_act) cvf = K.cv.p; else { expand_cv(K, cvfull.p); cvf = cvfull.p; }
+    launch_admm_m1(ctx, m, b.p, s.p, cvf, lam.p, rho, M1.p);
+    // bLinSys = -( (C + A^*(M1)) V - rho V ) / rho
+    cone_wsum(K, M1.p, false, true);
+    cone_mul(K, noupd, -1.0 / rho, 1.0, noupd, nullptr, Bls.p, nullptr);
+
+    double *x = upd + off, *bl = Bls.p + off, *r = cg_r.p + off, *p = cg_p.p + off, *Q = cg_Q.p + off;
+    // shifted views so that the cone_* helpers (which add K.off) see this cone's slice
+    double *r0 = cg_r.p, *p0 = cg_p.p, *Q0 = cg_Q.p;
+    const double t0 = wall_time();
+    launch_asum(ctx, nk, bl, S.p, SL_CG_BN);
+    cg_matvec(K, upd, noupd, r0, nullptr, nullptr);
+    int rrA = SL_CG_RR_A, rrB = SL_CG_RR_B;
+    // r = b - A x ; <r,r>
+    launch_axpby_dot(ctx, nk, r, coef_const(-1.0), r, coef_const(1.0), bl, r, S.p, rrA, false);
+    if (world > 1) { allreduce(S.p + SL_CG_BN, 1); allreduce(S.p + rrA, 1); }
+    read_slots();
+    const double bNorm = S_host[SL_CG_BN];
+    double rr = S_host[rrA];
+    if (std::sqrt(rr) / bNorm < tol) {   // converged at the warm start; cg->iter keeps its previous value
+        cgTime += wall_time() - t0;
+        cgIter += K.cg_iter_last;
+        return;
+    }
+    LB2_CUDA(cudaMemcpyAsync(p, r, sizeof(double) * nk, cudaMemcpyDeviceToDevice, ctx.stream));
+    long long iter = 0;
+    for (long long k = 0; k < maxit; ++k) {
+        iter += 1;
+        cg_matvec(K, p0, noupd, Q0, p0, S.p + SL_CG_RED);       // Q = A p, S[SL_CG_RED+1] = <p,Q>
+        if (world > 1) allreduce(S.p + SL_CG_RED, 2);
+        launch_cg_update(ctx, nk, x, r, p, Q, S.p, rrA, SL_CG_RED + 1, rrB);
+        if (world > 1) allreduce(S.p + rrB, 1);
+        read_slots();
+        double rrNew = S_host[rrB];
+        const double resi = std::sqrt(rrNew);
+        if (resi / bNorm < tol) break;
+        double beta;
+        if (k % 20 == 0) {
+            // restart (also at k = 0, lorads_cgs.c:195): r = b - A x, p = q = r, then beta = <r,r>/<r,r>
+            cg_matvec(K, upd, noupd, r0, nullptr, nullptr);
+            launch_axpby_dot(ctx, nk, r, coef_const(-1.0), r, coef_const(1.0), bl, r, S.p, rrB, false);
+            if (world > 1) allreduce(S.p + rrB, 1);
+            LB2_CUDA(cudaMemcpyAsync(p, r, sizeof(double) * nk, cudaMemcpyDeviceToDevice, ctx.stream));
+            beta = 1.0;
+        } else {
+            beta = rrNew / rr;
+        }
+        // p = r + beta p
+        launch_axpby_dot(ctx, nk, p, coef_const(beta), p, coef_const(1.0), r, nullptr, S.p, SL_T1, false);
+        if (k % 20 == 0) { read_slots(); rrNew = S_host[rrB]; }
+        rr = rrNew;
+        std::swap(rrA, rrB);
+        if (resi != resi) printf("File [%30s] Line [%d]\n", "lorads_b200 cg", (int)k);   // NaN trace, as the reference
+    }
+    K.cg_iter_last = iter;
+    cgTime += wall_time() - t0;
+    cgIter += iter;
+}
+
+void Solver::update_sdp_var(double rho, double tol, long long maxit) {
+    // LORADSUpdateSDPVar, lorads_alg_common.c:187-215 (Gauss-Seidel over cones)
+    for (long long c = 0; c < nCones; ++c) {
+        ConeDev &K = cones[c];
+        const int *map = K.identity_act ? nullptr : K.act_idx.p;
+        for (int half = 0; half < 2; ++half) {
+            if (half == 0) update_sdp_var_one(c, U.p, V.p, rho, tol, maxit);
+            else update_sdp_var_one(c, V.p, U.p, rho, tol, maxit);
+            launch_scatter_add(ctx, s.p, K.cv.p, map, K.n_act, -1.0, true, nullptr);
+            update_constr_val(c, U.p, V.p);
+            launch_scatter_add(ctx, s.p, K.cv.p, map, K.n_act, 1.0, true, nullptr);
+        }
+    }
+}
+
+}  // namespace lb2

@@ -1,0 +1,175 @@
+// solver.hpp -- device-resident solver state and the operators of the hot path.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/lorads_b200.h"
+#include "kernels.cuh"
+#include "layout.hpp"
+
+namespace lb2 {
+
+// scalar slots on the device (double S[kNumSlots + 2*nCones])
+enum Slot : int {
+    SL_ONE = 0, SL_ZERO = 1,
+    SL_T0 = 2, SL_T1 = 3,
+    SL_LS = 8,            // 8..12 line-search sums
+    SL_P1 = 13, SL_P2 = 14,
+    SL_PINF = 17, SL_DG = 19, SL_OBJ = 20, SL_DOBJ = 21,
+    SL_CG_RED = 24,       // 24 = sum Q.Q (unused), 25 = p.Q
+    SL_CG_RR_A = 26, SL_CG_RR_B = 27, SL_CG_BN = 28,
+    SL_NEGALPHA0 = 32,    // 32..47  -alpha of the L-BFGS two-loop, per history node
+    SL_BETA0 = 48,        // 48..63  beta = 1/<y,s> per history node
+    kNumSlots = 64        // followed by 2 slots per cone: sum G.G and sum G.Z2 of that cone
+};
+constexpr int kMaxLbfgs = 16;
+
+struct ItemListBufs {
+    DBuf<int> ptr, irow, icol, split_row, split_first_slot, split_tile_a, split_tile_b;
+    DBuf<double> coef;
+    ItemListDev dev;
+    void upload(const ItemList &L);
+};
+
+struct ConeDev {
+    long long n = 0;
+    int r = 0;           // rank (number of factor columns held on this device)
+    int ld = 0;          // padded leading dimension of the row-major factor storage
+    long long off = 0;   // offset of this cone inside the concatenated N-vectors
+    bool dense_path = false, dense_cone = true, identity_act = false;
+    long long n_act = 0, np = 0, nnzA = 0, nnzC = 0, n_nonzero_coeff = 0, n_pos = 0;
+    long long obj_item_begin = 0;   // first objective item of listAC
+    double cNrm1 = 0, cNrm2Sq = 0, cNrmInf = 0;
+    std::vector<int32_t> act_idx_h;
+    std::vector<int32_t> P_row_h, P_col_h;          // kept for lb2_get_pattern / dual infeasibility
+    DBuf<int> act_idx;
+    ItemListBufs listA, listAC;
+    DBuf<double> carry1, carry2;
+    DBuf<double> C_onP, S, T_val;
+    DBuf<int> T_ptr, T_con, adj_ptr, adj_col, adj_pos;
+    DBuf<long long> D_pos;
+    DBuf<double> Z1, Z2;                            // dense path: packed sym(UV^T)
+    DBuf<double> cv;                                // constrVal of the cone (compact, n_act + 1)
+    DBuf<double> t1, t2;                            // compact AUV outputs (n_act + 1)
+    long long cg_iter_last = 0;
+};
+
+struct AlmState {   // lorads_alm_state, def_lorads_solver.h:130-145
+    long long outerIter = 0, innerIter = 0;
+    double rho = 0, pinf_inf = 1e30, pinf_1 = 1e30, pinf_2 = 0, gap = 1e30, pobj = 1e30, dobj = 1e30;
+    double dinf_inf = 1e30, dinf_1 = 1e30, dinf_2 = 0, tau = 0;
+};
+struct AdmmState {  // lorads_admm_state, def_lorads_solver.h:147-161
+    long long iter = 0, nBlks = 0, cg_iter = 0;
+    double rho = 0, dinf_1 = 1e30, dinf_inf = 1e30, pinf_1 = 1e30, pinf_inf = 1e30, pinf_2 = 1e30, dinf_2 = 1e30;
+    double pobj = 1e30, dobj = 1e30, gap = 1e30;
+};
+
+struct Solver {
+    int device = 0;
+    Ctx ctx;
+    long long m = 0, nCones = 0;
+    std::vector<long long> blkDims;
+    std::vector<double> b_h;
+    // reader arrays, kept until preprocess
+    struct ConeInput { std::vector<int64_t> beg, idx; std::vector<double> elem; bool set = false; };
+    std::vector<ConeInput> inputs;
+    std::vector<ConeDev> cones;
+    bool preprocessed = false, vars_ready = false;
+    bool single_identity = false;      // one cone whose active set is all constraints: no scatter passes
+
+    // m-vectors (capacity m + 1: slot m receives the objective value of fused evaluations)
+    DBuf<double> b, lam, s, q1, q2, M1, cvfull;
+    // N-vectors
+    long long N = 0;
+    DBuf<double> R, U, V, G, M2, Bls, cg_r, cg_p, cg_Q, Dtemp;
+    std::vector<DBuf<double>> lb_s, lb_y;
+    int lbfgs_len = 2, lb_head = 0;
+    // scalars
+    DBuf<double> S;
+    double *S_host = nullptr;          // pinned mirror
+    DBuf<double> red_partials;
+    DBuf<unsigned int> red_counter;
+
+    // ranks
+    std::vector<long long> rank, rank_max;
+    // communicator (column sharding)
+    int world = 1, myrank = 0;
+    void *nccl = nullptr;
+    std::vector<std::vector<int>> my_cols;   // per cone: global column ids held here
+
+    // problem constants / convergence state (lorads_solver fields, def_lorads_solver.h:76-105)
+    double cObjNrm1 = 0, cObjNrm2 = 0, cObjNrmInf = 0, bNrm1 = 0, bNrm2 = 0, bNrmInf = 0;
+    double pObj = 0, dObj = 0, scaleObjHis = 1.0;
+    double dimac_pinf = 0, dimac_gap = 0, dimac_dinf = 0;
+    long long cgIter = 0;
+    double cgTime = 0;
+    int status = LB2_STATUS_UNKNOWN;
+    AlmState alm;
+    AdmmState admm;
+    int MAX_ALM_SUB_ITER = 5000;   // the reference's global, lorads_alm.c:7
+
+    ~Solver();
+    // setup
+    void create(long long nRows, long long nCones, const lb2_int *blkDims, const double *rhs, int dev);
+    void set_cone(long long i, const lb2_int *beg, const lb2_int *idx, const double *elem);
+    void preprocess();
+    void determine_rank(double timesLogRank);
+    void init_vars(long long lbfgsLen, double initRho);
+    void alloc_vars();
+    // transfers
+    double *factor_ptr(char which);
+    double *vec_ptr(char which);
+    void set_factor(char which, long long c, const double *colMajor);
+    void get_factor(char which, long long c, double *colMajor) const;
+    void upload_factor(double *dst, const ConeDev &K, const double *colMajor);
+    void download_factor(const double *src, const ConeDev &K, double *colMajor) const;
+    void read_slots();          // S -> S_host (synchronises the stream)
+    void sync();
+    void allreduce(double *p, long long count);
+    // operators
+    // A(sym(U V^T)) of cone c with the A or A+C item list: writes (scale*values) to out1 (n_rows of the list)
+    void cone_auv(ConeDev &K, bool with_obj, const double *U, const double *V, bool same, double scale, double *out);
+    void cone_auv_dual(ConeDev &K, const double *Rm, const double *Dm, double *out1, double *out2);
+    void cone_wsum(ConeDev &K, const double *w, bool w_compact, bool addC);
+    void cone_mul(ConeDev &K, const double *X, double a, double bcoef, const double *Z, const double *Z2, double *Y, double *red);
+    // constrVal[c] = A(sym(U V^T)) for all cones, then constrValSum (LORADSInitConstrValAll + InitConstrValSum)
+    void init_constr_val_all(const double *Um, const double *Vm, bool same);
+    void constr_val_sum();
+    void update_constr_val(long long c, const double *Um, const double *Vm);   // LORADSUpdateConstrVal
+    void expand_cv(ConeDev &K, double *full);                                    // compact cv -> length m
+    void expand_cv_from(ConeDev &K, const double *src, double *full);
+    double cal_grad(double rho);                                                 // ALMCalGrad, returns sum ||G||^2
+    void lbfgs_direction(long long counter);
+    void q12p12();
+    void primal_infeasibility(const double *Rm);                                 // fills S_host[SL_PINF] lazily
+    double cal_obj(const double *Rm);                                            // <C, R R^T> / scaleObjHis
+    double cal_dual_obj();
+    void average_uv();                                                           // R = (U+V)/2
+    void cg_matvec(ConeDev &K, const double *x, const double *Vnoupd, double *res, const double *Z2, double *red);
+    void update_sdp_var_one(long long c, double *upd, const double *noupd, double rho, double tol, long long maxit);
+    void update_sdp_var(double rho, double tol, long long maxit);
+    void update_dual_var(double rho);
+    // phases
+    int alm_inner_front(double rho, long long counter, double *tau, double *p12, long long *rootNum);
+    void alm_inner_back(double rho, double tau, double *lagNormSq, double *pinf1);
+    void update_dimacs_alm();
+    void update_dimacs_admm();
+    int alm_optimize(lb2_params *p, double rho_update_factor_unused, double timeSolveStart, bool reopt, bool early_stop,
+                     double reopt_rho_factor);
+    void alm_to_admm(lb2_params *p);
+    int admm_optimize(lb2_params *p, long long iter_celling, double timeSolveStart, bool reopt);
+    double reopt(lb2_params *p, double *reopt_param, long long *alm_iter, long long *admm_iter, double timeSolveStart,
+                 int *admm_bad_iter_flag, int reopt_level);
+    void obj_scale_dualvar(double f);
+    void dual_infeasibility();
+    bool check_all_rank_max(double aug_factor) const;
+    bool aug_rank(double aug_factor);
+    int solve(lb2_params *p, lb2_result *res);
+};
+
+double wall_time();
+long long line_search(double rho, const double *sums, double p1, double p2, double *tau);
+
+}  // namespace lb2
