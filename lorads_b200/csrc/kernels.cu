@@ -73,52 +73,56 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
     } else {
         constexpr int NG = kBlock / G;          // groups per block
         const int g = tid / G, gl = tid % G;
-        for (int k = t0 + g; k < t1; k += NG) {
-            const int i = L.irow[k], j = L.icol[k];
-            const double cf = L.coef[k];
-            const double *ui = U + (size_t)i * ld, *uj = U + (size_t)j * ld;
-            double a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            if constexpr (MODE == AUV_SAME) {
-                if (i == j) {
-                    for (int col = 2 * gl; col < ld; col += 2 * G) {
-                        double2 x = ld2(ui + col);
-                        a1 = fma(x.x, x.x, a1); a1 = fma(x.y, x.y, a1);
+        // warp-uniform trip count: every lane reaches the shuffles of every iteration (tail lanes idle)
+        for (int base = t0; base < t1; base += NG) {
+            const int k = base + g;
+            const bool live = k < t1;
+            double a1 = 0.0, a2 = 0.0, a3 = 0.0, cf = 0.0;
+            bool diag = true;
+            if (live) {
+                const int i = L.irow[k], j = L.icol[k];
+                cf = L.coef[k];
+                diag = (i == j);
+                const double *ui = U + (size_t)i * ld, *uj = U + (size_t)j * ld;
+                if constexpr (MODE == AUV_SAME) {
+                    if (diag) {
+                        for (int col = 2 * gl; col < ld; col += 2 * G) {
+                            double2 x = ld2(ui + col);
+                            a1 = fma(x.x, x.x, a1); a1 = fma(x.y, x.y, a1);
+                        }
+                    } else {
+                        for (int col = 2 * gl; col < ld; col += 2 * G) {
+                            double2 x = ld2(ui + col), y = ld2(uj + col);
+                            a1 = fma(x.x, y.x, a1); a1 = fma(x.y, y.y, a1);
+                        }
                     }
                 } else {
-                    for (int col = 2 * gl; col < ld; col += 2 * G) {
-                        double2 x = ld2(ui + col), y = ld2(uj + col);
-                        a1 = fma(x.x, y.x, a1); a1 = fma(x.y, y.y, a1);
+                    const double *vi = V + (size_t)i * ld, *vj = V + (size_t)j * ld;
+                    if (diag) {
+                        for (int col = 2 * gl; col < ld; col += 2 * G) {
+                            double2 x = ld2(ui + col), y = ld2(vi + col);
+                            a1 = fma(x.x, y.x, a1); a1 = fma(x.y, y.y, a1);
+                            if constexpr (DUAL) { a3 = fma(y.x, y.x, a3); a3 = fma(y.y, y.y, a3); }
+                        }
+                    } else {
+                        for (int col = 2 * gl; col < ld; col += 2 * G) {
+                            double2 x = ld2(ui + col), y = ld2(vj + col), p = ld2(uj + col), q = ld2(vi + col);
+                            a1 = fma(x.x, y.x, a1); a1 = fma(x.y, y.y, a1);
+                            a2 = fma(p.x, q.x, a2); a2 = fma(p.y, q.y, a2);
+                            if constexpr (DUAL) { a3 = fma(q.x, y.x, a3); a3 = fma(q.y, y.y, a3); }
+                        }
                     }
                 }
-                a1 = group_sum<G>(a1);
-                if (gl == 0) sp1[k - t0] = scale1 * cf * a1;
-            } else {
-                const double *vi = V + (size_t)i * ld, *vj = V + (size_t)j * ld;
-                if (i == j) {
-                    for (int col = 2 * gl; col < ld; col += 2 * G) {
-                        double2 x = ld2(ui + col), y = ld2(vi + col);
-                        a1 = fma(x.x, y.x, a1); a1 = fma(x.y, y.y, a1);
-                        if constexpr (DUAL) { a3 = fma(y.x, y.x, a3); a3 = fma(y.y, y.y, a3); }
-                    }
-                    a1 = group_sum<G>(a1);
-                    if constexpr (DUAL) a3 = group_sum<G>(a3);
-                    if (gl == 0) {
-                        sp1[k - t0] = scale1 * cf * a1;
-                        if constexpr (DUAL) sp2[k - t0] = scale2 * cf * a3;
-                    }
+            }
+            a1 = group_sum<G>(a1);
+            if constexpr (MODE != AUV_SAME) a2 = group_sum<G>(a2);
+            if constexpr (DUAL) a3 = group_sum<G>(a3);
+            if (live && gl == 0) {
+                if constexpr (MODE == AUV_SAME) {
+                    sp1[k - t0] = scale1 * cf * a1;
                 } else {
-                    for (int col = 2 * gl; col < ld; col += 2 * G) {
-                        double2 x = ld2(ui + col), y = ld2(vj + col), p = ld2(uj + col), q = ld2(vi + col);
-                        a1 = fma(x.x, y.x, a1); a1 = fma(x.y, y.y, a1);
-                        a2 = fma(p.x, q.x, a2); a2 = fma(p.y, q.y, a2);
-                        if constexpr (DUAL) { a3 = fma(q.x, y.x, a3); a3 = fma(q.y, y.y, a3); }
-                    }
-                    a1 = group_sum<G>(a1); a2 = group_sum<G>(a2);
-                    if constexpr (DUAL) a3 = group_sum<G>(a3);
-                    if (gl == 0) {
-                        sp1[k - t0] = scale1 * cf * (0.5 * a1 + 0.5 * a2);
-                        if constexpr (DUAL) sp2[k - t0] = scale2 * cf * a3;
-                    }
+                    sp1[k - t0] = scale1 * cf * (diag ? a1 : (0.5 * a1 + 0.5 * a2));
+                    if constexpr (DUAL) sp2[k - t0] = scale2 * cf * a3;
                 }
             }
         }

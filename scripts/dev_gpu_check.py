@@ -1,5 +1,6 @@
 """Development check on a GPU box: CUDA path vs the compiled reference (oracle/_ref) on small instances."""
-import os, sys, time, tempfile
+import os, sys, time, tempfile, functools
+print = functools.partial(print, flush=True)
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lorads_b200 import sdpa
@@ -55,7 +56,9 @@ def check(inst, bits=32, solve=True):
         print("  gpu solve:", {k: (f"{v:.8e}" if isinstance(v, float) else v) for k, v in sg.items()}, f"{tg:.2f}s")
 
 if __name__ == "__main__":
-    check(sdpa.maxcut(800, 19176, 1))
-    check(sdpa.matrix_completion(150, 150, 4000, 3, 7))
-    check(sdpa.lovasz_theta(120, 900, 5))
-    check(sdpa.maxcut(20000, 100000, 2), solve=False)
+    which = sys.argv[1] if len(sys.argv) > 1 else "mc800"
+    solve = "nosolve" not in sys.argv
+    if which == "mc800": check(sdpa.maxcut(800, 19176, 1), solve=solve)
+    if which == "mcomp": check(sdpa.matrix_completion(150, 150, 4000, 3, 7), solve=solve)
+    if which == "theta": check(sdpa.lovasz_theta(120, 900, 5), solve=solve)
+    if which == "mc20k": check(sdpa.maxcut(20000, 100000, 2), solve=False)
