@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- ALM inner iterations per second on the BASELINE.json MaxCut configuration.
+
+A *step* is one ALM inner iteration of the LoRADS hot path (L-BFGS direction, the fused A(sym(R D^T)) / A(D D^T)
+evaluation with objective, exact quartic line search, variable update, gradient 2 (C + A^*(w)) R, L-BFGS history
+update, A(R R^T) + primal infeasibility; reference src_semi/lorads_alg/lorads_alm.c:1073-1146) on the synthetic
+MaxCut SDP of BASELINE.json configs[1] (n = m = 100 000, 500 000 edges, seed 3, rank 24), at fixed rho from the
+reference's random start (srand(925)).
+
+  python bench.py --gpus N --steps K --warmup W                 our CUDA path (N > 1: launched under torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W  the reference's own CPU code on the host cores
+
+`value`   : iterations/s with everything resident in HBM (CUDA events on the solver's stream, max over ranks)
+`e2e`     : the same metric through the host-buffer C-ABI call lb2_alm_run_host (R and lambda copied host->device,
+            K iterations, R copied back; wall clock)
+`roofline`: the dominant kernel's algorithmic bytes / its CUDA-event launch time vs MEASURED_PEAKS.json
+`cpu_baseline`: the compiled reference (oracle/_ref) timed on this box's host cores on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(kind="maxcut", n=100_000, edges=500_000, seed=3)
+FALLBACK_HBM_GBS = 6650.0
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_instance():
+    from lorads_b200 import sdpa
+    return sdpa.maxcut(WORKLOAD["n"], WORKLOAD["edges"], WORKLOAD["seed"])
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def kernel_bytes(S) -> dict:
+    """Algorithmic (compulsory) bytes per launch of each hot kernel; formulas in DESIGN.md section 4."""
+    n, ld, m = S.dim(0), S.info(17), S.m
+    itAC, itA, nact = S.info(15), S.info(16), S.info(8)
+    npat, nadj, nnzA = S.info(4), S.info(14), S.info(12)
+    N = S.info(18)
+    return {
+        0: ("auv_items_kernel<DUAL> A(sym(RD^T)),A(DD^T)+obj", 2 * 8 * n * ld + 16 * itAC + 4 * (nact + 2) + 2 * 8 * (nact + 1)),
+        1: ("auv_items_kernel<SAME> A(RR^T)", 8 * n * ld + 16 * itA + 4 * (nact + 1) + 8 * nact),
+        2: ("wsum_kernel S=C+A^*(w)", npat * (8 + 8 + 4) + nnzA * (4 + 8 + 8)),
+        3: ("spmm_sym_kernel G=2SR", nadj * 8 + npat * 8 + 4 * (n + 1) + 2 * 8 * n * ld),
+        4: ("axpby_dot2_kernel (L-BFGS pass)", 4 * 8 * N),
+    }
+
+
+def cpu_reference_rate(inst, iters: int):
+    """ALM inner iterations/s of the compiled reference (oracle/_ref, 64-bit build) on this host; 1 thread."""
+    from lorads_b200 import sdpa
+    from oracle import ref
+    if not ref.available(64):
+        return None
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    d = tempfile.mkdtemp(prefix="lorads_bench_")
+    path = os.path.join(d, inst.name + ".dat-s")
+    sdpa.write_dat_s(inst, path)
+    R = ref.RefSolver(path, 64)
+    rho = R.dinfo(6)
+    sec = R.time_alm_inner_iters(rho, iters)
+    return iters / sec, sec, R.rank()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    inst = make_instance()
+    steps = max(1, min(args.steps, 30))
+    warm = min(args.warmup, 2)
+    t0 = time.time()
+    out = cpu_reference_rate(inst, warm + steps)
+    if out is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libloradsref64.so missing (build with make -C oracle ref where /root/reference exists)"}))
+        return 0
+    rate, sec, r = out
+    line = {
+        "impl": "reference", "metric": "alm_inner_iterations_per_second", "value": rate, "unit": "iterations/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 / rate, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"MaxCut SDP n=m={WORKLOAD['n']} edges={WORKLOAD['edges']} seed={WORKLOAD['seed']} rank={r} (BASELINE.json configs[1]); one step = one ALM inner iteration, lorads_alm.c:1073-1146"},
+        "cpu_baseline": {"value": rate, "unit": "iterations/s", "cores": 1, "kind": "reference",
+                         "sample": f"{warm + steps} inner iterations of the untouched reference (oracle/_ref, -DMAC_INT64, OpenBLAS 1 thread) from the srand(925) start, {sec:.1f} s; host has {os.cpu_count()} cores, the reference is single-threaded"},
+        "e2e": {"value": rate, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the LoRADS B200 kernel layer has no CPU fallback")
+    torch.cuda.set_device(local)
+    from lorads_b200.capi import Solver, load_library
+    import ctypes as C
+    comm = None
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        lib = load_library()
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            rc = lib.lb2_comm_unique_id(buf)
+            assert rc == 0, lib.lb2_last_error()
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        uid_bytes = bytes(uid.cpu().numpy().tobytes())
+        comm = (C.create_string_buffer(uid_bytes, 128), rank, world)
+
+    inst = make_instance()
+    t_setup = time.time()
+    S = Solver(inst, device=local, comm=comm)
+    t_setup = time.time() - t_setup
+    rho = S.dinfo(6)
+    n, r, m = S.dim(0), S.rank(0), S.m
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing ----------------
+    S.alm_prepare(rho)
+    S.time_alm_inner_iters(rho, max(3, args.warmup))
+    S.alm_prepare(rho)     # same start for every arm: ALG_START state of the random point advanced by the warm-up
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = S.launches
+    sec, done = S.time_alm_inner_iters(rho, args.steps)
+    launches = S.launches - l0
+    barrier()
+    clocks = sampler.stop()
+    if dist is not None:
+        t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    if done != args.steps:
+        log(f"warning: only {done} of {args.steps} iterations ran (line search reported no root)")
+    value = done / sec
+
+    # ---------------- end to end through host buffers ----------------
+    Rh = torch.empty(n * r, dtype=torch.float64).pin_memory().numpy()
+    Ro = torch.empty(n * r, dtype=torch.float64).pin_memory().numpy()
+    lam = torch.zeros(m, dtype=torch.float64).pin_memory().numpy()
+    Rh[:] = np.ascontiguousarray(S.get_factor("R").T).ravel() if world == 1 else 0.0
+    if world == 1:
+        S.alm_run_host(Rh, lam, rho, 3, Ro)        # warm
+        barrier()
+        t0 = time.perf_counter()
+        done_e, _ = S.alm_run_host(Rh, lam, rho, args.steps, Ro)
+        torch.cuda.synchronize()
+        e2e_sec = time.perf_counter() - t0
+        e2e = {"value": done_e / e2e_sec, "unit": "iterations/s",
+               "h2d_bytes_per_step": (Rh.nbytes + lam.nbytes) / max(done_e, 1), "d2h_bytes_per_step": Ro.nbytes / max(done_e, 1),
+               "note": "one lb2_alm_run_host call: R, lambda host->device, K iterations, R device->host; copies amortised over the K steps of the call"}
+    else:
+        e2e = {"value": None, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": "e2e is measured at N=1 only (column shards are per-rank host buffers)"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline of the hot kernels (cone 0, CUDA events, back-to-back launches) ----------------
+    peak, peak_src = measured_peak_gbs()
+    kb = kernel_bytes(S)
+    kt = {}
+    for which in kb:
+        kt[which] = S.bench_kernel(which, 50)
+    # per-iteration share: 1 dual pass, 1 A-only pass, 1 wsum, 1 spmm, ~6 BLAS-1 passes
+    mult = {0: 1, 1: 1, 2: 1, 3: 1, 4: 6}
+    share = {w: kt[w] * mult[w] for w in kt}
+    dom = max(share, key=share.get)
+    kernels = {kb[w][0]: {"ms": kt[w], "alg_bytes": kb[w][1], "gbs": kb[w][1] / (kt[w] * 1e-3) / 1e9,
+                          "frac_of_peak": kb[w][1] / (kt[w] * 1e-3) / 1e9 / peak,
+                          "share_of_step": share[w] / (1e3 * sec / done)} for w in kb}
+    achieved = kb[dom][1] / (kt[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": kb[dom][0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": kb[dom][1],
+                "launch_ms": kt[dom], "kernels": kernels}
+
+    # ---------------- CPU baseline (bounded sample) ----------------
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            out = cpu_reference_rate(inst, args.cpu_iters)
+            if out is not None:
+                rate, csec, _ = out
+                cpu = {"value": rate, "unit": "iterations/s", "cores": 1, "kind": "reference",
+                       "sample": f"{args.cpu_iters} inner iterations of the untouched reference (oracle/_ref, -DMAC_INT64, OpenBLAS 1 thread) on the same instance and start, {csec:.1f} s; host has {os.cpu_count()} cores, the reference is single-threaded"}
+        except Exception as e:  # the baseline must never take the bench line down
+            log("cpu baseline failed:", e)
+    if cpu is None:
+        cpu = {"value": None, "unit": "iterations/s", "cores": 1, "kind": "reference", "sample": "not run"}
+
+    line = {
+        "metric": "alm_inner_iterations_per_second", "value": value, "unit": "iterations/s", "n_gpus": world,
+        "steps": done, "warmup": max(3, args.warmup), "ms_per_step": 1e3 * sec / done, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"MaxCut SDP n=m={WORKLOAD['n']} edges={WORKLOAD['edges']} seed={WORKLOAD['seed']} rank={r} (BASELINE.json configs[1]); one step = one ALM inner iteration, lorads_alm.c:1073-1146",
+                   "l2": "no explicit flush: the step streams ~12 factor-sized vectors (19 MB each) plus 30 MB of index data (> 126 MB L2 in total)",
+                   "parallelism": "single GPU" if world == 1 else f"factor columns sharded over {world} GPUs, NCCL all-reduce per A() evaluation and per dot",
+                   "setup_seconds": t_setup},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-iters", type=int, default=12)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

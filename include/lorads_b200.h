@@ -120,11 +120,26 @@ void lb2_destroy(lb2_solver *s);
 int lb2_comm_unique_id(void *id128);
 int lb2_comm_init(lb2_solver *s, const void *id128, int rank, int world);
 
+/* ---- host-only pieces (no GPU needed; used by the CPU test-suite) -------------------------------- */
+/* The pre-solve of one cone on the host (what lb2_preprocess runs before uploading).
+ * info[0]=|P| (or n(n+1)/2) info[1]=dense scratch? info[2]=dense-constraint cone? info[3]=active constraints
+ * info[4]=nnzA info[5]=nnzC info[6]=non-zero constraint matrices info[7]=#rows split over A(UV^T) tiles.
+ * rows/cols (capacity >= |P|, may be NULL) receive the union pattern of a sparse-scratch cone. */
+int lb2_host_presolve(lb2_int n, lb2_int m, const lb2_int *coneMatBeg, const lb2_int *coneMatIdx,
+                      const double *coneMatElem, lb2_int *info, lb2_int *rows, lb2_int *cols);
+/* ALMLineSearch (lorads_alm.c:161-228) from its five m-vector sums {|q2|^2, q1.q2, q0.q2, |q1|^2, q0.q1};
+ * returns rootNum, *tau is in/out exactly as in the reference. */
+lb2_int lb2_host_line_search(double rho, const double *sums, double p1, double p2, double *tau);
+/* LORADSDetermineRank rule for one cone (lorads_solver.c:290-319); returns the rank, *rankMax the cap. */
+lb2_int lb2_host_rank_rule(lb2_int n, lb2_int nNonzeroCoeff, lb2_int nCones, double timesLogRank, lb2_int *rankMax);
+
 /* ---- queries ------------------------------------------------------------------------------ */
 /* what: 0 nRows, 1 nCones, 2 blkDim, 3 rank, 4 |P| (pattern entries; n(n+1)/2 on the dense path),
  *       5 1 if the cone is a "dense-constraint cone" (> 30% of rows touch it, lorads_user_data.c:68-70)
  *       6 1 if the cone uses the dense scratch path, 7 nnz of the cone, 8 active constraints of the cone,
- *       9 rank_max, 10 local rank (column shard) , 11 kernel launches so far, 12 nnzA, 13 nnzC */
+ *       9 rank_max, 10 local rank (column shard) , 11 kernel launches so far, 12 nnzA, 13 nnzC,
+ *       14 adjacency entries (2|P| - #diag), 15 items of [A;C], 16 items of A, 17 padded row length ld,
+ *       18 length N of the concatenated factor vectors */
 lb2_int lb2_info(const lb2_solver *s, int what, lb2_int iCone);
 /* what: 0 cObjNrm1, 1 cObjNrm2, 2 cObjNrmInf, 3 bNrm1, 4 bNrm2, 5 bNrmInf, 6 rho0, 7 pObj, 8 dObj,
  *       9 pinf(1), 10 gap, 11 dinf(1), 12 scaleObjHis */
@@ -162,6 +177,18 @@ int lb2_alm_prepare(lb2_solver *s, double rho, double *lagNormSquare);
 int lb2_alm_inner_iter(lb2_solver *s, double rho, lb2_int lbfgsCounter, double *out, lb2_int *rootNum);
 /* `iters` inner iterations back to back, device resident; seconds = CUDA-event time of the loop. */
 int lb2_time_alm_inner_iters(lb2_solver *s, double rho, lb2_int iters, double *out, double *seconds);
+
+/* Host-buffer form of the ALM inner loop, the shape a LORADS_ALMOptimize call has for the reference driver:
+ * R (all cones, column-major, concatenated) and lambda come from HOST memory, `iters` inner iterations run at
+ * fixed rho starting from ALG_START, and R is copied back.  Used for the end-to-end (e2e) benchmark number.
+ * out[0..4] as lb2_alm_inner_iter, out[5] = iterations actually done. */
+int lb2_alm_run_host(lb2_solver *s, const double *R_in, const double *lambda_in, double rho, lb2_int iters,
+                     double *R_out, double *out);
+/* Times `reps` back-to-back launches of one hot kernel with CUDA events on the solver's stream (cone 0).
+ * which: 0 A(UV^T) dual pass (R,D)+(D,D) with objective, 1 A(RR^T) constraints only, 2 S = C + A^*(w),
+ *        3 Y = 2 S R (+ sum Y.Y), 4 one fused BLAS-1 pass (axpby + dot) over the factor vector.
+ * ms = average milliseconds per launch. */
+int lb2_bench_kernel(lb2_solver *s, int which, lb2_int reps, double *ms);
 
 /* ---- phases (host control flow feeding on device-computed scalars) --------------------------- */
 /* LORADS_ALMOptimize (lorads_alm.c:991) */

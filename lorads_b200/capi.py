@@ -51,8 +51,8 @@ EXPORTS = [
     "lb2_determine_rank", "lb2_init_vars", "lb2_destroy", "lb2_comm_unique_id", "lb2_comm_init", "lb2_info", "lb2_dinfo",
     "lb2_get_pattern", "lb2_set_factor", "lb2_get_factor", "lb2_set_vec", "lb2_get_vec", "lb2_auv", "lb2_wsum_mulrk",
     "lb2_alm_cal_grad", "lb2_cg_matvec", "lb2_update_sdp_var_one", "lb2_alm_prepare", "lb2_alm_inner_iter",
-    "lb2_time_alm_inner_iters", "lb2_alm_optimize", "lb2_alm_to_admm", "lb2_admm_optimize", "lb2_dual_infeasibility",
-    "lb2_solve", "lb2_get_solution",
+    "lb2_time_alm_inner_iters", "lb2_alm_run_host", "lb2_bench_kernel", "lb2_alm_optimize", "lb2_alm_to_admm", "lb2_admm_optimize", "lb2_dual_infeasibility",
+    "lb2_solve", "lb2_get_solution", "lb2_host_presolve", "lb2_host_line_search", "lb2_host_rank_rule",
 ]
 
 _lib = None
@@ -97,12 +97,19 @@ def load_library():
     lib.lb2_alm_prepare.argtypes = [C.c_void_p, C.c_double, _dp]
     lib.lb2_alm_inner_iter.argtypes = [C.c_void_p, C.c_double, C.c_int64, _dp, _ip]
     lib.lb2_time_alm_inner_iters.argtypes = [C.c_void_p, C.c_double, C.c_int64, _dp, _dp]
+    lib.lb2_alm_run_host.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_int64, _dp, _dp]
+    lib.lb2_bench_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp]
     lib.lb2_alm_optimize.argtypes = [C.c_void_p, C.POINTER(Params), C.c_double]
     lib.lb2_alm_to_admm.argtypes = [C.c_void_p, C.POINTER(Params)]
     lib.lb2_admm_optimize.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int64, C.c_double]
     lib.lb2_dual_infeasibility.argtypes = [C.c_void_p]
     lib.lb2_solve.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Result)]
     lib.lb2_get_solution.argtypes = [C.c_void_p, C.c_int64, _dp, _dp]
+    lib.lb2_host_presolve.argtypes = [C.c_int64, C.c_int64, _ip, _ip, _dp, _ip, _ip, _ip]
+    lib.lb2_host_line_search.restype = C.c_int64
+    lib.lb2_host_line_search.argtypes = [C.c_double, _dp, C.c_double, C.c_double, _dp]
+    lib.lb2_host_rank_rule.restype = C.c_int64
+    lib.lb2_host_rank_rule.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_double, _ip]
     _lib = lib
     return lib
 
@@ -125,6 +132,39 @@ def _i(a):
 
 class Lb2Error(RuntimeError):
     pass
+
+
+def host_presolve(cone, m: int):
+    """Host-only pre-solve of one cone: returns (info dict, pattern rows, pattern cols)."""
+    lib = load_library()
+    info = np.zeros(8, np.int64)
+    beg = np.ascontiguousarray(cone.beg, dtype=np.int64)
+    idx = np.ascontiguousarray(cone.idx, dtype=np.int64)
+    elem = np.ascontiguousarray(cone.elem, dtype=np.float64)
+    rc = lib.lb2_host_presolve(cone.n, m, _i(beg), _i(idx), _d(elem), _i(info), None, None)
+    if rc != 0:
+        raise Lb2Error(lib.lb2_last_error().decode())
+    rows = np.zeros(int(info[0]) if not info[1] else 0, np.int64)
+    cols = np.zeros_like(rows)
+    if not info[1]:
+        lib.lb2_host_presolve(cone.n, m, _i(beg), _i(idx), _d(elem), _i(info), _i(rows), _i(cols))
+    keys = ["psize", "dense_path", "dense_cone", "n_act", "nnzA", "nnzC", "n_nonzero_coeff", "n_split_rows"]
+    return dict(zip(keys, info.tolist())), rows, cols
+
+
+def host_line_search(rho: float, sums, p1: float, p2: float, tau0: float = 0.0):
+    lib = load_library()
+    sums = np.ascontiguousarray(sums, dtype=np.float64)
+    tau = C.c_double(tau0)
+    root = lib.lb2_host_line_search(rho, _d(sums), p1, p2, C.byref(tau))
+    return int(root), tau.value
+
+
+def host_rank_rule(n: int, n_nonzero_coeff: int, n_cones: int, times_log_rank: float = 2.0):
+    lib = load_library()
+    cap = C.c_int64(0)
+    r = lib.lb2_host_rank_rule(n, n_nonzero_coeff, n_cones, times_log_rank, C.byref(cap))
+    return int(r), int(cap.value)
 
 
 class Solver:
@@ -255,11 +295,23 @@ class Solver:
         self._ck(self.lib.lb2_alm_inner_iter(self.h, rho, counter, _d(out), C.byref(root)))
         return root.value, dict(tau=out[0], lag_norm_sq=out[1], pinf=out[2], p1=out[3], p2=out[4])
 
-    def time_alm_inner_iters(self, rho: float, iters: int) -> float:
+    def time_alm_inner_iters(self, rho: float, iters: int):
+        """Returns (seconds by CUDA events, iterations actually done)."""
         out = np.zeros(8)
         sec = C.c_double(0.0)
         self._ck(self.lib.lb2_time_alm_inner_iters(self.h, rho, iters, _d(out), C.byref(sec)))
-        return sec.value
+        return sec.value, int(out[5])
+
+    def alm_run_host(self, R_in: np.ndarray, lam_in: np.ndarray, rho: float, iters: int, R_out: np.ndarray):
+        """R_in / R_out: flat column-major concatenation over cones (host, ideally pinned)."""
+        out = np.zeros(8)
+        self._ck(self.lib.lb2_alm_run_host(self.h, _d(R_in), _d(lam_in), rho, iters, _d(R_out), _d(out)))
+        return int(out[5]), out
+
+    def bench_kernel(self, which: int, reps: int) -> float:
+        ms = C.c_double(0.0)
+        self._ck(self.lib.lb2_bench_kernel(self.h, which, reps, C.byref(ms)))
+        return ms.value
 
     # ---- phases
     def solve(self, params: Params | None = None) -> dict:

@@ -126,6 +126,32 @@ int lb2_comm_init(lb2_solver *s, const void *id128, int rank, int world) {
     LB2_CATCH
 }
 
+int lb2_host_presolve(lb2_int n, lb2_int m, const lb2_int *beg, const lb2_int *idx, const double *elem, lb2_int *info,
+                      lb2_int *rows, lb2_int *cols) {
+    if (!beg || !info || n <= 0 || m <= 0) { g_err = "lb2_host_presolve: bad argument"; return LB2_ERR_ARG; }
+    LB2_TRY
+    ConeLayout L = build_cone_layout(n, m, beg, idx, elem);
+    info[0] = L.psize(); info[1] = L.dense_path; info[2] = L.dense_cone; info[3] = L.n_act;
+    info[4] = L.nnzA; info[5] = L.nnzC; info[6] = L.n_nonzero_coeff; info[7] = (lb2_int)L.listAC.split_row.size();
+    if (!L.dense_path && rows && cols)
+        for (size_t p = 0; p < L.P_row.size(); ++p) { rows[p] = L.P_row[p]; cols[p] = L.P_col[p]; }
+    LB2_CATCH
+}
+
+lb2_int lb2_host_line_search(double rho, const double *sums, double p1, double p2, double *tau) {
+    return line_search(rho, sums, p1, p2, tau);
+}
+
+lb2_int lb2_host_rank_rule(lb2_int n, lb2_int nnzRows, lb2_int nCones, double timesRank, lb2_int *rankMax) {
+    const long long cap = std::min<long long>((long long)std::sqrt((double)(2 * nnzRows)) + 1, n);
+    long long r;
+    if (timesRank <= 1e-6) r = cap;
+    else if (nnzRows / n >= 20 && n <= 400 && nCones <= 3) r = cap;
+    else r = (long long)std::min<double>(std::ceil(timesRank * std::log((double)n)), (double)cap);
+    if (rankMax) *rankMax = cap;
+    return std::max<long long>(1, r);
+}
+
 lb2_int lb2_info(const lb2_solver *s, int what, lb2_int c) {
     if (!s) return -1;
     const Solver &S = s->impl;
@@ -149,6 +175,11 @@ lb2_int lb2_info(const lb2_solver *s, int what, lb2_int c) {
     case 10: return K.r;
     case 12: return K.nnzA;
     case 13: return K.nnzC;
+    case 14: return K.dense_path ? 0 : (long long)K.adj_col.n;
+    case 15: return K.listAC.dev.n_items;
+    case 16: return K.listA.dev.n_items;
+    case 17: return K.ld;
+    case 18: return S.N;
     }
     return -1;
 }
@@ -285,13 +316,16 @@ int lb2_time_alm_inner_iters(lb2_solver *s, double rho, lb2_int iters, double *o
     cudaEvent_t e0, e1;
     LB2_CUDA(cudaEventCreate(&e0)); LB2_CUDA(cudaEventCreate(&e1));
     LB2_CUDA(cudaEventRecord(e0, S.ctx.stream));
-    double tau = 0.0, p12[2], lag = 0, pinf = 0;
+    double tau = 0.0, p12[2] = {0, 0}, lag = 0, pinf = 0;
+    lb2_int done = 0;
     for (lb2_int k = 0; k < iters; ++k) {
         long long rn = 0;
         S.alm_inner_front(rho, k, &tau, p12, &rn);
         if (rn == 0) break;
         S.alm_inner_back(rho, tau, &lag, &pinf);
+        done++;
     }
+    out[5] = (double)done;
     LB2_CUDA(cudaEventRecord(e1, S.ctx.stream));
     LB2_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
@@ -299,6 +333,67 @@ int lb2_time_alm_inner_iters(lb2_solver *s, double rho, lb2_int iters, double *o
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     out[0] = tau; out[1] = lag; out[2] = pinf; out[3] = p12[0]; out[4] = p12[1];
     *seconds = ms * 1e-3;
+    LB2_CATCH
+}
+
+int lb2_alm_run_host(lb2_solver *s, const double *R_in, const double *lambda_in, double rho, lb2_int iters,
+                     double *R_out, double *out) {
+    if (!s || !R_in || !lambda_in || !R_out || !out) return LB2_ERR_ARG;
+    LB2_TRY
+    Solver &S = s->impl;
+    size_t off = 0;
+    for (long long c = 0; c < S.nCones; ++c) {
+        S.upload_factor(S.R.p, S.cones[c], R_in + off);
+        off += (size_t)(S.blkDims[c] * S.rank[c]);
+    }
+    LB2_CUDA(cudaMemcpyAsync(S.lam.p, lambda_in, sizeof(double) * S.m, cudaMemcpyHostToDevice, S.ctx.stream));
+    S.init_constr_val_all(S.R.p, S.R.p, true);
+    S.constr_val_sum();
+    S.cal_grad(rho);
+    double tau = 0.0, p12[2] = {0, 0}, lag = 0, pinf = 0;
+    lb2_int done = 0;
+    for (lb2_int k = 0; k < iters; ++k) {
+        long long rn = 0;
+        S.alm_inner_front(rho, k, &tau, p12, &rn);
+        if (rn == 0) break;
+        S.alm_inner_back(rho, tau, &lag, &pinf);
+        done++;
+    }
+    off = 0;
+    for (long long c = 0; c < S.nCones; ++c) {
+        S.download_factor(S.R.p, S.cones[c], R_out + off);
+        off += (size_t)(S.blkDims[c] * S.rank[c]);
+    }
+    out[0] = tau; out[1] = lag; out[2] = pinf; out[3] = p12[0]; out[4] = p12[1]; out[5] = (double)done;
+    LB2_CATCH
+}
+
+int lb2_bench_kernel(lb2_solver *s, int which, lb2_int reps, double *ms) {
+    if (!s || !ms || reps < 1) return LB2_ERR_ARG;
+    LB2_TRY
+    Solver &S = s->impl;
+    ConeDev &K = S.cones.at(0);
+    cudaEvent_t e0, e1;
+    LB2_CUDA(cudaEventCreate(&e0)); LB2_CUDA(cudaEventCreate(&e1));
+    auto once = [&]() {
+        switch (which) {
+        case 0: S.cone_auv_dual(K, S.R.p, S.U.p, K.t1.p, K.t2.p); break;
+        case 1: S.cone_auv(K, false, S.R.p, S.R.p, true, 1.0, K.cv.p); break;
+        case 2: S.cone_wsum(K, S.M1.p, false, true); break;
+        case 3: S.cone_mul(K, S.R.p, 2.0, 0.0, nullptr, nullptr, S.G.p, S.S.p + kNumSlots); break;
+        case 4: launch_axpby_dot(S.ctx, S.N, S.Dtemp.p, coef_const(1.0), S.G.p, coef_const(-0.5), S.V.p, S.R.p, S.S.p, SL_T1, false); break;
+        default: throw std::invalid_argument("unknown kernel id");
+        }
+    };
+    for (int w = 0; w < 3; ++w) once();
+    LB2_CUDA(cudaEventRecord(e0, S.ctx.stream));
+    for (lb2_int k = 0; k < reps; ++k) once();
+    LB2_CUDA(cudaEventRecord(e1, S.ctx.stream));
+    LB2_CUDA(cudaEventSynchronize(e1));
+    float t = 0;
+    LB2_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms = (double)t / (double)reps;
     LB2_CATCH
 }
 

@@ -110,8 +110,19 @@ void Solver::preprocess() {
     }
     cObjNrm2 = std::sqrt(n2);
     bNrm1 = 0; bNrmInf = 0; double b2 = 0;
-    for (double v : b_h) { bNrm1 += std::fabs(v); bNrmInf = std::max(bNrmInf, std::fabs(v)); b2 += v * v; }
+    for (double v : b_h) { bNrm1 += std::fabs(v); b2 += v * v; }
     bNrm2 = std::sqrt(b2);
+    {
+        // cal_sdp_const, lorads_solver.c:1059-1066.  The reference's Linux build (-DUNDER_BLAS) indexes rowRHS
+        // with the 1-based result of Fortran idamax_, i.e. it reads the element AFTER the first entry of largest
+        // magnitude.  The value only scales the reported / tested "Inf" infeasibility, but it steers the phase
+        // exits, so it is reproduced here (clamped to the last element); see DESIGN.md "reference quirks".
+        long long arg = 0;
+        double best = -1.0;
+        for (long long i = 0; i < m; ++i)
+            if (std::fabs(b_h[i]) > best) { best = std::fabs(b_h[i]); arg = i; }
+        bNrmInf = std::fabs(b_h[std::min<long long>(arg + 1, m - 1)]);
+    }
     single_identity = (nCones == 1 && cones[0].identity_act);
     b.alloc((size_t)m + 1); lam.alloc((size_t)m + 1); s.alloc((size_t)m + 1); q1.alloc((size_t)m + 1);
     q2.alloc((size_t)m + 1); M1.alloc((size_t)m + 1); cvfull.alloc((size_t)m + 1);
@@ -124,13 +135,8 @@ void Solver::determine_rank(double timesRank) {
     if (!preprocessed) throw std::logic_error("preprocess first");
     rank.assign(nCones, 1); rank_max.assign(nCones, 1);
     for (long long c = 0; c < nCones; ++c) {
-        const long long nnzRows = cones[c].n_nonzero_coeff, n = blkDims[c];
-        const long long cap = std::min<long long>((long long)std::sqrt((double)(2 * nnzRows)) + 1, n);
-        long long r;
-        if (timesRank <= 1e-6) r = cap;
-        else if (nnzRows / n >= 20 && n <= 400 && nCones <= 3) r = cap;
-        else r = (long long)std::min<double>(std::ceil(timesRank * std::log((double)n)), (double)cap);
-        rank[c] = std::max<long long>(1, r);
+        lb2_int cap = 0;
+        rank[c] = lb2_host_rank_rule(blkDims[c], cones[c].n_nonzero_coeff, nCones, timesRank, &cap);
         rank_max[c] = cap;
     }
 }

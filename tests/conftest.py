@@ -1,0 +1,45 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+GOLDEN_CASES = ["maxcut_n120", "maxcut_n800", "mcomp_60x50", "theta_n60", "twoblock"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def load_golden(name):
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    meta = json.loads(str(g["meta"]))
+    sys.path.insert(0, GOLDEN_DIR)
+    from make_golden import build_instance  # the generator script also knows how to rebuild the instance
+    inst = build_instance(meta["kind"], meta["kw"])
+    return g, inst
+
+
+@pytest.fixture(scope="session", params=GOLDEN_CASES)
+def golden(request):
+    return (request.param,) + load_golden(request.param)
+
+
+def have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
