@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -251,7 +251,7 @@ def run_ours(args):
     kb = kernel_bytes(S)
     kt = {}
     for which in kb:
-        kt[which] = S.bench_kernel(which, 50)
+        kt[which] = S.bench_kernel(which, 200)
     # per-iteration share: 1 dual pass, 1 A-only pass, 1 wsum, 1 spmm, ~6 BLAS-1 passes
     mult = {0: 1, 1: 1, 2: 1, 3: 1, 4: 6}
     share = {w: kt[w] * mult[w] for w in kt}
@@ -297,8 +297,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-iters", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -201,6 +201,18 @@ int lb2_admm_optimize(lb2_solver *s, lb2_params *p, lb2_int iterCelling, double 
 int lb2_dual_infeasibility(lb2_solver *s);
 /* The whole driver sequence of main.c:321-487 (ALM, ALM->ADMM, ADMM, reopt rounds, dual infeasibility). */
 int lb2_solve(lb2_solver *s, lb2_params *p, lb2_result *res);
+/* reopt (lorads_solver.c:1075-1117): rescale C and lambda by *reoptParam, re-enter ALM (reopt variant) and ADMM. */
+int lb2_reopt(lb2_solver *s, lb2_params *p, double *reoptParam, lb2_int *reoptAlmIter, lb2_int *reoptAdmmIter,
+              double timeSolveStart, int *admmBadIterFlag, int reoptLevel, double *seconds);
+/* averageUV for every cone (lorads_admm.c:310) and copyRtoV (lorads_alg_common.c:160), on the device state */
+int lb2_average_uv(lb2_solver *s);
+int lb2_copy_r_to_v(lb2_solver *s);
+/* The iteration state the reference keeps in lorads_alm_state / lorads_admm_state (def_lorads_solver.h:130-161),
+ * flattened in declaration order.  alm[13]: outerIter, innerIter, rho, pinf_inf, pinf_1, pinf_2, gap, pobj, dobj,
+ * dinf_inf, dinf_1, dinf_2, tau.  admm[13]: iter, nBlks, cg_iter, rho, dinf_1, dinf_inf, pinf_1, pinf_inf, pinf_2,
+ * dinf_2, pobj, dobj, gap.  set copies caller-side edits (main.c:404-410) back before the next phase call. */
+int lb2_get_state(const lb2_solver *s, double *alm13, double *admm13);
+int lb2_set_state(lb2_solver *s, const double *alm13, const double *admm13);
 /* copies the current primal factor R (n x r col-major) and the dual vector to the host */
 int lb2_get_solution(const lb2_solver *s, lb2_int iCone, double *R, double *dualVar);
 

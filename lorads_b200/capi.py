@@ -52,7 +52,7 @@ EXPORTS = [
     "lb2_get_pattern", "lb2_set_factor", "lb2_get_factor", "lb2_set_vec", "lb2_get_vec", "lb2_auv", "lb2_wsum_mulrk",
     "lb2_alm_cal_grad", "lb2_cg_matvec", "lb2_update_sdp_var_one", "lb2_alm_prepare", "lb2_alm_inner_iter",
     "lb2_time_alm_inner_iters", "lb2_alm_run_host", "lb2_bench_kernel", "lb2_alm_optimize", "lb2_alm_to_admm", "lb2_admm_optimize", "lb2_dual_infeasibility",
-    "lb2_solve", "lb2_get_solution", "lb2_host_presolve", "lb2_host_line_search", "lb2_host_rank_rule",
+    "lb2_solve", "lb2_get_solution", "lb2_reopt", "lb2_average_uv", "lb2_copy_r_to_v", "lb2_get_state", "lb2_set_state", "lb2_host_presolve", "lb2_host_line_search", "lb2_host_rank_rule",
 ]
 
 _lib = None

@@ -467,60 +467,57 @@ static void jacobi_eig(int k, std::vector<double> &a, std::vector<double> &q) {
 }
 
 void Solver::dual_infeasibility() {
-    // calculate_dual_infeasibility_solver, lorads_solver.c:1007-1037
+    // calculate_dual_infeasibility_solver, lorads_solver.c:1007-1037.  The Lanczos basis, the mat-vec
+    // (S = C - A^*(lambda) on the pattern) and the re-orthogonalisation all stay on the device; per Lanczos step
+    // the host reads two scalars (alpha, |w|^2) and solves the small tridiagonal eigenproblem per restart cycle.
     launch_axpby_dot(ctx, m, M1.p, coef_const(-1.0), lam.p, coef_const(0.0), nullptr, nullptr, S.p, SL_T1, false);
     double total = 0.0;
     for (long long c = 0; c < nCones; ++c) {
         ConeDev &K = cones[c];
         cone_wsum(K, M1.p, false, true);
         const long long n = K.n;
-        int kdim = (40 > n) ? 2 : 40;
+        int kdim = (40 > n) ? 2 : 40;       // dual_infeasible: ncv = 40, or 2 when ncv > n (lorads_sdp_conic.c:1288-1294)
         if (kdim > n) kdim = (int)n;
-        const int ld = 4;
-        // device work: basis vectors stored as n x 4 row-major "factors" with one live column
-        DBuf<double> x, y;
-        x.alloc((size_t)n * ld); y.alloc((size_t)n * ld);
-        std::vector<double> hx((size_t)n * ld, 0.0), hy((size_t)n * ld);
-        std::vector<std::vector<double>> Vb;
-        std::vector<double> alpha, beta;
+        const long long np2 = (n + 1) & ~1LL;            // even stride keeps every basis vector 16-byte aligned
+        DBuf<double> Vb, w, x0;
+        Vb.alloc((size_t)np2 * (kdim + 1)); w.alloc((size_t)np2); x0.alloc((size_t)np2);
         std::vector<double> v0((size_t)n);
         uint64_t st = 0x9E3779B97F4A7C15ull;
+        double nr0 = 0.0;
         for (long long i = 0; i < n; ++i) {
             st = st * 6364136223846793005ull + 1442695040888963407ull;
             v0[(size_t)i] = ((double)(st >> 11) / 9007199254740992.0) - 0.5;
+            nr0 += v0[(size_t)i] * v0[(size_t)i];
         }
-        auto nrm = [&](const std::vector<double> &v) { double t = 0; for (double e : v) t += e * e; return std::sqrt(t); };
-        auto matvec = [&](const std::vector<double> &in, std::vector<double> &out) {
-            for (long long i = 0; i < n; ++i) hx[(size_t)i * ld] = in[(size_t)i];
-            LB2_CUDA(cudaMemcpyAsync(x.p, hx.data(), sizeof(double) * hx.size(), cudaMemcpyHostToDevice, ctx.stream));
-            if (K.dense_path) launch_dense_symm(ctx, n, 1, ld, K.S.p, x.p, 1.0, 0.0, nullptr, nullptr, y.p, nullptr);
-            else launch_spmm(ctx, n, ld, K.adj_ptr.p, K.adj_col.p, K.adj_pos.p, K.S.p, x.p, 1.0, 0.0, nullptr, nullptr, y.p, nullptr);
-            LB2_CUDA(cudaMemcpyAsync(hy.data(), y.p, sizeof(double) * hy.size(), cudaMemcpyDeviceToHost, ctx.stream));
-            sync();
-            out.resize((size_t)n);
-            for (long long i = 0; i < n; ++i) out[(size_t)i] = hy[(size_t)i * ld];
+        nr0 = std::sqrt(nr0);
+        for (double &e : v0) e /= nr0;
+        LB2_CUDA(cudaMemcpyAsync(Vb.p, v0.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx.stream));
+        auto vec = [&](int l) { return Vb.p + (size_t)l * np2; };
+        auto matvec = [&](const double *in, double *out) {
+            if (K.dense_path) launch_dense_symv(ctx, n, K.S.p, in, out);
+            else launch_spmv_sym(ctx, n, K.adj_ptr.p, K.adj_col.p, K.adj_pos.p, K.S.p, in, out);
         };
         double theta = 0.0;
         const double tol = 1e-2;
-        double nr0 = nrm(v0);
-        for (double &e : v0) e /= nr0;
+        std::vector<double> alpha, beta;
         for (int cycle = 0; cycle < 600; ++cycle) {
-            Vb.assign(1, v0); alpha.clear(); beta.clear();
-            std::vector<double> w;
+            alpha.clear(); beta.clear();
             bool done = false;
             for (int j = 0; j < kdim; ++j) {
-                matvec(Vb[j], w);
-                double a = 0; for (long long i = 0; i < n; ++i) a += Vb[j][(size_t)i] * w[(size_t)i];
-                alpha.push_back(a);
-                for (long long i = 0; i < n; ++i) w[(size_t)i] -= a * Vb[j][(size_t)i];
-                if (j > 0) for (long long i = 0; i < n; ++i) w[(size_t)i] -= beta[j - 1] * Vb[j - 1][(size_t)i];
-                for (int pass = 0; pass < 2; ++pass)
+                matvec(vec(j), w.p);
+                launch_dot(ctx, n, vec(j), w.p, S.p, SL_T0);                       // alpha_j
+                launch_axpby_dot(ctx, n, w.p, coef_const(1.0), w.p, coef_slot(SL_T0, -1.0), vec(j), nullptr, S.p, SL_T1, false);
+                if (j > 0)
+                    launch_axpby_dot(ctx, n, w.p, coef_const(1.0), w.p, coef_const(-beta[j - 1]), vec(j - 1), nullptr, S.p, SL_T1, false);
+                for (int pass = 0; pass < 2; ++pass)                               // full re-orthogonalisation
                     for (int l = 0; l <= j; ++l) {
-                        double cdot = 0; for (long long i = 0; i < n; ++i) cdot += Vb[l][(size_t)i] * w[(size_t)i];
-                        for (long long i = 0; i < n; ++i) w[(size_t)i] -= cdot * Vb[l][(size_t)i];
+                        launch_dot(ctx, n, vec(l), w.p, S.p, SL_T1);
+                        launch_axpby_dot(ctx, n, w.p, coef_const(1.0), w.p, coef_slot(SL_T1, -1.0), vec(l), nullptr, S.p, SL_DG, false);
                     }
-                double bb = nrm(w);
-                beta.push_back(bb);
+                launch_dot(ctx, n, w.p, w.p, S.p, SL_T1);
+                read_slots();
+                const double a = S_host[SL_T0], bb = std::sqrt(S_host[SL_T1]);
+                alpha.push_back(a); beta.push_back(bb);
                 const int mdim = j + 1;
                 const bool breakdown = bb < 1e-14 * (std::fabs(a) + 1.0);
                 if (mdim == kdim || breakdown) {
@@ -536,16 +533,16 @@ void Solver::dual_infeasibility() {
                     const double est = std::fabs(bb * Q[(size_t)(mdim - 1) * mdim + best]);
                     const double scale = std::max(std::fabs(theta), 2.2e-16);
                     if (breakdown || est <= tol * scale || mdim >= n) { done = true; break; }
-                    std::vector<double> xr((size_t)n, 0.0);
+                    // explicit restart from the Ritz vector
+                    LB2_CUDA(cudaMemsetAsync(x0.p, 0, sizeof(double) * np2, ctx.stream));
                     for (int l = 0; l < mdim; ++l)
-                        for (long long i = 0; i < n; ++i) xr[(size_t)i] += Q[(size_t)l * mdim + best] * Vb[l][(size_t)i];
-                    double nx = nrm(xr);
-                    for (double &e : xr) e /= nx;
-                    v0 = xr;
+                        launch_axpby_dot(ctx, n, x0.p, coef_const(1.0), x0.p, coef_const(Q[(size_t)l * mdim + best]), vec(l), nullptr, S.p, SL_DG, false);
+                    launch_dot(ctx, n, x0.p, x0.p, S.p, SL_T1);
+                    read_slots();
+                    launch_axpby_dot(ctx, n, vec(0), coef_const(1.0 / std::sqrt(S_host[SL_T1])), x0.p, coef_const(0.0), nullptr, nullptr, S.p, SL_DG, false);
                     break;
                 }
-                for (double &e : w) e /= bb;
-                Vb.push_back(w);
+                launch_axpby_dot(ctx, n, vec(j + 1), coef_const(1.0 / bb), w.p, coef_const(0.0), nullptr, nullptr, S.p, SL_DG, false);
             }
             if (done) break;
         }

@@ -417,6 +417,57 @@ int lb2_solve(lb2_solver *s, lb2_params *p, lb2_result *res) {
     s->impl.solve(p, res);
     LB2_CATCH
 }
+int lb2_reopt(lb2_solver *s, lb2_params *p, double *reoptParam, lb2_int *almIter, lb2_int *admmIter, double timeSolveStart,
+              int *badFlag, int level, double *seconds) {
+    if (!s || !p || !reoptParam || !almIter || !admmIter || !badFlag) return LB2_ERR_ARG;
+    LB2_TRY
+    long long a = *almIter, b = *admmIter;
+    double t = s->impl.reopt(p, reoptParam, &a, &b, timeSolveStart, badFlag, level);
+    if (seconds) *seconds = t;
+    LB2_CATCH
+}
+int lb2_average_uv(lb2_solver *s) { if (!s) return LB2_ERR_ARG; LB2_TRY s->impl.average_uv(); s->impl.sync(); LB2_CATCH }
+int lb2_copy_r_to_v(lb2_solver *s) {
+    if (!s) return LB2_ERR_ARG;
+    LB2_TRY
+    Solver &S = s->impl;
+    LB2_CUDA(cudaMemcpyAsync(S.V.p, S.R.p, sizeof(double) * S.N, cudaMemcpyDeviceToDevice, S.ctx.stream));
+    S.sync();
+    LB2_CATCH
+}
+int lb2_get_state(const lb2_solver *s, double *a, double *d) {
+    if (!s) return LB2_ERR_ARG;
+    const Solver &S = s->impl;
+    if (a) {
+        const AlmState &x = S.alm;
+        double v[13] = {(double)x.outerIter, (double)x.innerIter, x.rho, x.pinf_inf, x.pinf_1, x.pinf_2, x.gap, x.pobj, x.dobj,
+                        x.dinf_inf, x.dinf_1, x.dinf_2, x.tau};
+        std::memcpy(a, v, sizeof(v));
+    }
+    if (d) {
+        const AdmmState &x = S.admm;
+        double v[13] = {(double)x.iter, (double)x.nBlks, (double)x.cg_iter, x.rho, x.dinf_1, x.dinf_inf, x.pinf_1, x.pinf_inf,
+                        x.pinf_2, x.dinf_2, x.pobj, x.dobj, x.gap};
+        std::memcpy(d, v, sizeof(v));
+    }
+    return LB2_OK;
+}
+int lb2_set_state(lb2_solver *s, const double *a, const double *d) {
+    if (!s) return LB2_ERR_ARG;
+    Solver &S = s->impl;
+    if (a) {
+        AlmState &x = S.alm;
+        x.outerIter = (long long)a[0]; x.innerIter = (long long)a[1]; x.rho = a[2]; x.pinf_inf = a[3]; x.pinf_1 = a[4];
+        x.pinf_2 = a[5]; x.gap = a[6]; x.pobj = a[7]; x.dobj = a[8]; x.dinf_inf = a[9]; x.dinf_1 = a[10]; x.dinf_2 = a[11]; x.tau = a[12];
+    }
+    if (d) {
+        AdmmState &x = S.admm;
+        x.iter = (long long)d[0]; x.nBlks = (long long)d[1]; x.cg_iter = (long long)d[2]; x.rho = d[3]; x.dinf_1 = d[4];
+        x.dinf_inf = d[5]; x.pinf_1 = d[6]; x.pinf_inf = d[7]; x.pinf_2 = d[8]; x.dinf_2 = d[9]; x.pobj = d[10]; x.dobj = d[11]; x.gap = d[12];
+    }
+    return LB2_OK;
+}
+
 int lb2_get_solution(const lb2_solver *s, lb2_int c, double *R, double *dualVar) {
     if (!s) return LB2_ERR_ARG;
     LB2_TRY

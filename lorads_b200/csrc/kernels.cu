@@ -36,37 +36,28 @@ static inline int grid_for(long long n, int per_thread, const Ctx &c) {
 // =================================================================================================
 // A(UV^T)
 // =================================================================================================
-constexpr int kTile = kAuvTileItems;
-
-__device__ __forceinline__ int upper_row(const int *__restrict__ ptr, int n_rows, int item) {
-    // largest row r with ptr[r] <= item (rows are non-empty except possibly trailing/isolated empties)
-    int lo = 0, hi = n_rows;   // invariant: ptr[lo] <= item < ptr[hi]
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (ptr[mid] <= item) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
-template <int MODE, int G>
+// One CTA per tile of TILE consecutive items.  A group of G lanes evaluates one item: it gathers the needed
+// factor rows with fully unrolled 16-byte loads (NP passes of 2*G columns, all issued before the FMAs so that a
+// thread keeps up to 4*NP independent loads in flight), reduces with shuffles and parks coef*z in shared
+// memory.  The tile is then reduced by constraint row: rows inside the tile are written, rows straddling tiles
+// leave partials in `carry`, and the last CTA to finish (atomic ticket) adds the partials of every split row
+// in a fixed order, so the result is deterministic.
+template <int MODE, int G, int NP, int TILE>
 __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const double *__restrict__ U,
                                                            const double *__restrict__ V, int ld, double scale1,
                                                            double scale2, double *__restrict__ out1,
-                                                           double *__restrict__ out2, double *__restrict__ carry1,
-                                                           double *__restrict__ carry2) {
+                                                           double *__restrict__ out2, double *obj1, double *obj2,
+                                                           double *carry1, double *carry2, unsigned int *ticket) {
     constexpr bool DUAL = (MODE == AUV_DUAL);
-    __shared__ double sp1[kTile];
-    __shared__ double sp2[DUAL ? kTile : 1];
-    __shared__ int s_rows[2];
+    __shared__ double sp1[TILE];
+    __shared__ double sp2[DUAL ? TILE : 1];
     __shared__ double sred[8];
+    __shared__ bool s_last;
 
     const int tile = blockIdx.x;
-    const int t0 = tile * kTile;
-    const int t1 = min(t0 + kTile, (int)L.n_items);
+    const int t0 = tile * TILE;
+    const int t1 = min(t0 + TILE, (int)L.n_items);
     const int tid = threadIdx.x;
-
-    if (tid == 0) s_rows[0] = upper_row(L.ptr, (int)L.n_rows, t0);
-    if (tid == 32) s_rows[1] = upper_row(L.ptr, (int)L.n_rows, t1 - 1);
 
     if constexpr (MODE == AUV_FROMZ) {
         for (int k = t0 + tid; k < t1; k += kBlock) sp1[k - t0] = scale1 * L.coef[k] * U[L.irow[k]];
@@ -74,6 +65,7 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
         constexpr int NG = kBlock / G;          // groups per block
         const int g = tid / G, gl = tid % G;
         // warp-uniform trip count: every lane reaches the shuffles of every iteration (tail lanes idle)
+#pragma unroll 1
         for (int base = t0; base < t1; base += NG) {
             const int k = base + g;
             const bool live = k < t1;
@@ -83,34 +75,35 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
                 const int i = L.irow[k], j = L.icol[k];
                 cf = L.coef[k];
                 diag = (i == j);
-                const double *ui = U + (size_t)i * ld, *uj = U + (size_t)j * ld;
+                const double *ui = U + (size_t)i * ld + 2 * gl, *uj = U + (size_t)j * ld + 2 * gl;
                 if constexpr (MODE == AUV_SAME) {
-                    if (diag) {
-                        for (int col = 2 * gl; col < ld; col += 2 * G) {
-                            double2 x = ld2(ui + col);
-                            a1 = fma(x.x, x.x, a1); a1 = fma(x.y, x.y, a1);
-                        }
-                    } else {
-                        for (int col = 2 * gl; col < ld; col += 2 * G) {
-                            double2 x = ld2(ui + col), y = ld2(uj + col);
-                            a1 = fma(x.x, y.x, a1); a1 = fma(x.y, y.y, a1);
-                        }
+                    double2 x[NP], y[NP];
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        const bool in = (2 * gl + 2 * G * q) < ld;
+                        x[q] = in ? ld2(ui + 2 * G * q) : make_double2(0.0, 0.0);
+                        y[q] = (in && !diag) ? ld2(uj + 2 * G * q) : x[q];
                     }
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) { a1 = fma(x[q].x, y[q].x, a1); a1 = fma(x[q].y, y[q].y, a1); }
                 } else {
-                    const double *vi = V + (size_t)i * ld, *vj = V + (size_t)j * ld;
-                    if (diag) {
-                        for (int col = 2 * gl; col < ld; col += 2 * G) {
-                            double2 x = ld2(ui + col), y = ld2(vi + col);
-                            a1 = fma(x.x, y.x, a1); a1 = fma(x.y, y.y, a1);
-                            if constexpr (DUAL) { a3 = fma(y.x, y.x, a3); a3 = fma(y.y, y.y, a3); }
-                        }
-                    } else {
-                        for (int col = 2 * gl; col < ld; col += 2 * G) {
-                            double2 x = ld2(ui + col), y = ld2(vj + col), p = ld2(uj + col), q = ld2(vi + col);
-                            a1 = fma(x.x, y.x, a1); a1 = fma(x.y, y.y, a1);
-                            a2 = fma(p.x, q.x, a2); a2 = fma(p.y, q.y, a2);
-                            if constexpr (DUAL) { a3 = fma(q.x, y.x, a3); a3 = fma(q.y, y.y, a3); }
-                        }
+                    const double *vi = V + (size_t)i * ld + 2 * gl, *vj = V + (size_t)j * ld + 2 * gl;
+                    double2 x[NP], y[NP], p[NP], qv[NP];
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        const bool in = (2 * gl + 2 * G * q) < ld;
+                        x[q] = in ? ld2(ui + 2 * G * q) : make_double2(0.0, 0.0);      // U_i
+                        qv[q] = in ? ld2(vi + 2 * G * q) : make_double2(0.0, 0.0);     // V_i
+                        if (!diag) {
+                            y[q] = in ? ld2(vj + 2 * G * q) : make_double2(0.0, 0.0);  // V_j
+                            p[q] = in ? ld2(uj + 2 * G * q) : make_double2(0.0, 0.0);  // U_j
+                        } else { y[q] = qv[q]; p[q] = x[q]; }
+                    }
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        a1 = fma(x[q].x, y[q].x, a1); a1 = fma(x[q].y, y[q].y, a1);          // U_i . V_j
+                        a2 = fma(p[q].x, qv[q].x, a2); a2 = fma(p[q].y, qv[q].y, a2);        // U_j . V_i
+                        if constexpr (DUAL) { a3 = fma(qv[q].x, y[q].x, a3); a3 = fma(qv[q].y, y[q].y, a3); }  // V_i . V_j
                     }
                 }
             }
@@ -129,9 +122,23 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
     }
     __syncthreads();
 
-    const int row_lo = s_rows[0], row_hi = s_rows[1];
+    const int row_lo = L.tile_row_lo[tile], row_hi = L.tile_row_hi[tile];
     const int nrows = row_hi - row_lo + 1;
     const int nit = t1 - t0;
+    auto emit = [&](int r, bool complete, double v1, double v2) {
+        if (complete) {
+            out1[r] = v1;
+            if constexpr (DUAL) out2[r] = v2;
+            if (r == L.obj_row) {
+                if (obj1) *obj1 += v1;
+                if constexpr (DUAL) { if (obj2) *obj2 += v2; }
+            }
+        } else {
+            const int slot = (r == row_lo) ? 2 * tile : 2 * tile + 1;
+            carry1[slot] = v1;
+            if constexpr (DUAL) carry2[slot] = v2;
+        }
+    };
 
     if (nrows == 1) {
         // the whole tile belongs to one row: block reduction in a fixed order
@@ -142,20 +149,8 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
         }
         v1 = block_sum(v1, sred);
         if constexpr (DUAL) v2 = block_sum(v2, sred);
-        if (tid == 0) {
-            const bool complete = (L.ptr[row_lo] >= t0) && (L.ptr[row_lo + 1] <= t1);
-            if (complete) {
-                out1[row_lo] = v1;
-                if constexpr (DUAL) out2[row_lo] = v2;
-            } else {
-                carry1[2 * tile] = v1;
-                if constexpr (DUAL) carry2[2 * tile] = v2;
-            }
-        }
-        return;
-    }
-
-    if (nrows * 8 >= nit) {
+        if (tid == 0) emit(row_lo, (L.ptr[row_lo] >= t0) && (L.ptr[row_lo + 1] <= t1), v1, v2);
+    } else if (nrows * 8 >= nit) {
         // short rows: one thread per row, sequential (deterministic) sum
         for (int r = row_lo + tid; r <= row_hi; r += kBlock) {
             const int pa = L.ptr[r], pb = L.ptr[r + 1];
@@ -165,14 +160,7 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
                 v1 += sp1[k];
                 if constexpr (DUAL) v2 += sp2[k];
             }
-            if (pa >= t0 && pb <= t1) {
-                out1[r] = v1;
-                if constexpr (DUAL) out2[r] = v2;
-            } else {
-                const int slot = (r == row_lo) ? 2 * tile : 2 * tile + 1;
-                carry1[slot] = v1;
-                if constexpr (DUAL) carry2[slot] = v2;
-            }
+            emit(r, pa >= t0 && pb <= t1, v1, v2);
         }
     } else {
         // longer rows: one warp per row
@@ -187,77 +175,93 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
             }
             v1 = warp_sum(v1);
             if constexpr (DUAL) v2 = warp_sum(v2);
+            if (lane == 0) emit(r, pa >= t0 && pb <= t1, v1, v2);
+        }
+    }
+
+    if (L.n_split == 0) return;
+    // ---- split rows: the last CTA adds the tile partials, one warp per split row, fixed order ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    {
+        const int w = tid >> 5, lane = tid & 31;
+        for (int sidx = w; sidx < (int)L.n_split; sidx += kBlock / 32) {
+            const int row = L.split_row[sidx], fs = L.split_first_slot[sidx], ta = L.split_tile_a[sidx];
+            const int ne = L.split_tile_b[sidx] - ta + 1;
+            double v1 = 0.0, v2 = 0.0;
+            for (int e = lane; e < ne; e += 32) {
+                const int slot = (e == 0) ? fs : 2 * (ta + e);
+                v1 += __ldcg(carry1 + slot);
+                if constexpr (DUAL) v2 += __ldcg(carry2 + slot);
+            }
+            v1 = warp_sum(v1);
+            if constexpr (DUAL) v2 = warp_sum(v2);
             if (lane == 0) {
-                if (pa >= t0 && pb <= t1) {
-                    out1[r] = v1;
-                    if constexpr (DUAL) out2[r] = v2;
-                } else {
-                    const int slot = (r == row_lo) ? 2 * tile : 2 * tile + 1;
-                    carry1[slot] = v1;
-                    if constexpr (DUAL) carry2[slot] = v2;
+                out1[row] = v1;
+                if constexpr (DUAL) out2[row] = v2;
+                if (row == L.obj_row) {
+                    if (obj1) *obj1 += v1;
+                    if constexpr (DUAL) { if (obj2) *obj2 += v2; }
                 }
             }
         }
+        if (tid == 0) *ticket = 0u;
     }
 }
 
-// rows split over several tiles: out[row] = sum of their tile partials, one warp per row, fixed order
-__global__ void __launch_bounds__(kBlock) auv_fixup_kernel(ItemListDev L, const double *__restrict__ carry1,
-                                                           const double *__restrict__ carry2,
-                                                           double *__restrict__ out1, double *__restrict__ out2) {
-    const int w = (blockIdx.x * kBlock + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= L.n_split) return;
-    const int row = L.split_row[w], fs = L.split_first_slot[w], ta = L.split_tile_a[w], tb = L.split_tile_b[w];
-    const int ne = tb - ta + 1;
-    double v1 = 0.0, v2 = 0.0;
-    for (int e = lane; e < ne; e += 32) {
-        const int slot = (e == 0) ? fs : 2 * (ta + e);
-        v1 += carry1[slot];
-        if (carry2) v2 += carry2[slot];
-    }
-    v1 = warp_sum(v1);
-    v2 = warp_sum(v2);
-    if (lane == 0) {
-        out1[row] = v1;
-        if (carry2) out2[row] = v2;
+template <int MODE, int G, int NP>
+static void launch_auv_tile(Ctx &c, const ItemListDev &L, const double *U, const double *V, int ld, double s1, double s2,
+                            double *o1, double *o2, double *b1, double *b2, double *c1, double *c2) {
+    const int grid = (int)L.n_tiles;
+    if (L.tile == kAuvTileSmall)
+        auv_items_kernel<MODE, G, NP, kAuvTileSmall><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2, c.ticket);
+    else
+        auv_items_kernel<MODE, G, NP, kAuvTileLarge><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2, c.ticket);
+    LB2_LAUNCH_CHECK(c);
+}
+
+template <int MODE, int G>
+static void launch_auv_np(Ctx &c, int np, const ItemListDev &L, const double *U, const double *V, int ld, double s1,
+                          double s2, double *o1, double *o2, double *b1, double *b2, double *c1, double *c2) {
+    switch (np) {
+    case 1: launch_auv_tile<MODE, G, 1>(c, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
+    case 2: launch_auv_tile<MODE, G, 2>(c, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
+    case 3: launch_auv_tile<MODE, G, 3>(c, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
+    default: launch_auv_tile<MODE, G, 4>(c, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
     }
 }
 
 template <int MODE>
 static void launch_auv_mode(Ctx &c, const ItemListDev &L, const double *U, const double *V, int ld, double s1,
-                            double s2, double *o1, double *o2, double *c1, double *c2) {
-    const int grid = (int)L.n_tiles;
-    if (MODE == AUV_FROMZ) {
-        auv_items_kernel<MODE, 4><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, c1, c2);
-    } else if (ld <= 32) {
-        auv_items_kernel<MODE, 4><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, c1, c2);
-    } else if (ld <= 64) {
-        auv_items_kernel<MODE, 8><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, c1, c2);
-    } else if (ld <= 128) {
-        auv_items_kernel<MODE, 16><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, c1, c2);
-    } else {
-        auv_items_kernel<MODE, 32><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, c1, c2);
+                            double s2, double *o1, double *o2, double *b1, double *b2, double *c1, double *c2) {
+    if (MODE == AUV_FROMZ) { launch_auv_tile<MODE, 4, 1>(c, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); return; }
+    if (ld > 256) throw std::runtime_error("rank above 256 is not supported by the A(UV^T) kernel yet");
+    const int G = ld <= 32 ? 4 : (ld <= 64 ? 8 : (ld <= 128 ? 16 : 32));
+    const int np = (ld + 2 * G - 1) / (2 * G);
+    switch (G) {
+    case 4: launch_auv_np<MODE, 4>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
+    case 8: launch_auv_np<MODE, 8>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
+    case 16: launch_auv_np<MODE, 16>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
+    default: launch_auv_np<MODE, 32>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
     }
-    LB2_LAUNCH_CHECK(c);
 }
 
 void launch_auv(Ctx &c, AuvMode mode, const ItemListDev &L, const double *U, const double *V, int ld, double scale1,
-                double scale2, double *out1, double *out2, double *carry1, double *carry2) {
+                double scale2, double *out1, double *out2, double *carry1, double *carry2, double *obj1, double *obj2) {
     if (L.has_empty_rows) {
         LB2_CUDA(cudaMemsetAsync(out1, 0, sizeof(double) * L.n_rows, c.stream));
         if (mode == AUV_DUAL) LB2_CUDA(cudaMemsetAsync(out2, 0, sizeof(double) * L.n_rows, c.stream));
     }
     if (L.n_items == 0) return;
     switch (mode) {
-    case AUV_SAME: launch_auv_mode<AUV_SAME>(c, L, U, V, ld, scale1, scale2, out1, out2, carry1, carry2); break;
-    case AUV_PAIR: launch_auv_mode<AUV_PAIR>(c, L, U, V, ld, scale1, scale2, out1, out2, carry1, carry2); break;
-    case AUV_DUAL: launch_auv_mode<AUV_DUAL>(c, L, U, V, ld, scale1, scale2, out1, out2, carry1, carry2); break;
-    case AUV_FROMZ: launch_auv_mode<AUV_FROMZ>(c, L, U, V, ld, scale1, scale2, out1, out2, carry1, carry2); break;
-    }
-    if (L.n_split > 0) {
-        const int grid = (int)((L.n_split * 32 + kBlock - 1) / kBlock);
-        auv_fixup_kernel<<<grid, kBlock, 0, c.stream>>>(L, carry1, mode == AUV_DUAL ? carry2 : nullptr, out1, out2);
-        LB2_LAUNCH_CHECK(c);
+    case AUV_SAME: launch_auv_mode<AUV_SAME>(c, L, U, V, ld, scale1, scale2, out1, out2, obj1, obj2, carry1, carry2); break;
+    case AUV_PAIR: launch_auv_mode<AUV_PAIR>(c, L, U, V, ld, scale1, scale2, out1, out2, obj1, obj2, carry1, carry2); break;
+    case AUV_DUAL: launch_auv_mode<AUV_DUAL>(c, L, U, V, ld, scale1, scale2, out1, out2, obj1, obj2, carry1, carry2); break;
+    case AUV_FROMZ: launch_auv_mode<AUV_FROMZ>(c, L, U, V, ld, scale1, scale2, out1, out2, obj1, obj2, carry1, carry2); break;
     }
 }
 
@@ -305,6 +309,9 @@ void launch_wsum(Ctx &c, double *S, long long np, const double *C_onP, const int
     LB2_LAUNCH_CHECK(c);
 }
 
+// One group of G lanes per matrix row i: Y[i,:] = a * sum_e S[pos_e] X[col_e,:] + b Z[i,:].  Four neighbours are
+// gathered per round with every 16-byte load issued before the first FMA (4*NP loads in flight per thread);
+// the kernel is latency bound on the random row gathers, so memory-level parallelism is what matters.
 template <int G, int NP>
 __global__ void __launch_bounds__(kBlock) spmm_sym_kernel(long long n, int ld, const int *__restrict__ adj_ptr,
                                                           const int *__restrict__ adj_col,
@@ -313,6 +320,7 @@ __global__ void __launch_bounds__(kBlock) spmm_sym_kernel(long long n, int ld, c
                                                           const double *__restrict__ Z, const double *__restrict__ Z2,
                                                           double *__restrict__ Y, ReduceScratch rs, double *red) {
     constexpr int NG = kBlock / G;
+    constexpr int UN = 4;
     const int g = threadIdx.x / G, gl = threadIdx.x % G;
     double ryy = 0.0, ryz = 0.0;
     for (long long i = (long long)blockIdx.x * NG + g; i < n; i += (long long)gridDim.x * NG) {
@@ -320,36 +328,30 @@ __global__ void __launch_bounds__(kBlock) spmm_sym_kernel(long long n, int ld, c
 #pragma unroll
         for (int q = 0; q < NP; ++q) acc[q] = make_double2(0.0, 0.0);
         const int ea = adj_ptr[i], eb = adj_ptr[i + 1];
-        int e = ea;
-        for (; e + 1 < eb; e += 2) {   // two neighbours in flight
-            const int j0 = adj_col[e], j1 = adj_col[e + 1];
-            const double s0 = S[adj_pos[e]], s1 = S[adj_pos[e + 1]];
-            const double *x0 = X + (size_t)j0 * ld, *x1 = X + (size_t)j1 * ld;
-            double2 v0[NP], v1[NP];
+        for (int e = ea; e < eb; e += UN) {
+            int jn[UN];
+            double sv[UN];
 #pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                const int col = 2 * gl + 2 * G * q;
-                if (col < ld) { v0[q] = ld2(x0 + col); v1[q] = ld2(x1 + col); }
-                else { v0[q] = make_double2(0.0, 0.0); v1[q] = v0[q]; }
+            for (int u = 0; u < UN; ++u) {
+                const bool ok = (e + u) < eb;
+                jn[u] = ok ? adj_col[e + u] : (int)i;
+                sv[u] = ok ? S[adj_pos[ok ? e + u : ea]] : 0.0;
+            }
+            double2 v[UN][NP];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const double *xr = X + (size_t)jn[u] * ld + 2 * gl;
+#pragma unroll
+                for (int q = 0; q < NP; ++q)
+                    v[u][q] = ((2 * gl + 2 * G * q) < ld) ? ld2(xr + 2 * G * q) : make_double2(0.0, 0.0);
             }
 #pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                acc[q].x = fma(s0, v0[q].x, acc[q].x); acc[q].y = fma(s0, v0[q].y, acc[q].y);
-                acc[q].x = fma(s1, v1[q].x, acc[q].x); acc[q].y = fma(s1, v1[q].y, acc[q].y);
-            }
-        }
-        if (e < eb) {
-            const int j0 = adj_col[e];
-            const double s0 = S[adj_pos[e]];
-            const double *x0 = X + (size_t)j0 * ld;
+            for (int u = 0; u < UN; ++u)
 #pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                const int col = 2 * gl + 2 * G * q;
-                if (col < ld) {
-                    double2 v = ld2(x0 + col);
-                    acc[q].x = fma(s0, v.x, acc[q].x); acc[q].y = fma(s0, v.y, acc[q].y);
+                for (int q = 0; q < NP; ++q) {
+                    acc[q].x = fma(sv[u], v[u][q].x, acc[q].x);
+                    acc[q].y = fma(sv[u], v[u][q].y, acc[q].y);
                 }
-            }
         }
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
@@ -380,9 +382,8 @@ static void launch_spmm_g(Ctx &c, int np, long long n, int ld, const int *ap, co
                           const double *S, const double *X, double a, double b, const double *Z, const double *Z2,
                           double *Y, double *red) {
     constexpr int NG = kBlock / G;
-    long long blocks = (n + NG - 1) / NG;
-    long long cap = (long long)c.num_sms * 8;
-    if (blocks > cap) blocks = cap;
+    long long blocks = (n + NG - 1) / NG;      // one row per lane group; the hardware balances the CTAs
+    if (blocks > 8192) blocks = 8192;           // capacity of the reduction scratch (grid-stride beyond that)
     const int grid = (int)blocks;
     switch (np) {
     case 1: spmm_sym_kernel<G, 1><<<grid, kBlock, 0, c.stream>>>(n, ld, ap, ac, apos, S, X, a, b, Z, Z2, Y, c.rs, red); break;
@@ -591,6 +592,43 @@ void launch_dense_symm(Ctx &c, long long n, int r, int ld, const double *Sp, con
     const size_t smem = sizeof(double) * (kDT * (kDT + 1) + kDT * ld);
     LB2_CUDA(cudaFuncSetAttribute(dense_symm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dense_symm_kernel<<<nb, kBlock, smem, c.stream>>>(n, r, ld, Sp, X, a, b, Z, Z2, Y, c.rs, red);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) spmv_sym_kernel(long long n, const int *__restrict__ adj_ptr,
+                                                          const int *__restrict__ adj_col, const int *__restrict__ adj_pos,
+                                                          const double *__restrict__ S, const double *__restrict__ x,
+                                                          double *__restrict__ y) {
+    for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+        double acc = 0.0;
+        for (int e = adj_ptr[i]; e < adj_ptr[i + 1]; ++e) acc = fma(S[adj_pos[e]], x[adj_col[e]], acc);
+        y[i] = acc;
+    }
+}
+
+void launch_spmv_sym(Ctx &c, long long n, const int *adj_ptr, const int *adj_col, const int *adj_pos, const double *S,
+                     const double *x, double *y) {
+    spmv_sym_kernel<<<grid_for(n, 1, c), kBlock, 0, c.stream>>>(n, adj_ptr, adj_col, adj_pos, S, x, y);
+    LB2_LAUNCH_CHECK(c);
+}
+
+// one warp per row i of the packed symmetric matrix: columns j <= i are strided reads, rows j > i are contiguous
+__global__ void __launch_bounds__(kBlock) dense_symv_kernel(long long n, const double *__restrict__ Sp,
+                                                            const double *__restrict__ x, double *__restrict__ y) {
+    const long long i = ((long long)blockIdx.x * kBlock + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    double acc = 0.0;
+    for (long long j = lane; j < i; j += 32) acc = fma(Sp[packed_col_start(n, j) + (i - j)], x[j], acc);
+    const long long base = packed_col_start(n, i);
+    for (long long j = i + lane; j < n; j += 32) acc = fma(Sp[base + (j - i)], x[j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) y[i] = acc;
+}
+
+void launch_dense_symv(Ctx &c, long long n, const double *Sp, const double *x, double *y) {
+    const long long blocks = (n * 32 + kBlock - 1) / kBlock;
+    dense_symv_kernel<<<(unsigned)blocks, kBlock, 0, c.stream>>>(n, Sp, x, y);
     LB2_LAUNCH_CHECK(c);
 }
 

@@ -8,6 +8,7 @@ namespace lb2 {
 struct Ctx {
     cudaStream_t stream = nullptr;
     ReduceScratch rs{nullptr, nullptr};
+    unsigned int *ticket = nullptr;    // zero-initialised counter for "last block finishes" kernels
     int num_sms = 148;
     long long launches = 0;
 };
@@ -20,6 +21,9 @@ struct ItemListDev {
     const int *ptr = nullptr, *irow = nullptr, *icol = nullptr;
     const double *coef = nullptr;
     const int *split_row = nullptr, *split_first_slot = nullptr, *split_tile_a = nullptr, *split_tile_b = nullptr;
+    const int *tile_row_lo = nullptr, *tile_row_hi = nullptr;
+    int tile = 512;          // items per CTA tile (512 or 128)
+    int obj_row = -1;        // index of the objective row (last row of an [A;C] list), -1 if none
     bool has_empty_rows = false;
 };
 
@@ -31,8 +35,10 @@ enum AuvMode {
 };
 
 // out1/out2: n_rows values each; carry: 2*n_tiles doubles per output.  U,V row-major n x ld (ld % 4 == 0).
+// obj1/obj2 (may be null): the value of the objective row is ADDED to *obj1 / *obj2 as well.
 void launch_auv(Ctx &c, AuvMode mode, const ItemListDev &L, const double *U, const double *V, int ld,
-                double scale1, double scale2, double *out1, double *out2, double *carry1, double *carry2);
+                double scale1, double scale2, double *out1, double *out2, double *carry1, double *carry2,
+                double *obj1 = nullptr, double *obj2 = nullptr);
 
 // dst[idx ? idx[a] : a] (+)= alpha * src[a]  for a < n ; when obj_dst != nullptr: *obj_dst += alpha*src[n]
 void launch_scatter_add(Ctx &c, double *dst, const double *src, const int *idx, long long n, double alpha,
@@ -65,6 +71,12 @@ void launch_dense_wsum(Ctx &c, double *Sp, long long psize, const double *Cp, co
 // Y = a * Sp(sym, packed) * X + b * Z ; reductions as launch_spmm
 void launch_dense_symm(Ctx &c, long long n, int r, int ld, const double *Sp, const double *X, double a, double b,
                        const double *Z, const double *Z2, double *Y, double *red);
+
+// y = S x for one n-vector (dual infeasibility Lanczos; reference mv: dataMatSparseMV / dataMatDenseMV,
+// lorads_sdp_data.c:506-521,673-696)
+void launch_spmv_sym(Ctx &c, long long n, const int *adj_ptr, const int *adj_col, const int *adj_pos, const double *S,
+                     const double *x, double *y);
+void launch_dense_symv(Ctx &c, long long n, const double *Sp, const double *x, double *y);
 
 // ------------------------------------------------------------------------------------------------
 // fused BLAS-1 on the concatenated factor vectors (length N) and on m-vectors

@@ -22,7 +22,10 @@
 
 namespace lb2 {
 
-constexpr int kAuvTileItems = 512;   // items per CTA tile of the A(UV^T) kernel (must match kernels.cu)
+// items per CTA tile of the A(UV^T) kernel: large lists use 512, small ones 128 so that the grid still fills
+// the 148 SMs several times over (kernels.cu instantiates both)
+constexpr int kAuvTileLarge = 512, kAuvTileSmall = 128;
+constexpr long long kAuvSmallListItems = 400000;
 
 struct ItemList {
     // rows 0..n_rows-1; when has_obj the last row is the objective C
@@ -34,8 +37,10 @@ struct ItemList {
     std::vector<double> coef;     // 2a off-diagonal, a on the diagonal (lorads_sdp_data.c:545-549)
     // rows that straddle tile boundaries: their tile partials are summed by the fix-up kernel
     std::vector<int32_t> split_row, split_first_slot, split_tile_a, split_tile_b;
+    int tile = kAuvTileLarge;                 // items per tile chosen for this list
+    std::vector<int32_t> tile_row_lo, tile_row_hi;   // first / last row with an item in each tile
     int64_t n_items() const { return (int64_t)irow.size(); }
-    int64_t n_tiles() const { return (n_items() + kAuvTileItems - 1) / kAuvTileItems; }
+    int64_t n_tiles() const { return (n_items() + tile - 1) / tile; }
 };
 
 struct ConeLayout {
@@ -75,13 +80,17 @@ inline void unpack_lower(int64_t n, int64_t packed, int64_t &row, int64_t &col) 
 }
 
 inline void finish_item_list(ItemList &L) {
+    L.tile = (L.n_items() < kAuvSmallListItems) ? kAuvTileSmall : kAuvTileLarge;
+    const int64_t T = L.tile;
     // static table of the rows whose items straddle tile boundaries
-    const int64_t T = kAuvTileItems;
     L.split_row.clear(); L.split_first_slot.clear(); L.split_tile_a.clear(); L.split_tile_b.clear();
+    const int64_t nt = L.n_tiles();
+    L.tile_row_lo.assign(nt, 0); L.tile_row_hi.assign(nt, 0);
     for (int64_t r = 0; r < L.n_rows; ++r) {
         int64_t a = L.ptr[r], b = L.ptr[r + 1];
         if (b <= a) continue;
         int64_t ta = a / T, tb = (b - 1) / T;
+        for (int64_t t = ta; t <= tb; ++t) L.tile_row_hi[t] = (int32_t)r;   // rows ascend: the last writer wins
         if (ta == tb) continue;
         // in tile ta the row is the LAST row of the tile: slot 2*ta+1, unless it starts exactly at the tile
         // start (then it is also the first row: slot 2*ta)
@@ -90,6 +99,15 @@ inline void finish_item_list(ItemList &L) {
         L.split_first_slot.push_back((int32_t)first_slot);
         L.split_tile_a.push_back((int32_t)ta);
         L.split_tile_b.push_back((int32_t)tb);
+    }
+    // first row of a tile = row containing the tile's first item
+    {
+        int64_t r = 0;
+        for (int64_t t = 0; t < nt; ++t) {
+            const int64_t first = t * T;
+            while (r + 1 < L.n_rows && L.ptr[r + 1] <= first) ++r;
+            L.tile_row_lo[t] = (int32_t)r;
+        }
     }
 }
 

@@ -26,6 +26,10 @@ void ItemListBufs::upload(const ItemList &L) {
     dev.ptr = ptr.p; dev.irow = irow.p; dev.icol = icol.p; dev.coef = coef.p;
     dev.split_row = split_row.p; dev.split_first_slot = split_first_slot.p;
     dev.split_tile_a = split_tile_a.p; dev.split_tile_b = split_tile_b.p;
+    tile_row_lo.upload(L.tile_row_lo); tile_row_hi.upload(L.tile_row_hi);
+    dev.tile_row_lo = tile_row_lo.p; dev.tile_row_hi = tile_row_hi.p;
+    dev.tile = L.tile;
+    dev.obj_row = L.has_obj ? (int)(L.n_rows - 1) : -1;
     dev.has_empty_rows = false;
     for (int64_t r = 0; r < L.n_rows; ++r)
         if (L.ptr[r + 1] == L.ptr[r]) dev.has_empty_rows = true;
@@ -56,6 +60,7 @@ void Solver::create(long long nRows, long long nC, const lb2_int *dims, const do
     red_counter.alloc(4);
     ctx.rs.partials = red_partials.p;
     ctx.rs.counter = red_counter.p;
+    ctx.ticket = red_counter.p + 1;
     S.alloc(kNumSlots + 2 * nC);
     LB2_CUDA(cudaMallocHost((void **)&S_host, sizeof(double) * (kNumSlots + 2 * nC)));
     std::memset(S_host, 0, sizeof(double) * (kNumSlots + 2 * nC));
@@ -267,29 +272,34 @@ void Solver::read_slots() {
 // ---------------------------------------------------------------------------------------------------
 // operators
 // ---------------------------------------------------------------------------------------------------
-void Solver::cone_auv(ConeDev &K, bool with_obj, const double *Um, const double *Vm, bool same, double scale, double *out) {
+void Solver::cone_auv(ConeDev &K, bool with_obj, const double *Um, const double *Vm, bool same, double scale, double *out,
+                      double *obj) {
     ItemListBufs &L = with_obj ? K.listAC : K.listA;
     if (K.dense_path) {
+        if (world > 1 && myrank != 0) obj = nullptr;   // Z is all-reduced first: only one rank may feed the slot
         launch_dense_uvt(ctx, K.n, K.r, K.ld, Um + K.off, Vm + K.off, K.Z1.p, same);
         if (world > 1) allreduce(K.Z1.p, K.np);
-        launch_auv(ctx, AUV_FROMZ, L.dev, K.Z1.p, nullptr, K.ld, scale, 0.0, out, nullptr, K.carry1.p, nullptr);
+        launch_auv(ctx, AUV_FROMZ, L.dev, K.Z1.p, nullptr, K.ld, scale, 0.0, out, nullptr, K.carry1.p, nullptr, obj, nullptr);
         return;
     }
+    // with column sharding the objective is summed over ranks by the caller (the slot is all-reduced once)
     launch_auv(ctx, same ? AUV_SAME : AUV_PAIR, L.dev, Um + K.off, Vm + K.off, K.ld, scale, 0.0, out, nullptr,
-               K.carry1.p, nullptr);
+               K.carry1.p, nullptr, obj, nullptr);
     if (world > 1) allreduce(out, L.dev.n_rows);
 }
 
-void Solver::cone_auv_dual(ConeDev &K, const double *Rm, const double *Dm, double *out1, double *out2) {
+void Solver::cone_auv_dual(ConeDev &K, const double *Rm, const double *Dm, double *out1, double *out2, double *obj1,
+                           double *obj2) {
     ItemListBufs &L = K.listAC;
     if (K.dense_path) {
+        if (world > 1 && myrank != 0) { obj1 = nullptr; obj2 = nullptr; }
         launch_dense_uvt_dual(ctx, K.n, K.r, K.ld, Rm + K.off, Dm + K.off, K.Z1.p, K.Z2.p);
         if (world > 1) { allreduce(K.Z1.p, K.np); allreduce(K.Z2.p, K.np); }
-        launch_auv(ctx, AUV_FROMZ, L.dev, K.Z1.p, nullptr, K.ld, 2.0, 0.0, out1, nullptr, K.carry1.p, nullptr);
-        launch_auv(ctx, AUV_FROMZ, L.dev, K.Z2.p, nullptr, K.ld, 1.0, 0.0, out2, nullptr, K.carry1.p, nullptr);
+        launch_auv(ctx, AUV_FROMZ, L.dev, K.Z1.p, nullptr, K.ld, 2.0, 0.0, out1, nullptr, K.carry1.p, nullptr, obj1, nullptr);
+        launch_auv(ctx, AUV_FROMZ, L.dev, K.Z2.p, nullptr, K.ld, 1.0, 0.0, out2, nullptr, K.carry1.p, nullptr, obj2, nullptr);
         return;
     }
-    launch_auv(ctx, AUV_DUAL, L.dev, Rm + K.off, Dm + K.off, K.ld, 2.0, 1.0, out1, out2, K.carry1.p, K.carry2.p);
+    launch_auv(ctx, AUV_DUAL, L.dev, Rm + K.off, Dm + K.off, K.ld, 2.0, 1.0, out1, out2, K.carry1.p, K.carry2.p, obj1, obj2);
     if (world > 1) { allreduce(out1, L.dev.n_rows); allreduce(out2, L.dev.n_rows); }
 }
 
@@ -408,19 +418,17 @@ void Solver::q12p12() {
     // ALMCalq12p12, lorads_alm.c:540-560: q1 = 2 A(sym(R D^T)), p1 = 2 <C, sym(R D^T)>, q2 = A(D D^T), p2 = <C, D D^T>
     LB2_CUDA(cudaMemsetAsync(S.p + SL_P1, 0, 2 * sizeof(double), ctx.stream));
     if (single_identity) {
-        ConeDev &K = cones[0];
-        cone_auv_dual(K, R.p, U.p, q1.p, q2.p);   // row m of the outputs is the objective row
-        launch_scatter_add(ctx, S.p + SL_P1, q1.p + m, nullptr, 0, 1.0, true, S.p + SL_P1);
-        launch_scatter_add(ctx, S.p + SL_P2, q2.p + m, nullptr, 0, 1.0, true, S.p + SL_P2);
+        // row m of the outputs is the objective row; its value is also accumulated into the P1 / P2 slots
+        cone_auv_dual(cones[0], R.p, U.p, q1.p, q2.p, S.p + SL_P1, S.p + SL_P2);
         return;
     }
     LB2_CUDA(cudaMemsetAsync(q1.p, 0, sizeof(double) * m, ctx.stream));
     LB2_CUDA(cudaMemsetAsync(q2.p, 0, sizeof(double) * m, ctx.stream));
     for (ConeDev &K : cones) {
-        cone_auv_dual(K, R.p, U.p, K.t1.p, K.t2.p);
+        cone_auv_dual(K, R.p, U.p, K.t1.p, K.t2.p, S.p + SL_P1, S.p + SL_P2);
         const int *map = K.identity_act ? nullptr : K.act_idx.p;
-        launch_scatter_add(ctx, q1.p, K.t1.p, map, K.n_act, 1.0, true, S.p + SL_P1);
-        launch_scatter_add(ctx, q2.p, K.t2.p, map, K.n_act, 1.0, true, S.p + SL_P2);
+        launch_scatter_add(ctx, q1.p, K.t1.p, map, K.n_act, 1.0, true, nullptr);
+        launch_scatter_add(ctx, q2.p, K.t2.p, map, K.n_act, 1.0, true, nullptr);
     }
 }
 
@@ -434,10 +442,8 @@ void Solver::primal_infeasibility(const double *Rm) {
 double Solver::cal_obj(const double *Rm) {
     // LORADSCalObjRR_ALM, lorads_alm.c:1259-1268
     LB2_CUDA(cudaMemsetAsync(S.p + SL_OBJ, 0, sizeof(double), ctx.stream));
-    for (ConeDev &K : cones) {
-        cone_auv(K, true, Rm, Rm, true, 1.0, K.t1.p);
-        launch_scatter_add(ctx, S.p + SL_OBJ, K.t1.p + K.n_act, nullptr, 0, 1.0, true, S.p + SL_OBJ);
-    }
+    for (ConeDev &K : cones) cone_auv(K, true, Rm, Rm, true, 1.0, K.t1.p, S.p + SL_OBJ);
+    if (world > 1) allreduce(S.p + SL_OBJ, 1);
     read_slots();
     return S_host[SL_OBJ] / scaleObjHis;
 }

@@ -26,7 +26,7 @@ enum Slot : int {
 constexpr int kMaxLbfgs = 16;
 
 struct ItemListBufs {
-    DBuf<int> ptr, irow, icol, split_row, split_first_slot, split_tile_a, split_tile_b;
+    DBuf<int> ptr, irow, icol, split_row, split_first_slot, split_tile_a, split_tile_b, tile_row_lo, tile_row_hi;
     DBuf<double> coef;
     ItemListDev dev;
     void upload(const ItemList &L);
@@ -130,8 +130,10 @@ struct Solver {
     void allreduce(double *p, long long count);
     // operators
     // A(sym(U V^T)) of cone c with the A or A+C item list: writes (scale*values) to out1 (n_rows of the list)
-    void cone_auv(ConeDev &K, bool with_obj, const double *U, const double *V, bool same, double scale, double *out);
-    void cone_auv_dual(ConeDev &K, const double *Rm, const double *Dm, double *out1, double *out2);
+    void cone_auv(ConeDev &K, bool with_obj, const double *U, const double *V, bool same, double scale, double *out,
+                  double *obj = nullptr);
+    void cone_auv_dual(ConeDev &K, const double *Rm, const double *Dm, double *out1, double *out2, double *obj1 = nullptr,
+                       double *obj2 = nullptr);
     void cone_wsum(ConeDev &K, const double *w, bool w_compact, bool addC);
     void cone_mul(ConeDev &K, const double *X, double a, double bcoef, const double *Z, const double *Z2, double *Y, double *red);
     // constrVal[c] = A(sym(U V^T)) for all cones, then constrValSum (LORADSInitConstrValAll + InitConstrValSum)
