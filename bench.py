@@ -241,17 +241,18 @@ def run_ours(args):
         e2e = {"value": None, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "note": "e2e is measured at N=1 only (column shards are per-rank host buffers)"}
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
-
     # ---------------- roofline of the hot kernels (cone 0, CUDA events, back-to-back launches) ----------------
+    # every rank takes part: with column sharding the A(UV^T) launches are followed by their all-reduce
     peak, peak_src = measured_peak_gbs()
     kb = kernel_bytes(S)
     kt = {}
     for which in kb:
         kt[which] = S.bench_kernel(which, 200)
+    barrier()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
     # per-iteration share: 1 dual pass, 1 A-only pass, 1 wsum, 1 spmm, ~6 BLAS-1 passes
     mult = {0: 1, 1: 1, 2: 1, 3: 1, 4: 6}
     share = {w: kt[w] * mult[w] for w in kt}
