@@ -180,11 +180,17 @@ alg_start:
             if (cur_iter_counter >= MAX_ALM_SUB_ITER) { update_max_sub_iter_counter += 1; break; }
             if ((double)rank_flag >= rank_flag_thres && !is_rank_max && (k - last_outer_start >= 3)) break;
             if (cert_val <= cert_tol) break;
+            // S_host may already hold the line-search scalars of a speculatively issued front half (same rho,
+            // counter spec_counter); it is only reused inside this sub-problem loop
+            bool spec = false;
+            long long spec_counter = -1;
+            auto reset_rule = [&](long long li) { return reopt_variant ? ((li - 1) % 300 == 0) : (li % 300 == 0); };
             while (cert_val - cert_tol > P->endALMSubTol) {
-                if (reopt_variant ? ((localIter - 1) % 300 == 0) : (localIter % 300 == 0)) clearLBFGS = 0;
+                if (reset_rule(localIter)) clearLBFGS = 0;
                 double p12[2];
-                long long rootNum = 0;
-                alm_inner_front(alm.rho, clearLBFGS, &tau, p12, &rootNum);
+                if (!spec || spec_counter != clearLBFGS) { enqueue_front(alm.rho, clearLBFGS); read_slots(); }
+                spec = false;
+                const long long rootNum = finish_front(alm.rho, &tau, p12);
                 if (rootNum == 0) { retcode = LB2_RET_NUM_ERR; jump = GO_END_ALM; goto after_loops; }
                 if (std::fabs(tau) < P->endTauTol) {
                     if (verbose) printf("update rho:%5.8e since tau is too small.\n", tau);
@@ -193,7 +199,12 @@ alg_start:
                     break;
                 }
                 double pinf1 = 0;
-                alm_inner_back(alm.rho, tau, &lagSq, &pinf1);
+                enqueue_back(alm.rho, tau);
+                spec_counter = reset_rule(localIter + 1) ? 0 : clearLBFGS + 1;
+                enqueue_front(alm.rho, spec_counter);      // next iteration's front half rides behind this one
+                spec = true;
+                read_slots();
+                finish_back(&lagSq, &pinf1);
                 alm.pinf_1 = pinf1;
                 alm.pinf_inf = pinf1 * (1 + bNrm1) / (1 + bNrmInf);
                 if (!reopt_variant) {

@@ -316,22 +316,12 @@ int lb2_time_alm_inner_iters(lb2_solver *s, double rho, lb2_int iters, double *o
     cudaEvent_t e0, e1;
     LB2_CUDA(cudaEventCreate(&e0)); LB2_CUDA(cudaEventCreate(&e1));
     LB2_CUDA(cudaEventRecord(e0, S.ctx.stream));
-    double tau = 0.0, p12[2] = {0, 0}, lag = 0, pinf = 0;
-    lb2_int done = 0;
-    for (lb2_int k = 0; k < iters; ++k) {
-        long long rn = 0;
-        S.alm_inner_front(rho, k, &tau, p12, &rn);
-        if (rn == 0) break;
-        S.alm_inner_back(rho, tau, &lag, &pinf);
-        done++;
-    }
-    out[5] = (double)done;
+    S.run_inner_iters(rho, iters, out);
     LB2_CUDA(cudaEventRecord(e1, S.ctx.stream));
     LB2_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
     LB2_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    out[0] = tau; out[1] = lag; out[2] = pinf; out[3] = p12[0]; out[4] = p12[1];
     *seconds = ms * 1e-3;
     LB2_CATCH
 }
@@ -350,21 +340,12 @@ int lb2_alm_run_host(lb2_solver *s, const double *R_in, const double *lambda_in,
     S.init_constr_val_all(S.R.p, S.R.p, true);
     S.constr_val_sum();
     S.cal_grad(rho);
-    double tau = 0.0, p12[2] = {0, 0}, lag = 0, pinf = 0;
-    lb2_int done = 0;
-    for (lb2_int k = 0; k < iters; ++k) {
-        long long rn = 0;
-        S.alm_inner_front(rho, k, &tau, p12, &rn);
-        if (rn == 0) break;
-        S.alm_inner_back(rho, tau, &lag, &pinf);
-        done++;
-    }
+    S.run_inner_iters(rho, iters, out);
     off = 0;
     for (long long c = 0; c < S.nCones; ++c) {
         S.download_factor(S.R.p, S.cones[c], R_out + off);
         off += (size_t)(S.blkDims[c] * S.rank[c]);
     }
-    out[0] = tau; out[1] = lag; out[2] = pinf; out[3] = p12[0]; out[4] = p12[1]; out[5] = (double)done;
     LB2_CATCH
 }
 

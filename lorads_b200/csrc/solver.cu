@@ -541,18 +541,25 @@ long long line_search(double rho, const double *sums, double p1, double p2, doub
     return rootNum;
 }
 
-int Solver::alm_inner_front(double rho, long long counter, double *tau, double *p12, long long *rootNum) {
+// The inner iteration is issued in two halves so that the host needs ONE synchronisation per iteration:
+//   front(k): L-BFGS direction, q1/q2/p1/p2, line-search sums          (device, no host input but the counter)
+//   back(k) : needs tau_k (host line search on the 7 scalars of front(k))
+// The loop enqueues back(k) and, speculatively, front(k+1) right behind it, then reads all scalars at once.
+// front() only writes the direction U, Dtemp, q1, q2 and scalar slots, so a speculative front that turns out
+// not to be needed (loop exit) is simply discarded.
+void Solver::enqueue_front(double rho, long long counter) {
     lbfgs_direction(counter);
     q12p12();
     if (world > 1) allreduce(S.p + SL_P1, 2);
     launch_linesearch_dots(ctx, m, b.p, s.p, lam.p, rho, q1.p, q2.p, S.p, SL_LS);
-    read_slots();
-    p12[0] = S_host[SL_P1]; p12[1] = S_host[SL_P2];
-    *rootNum = line_search(rho, S_host + SL_LS, p12[0], p12[1], tau);
-    return 0;
 }
 
-void Solver::alm_inner_back(double rho, double tau, double *lagNormSq, double *pinf1) {
+long long Solver::finish_front(double rho, double *tau, double *p12) {
+    p12[0] = S_host[SL_P1]; p12[1] = S_host[SL_P2];
+    return line_search(rho, S_host + SL_LS, p12[0], p12[1], tau);
+}
+
+void Solver::enqueue_back(double rho, double tau) {
     const int head = lb_head;
     launch_alm_step(ctx, N, tau, G.p, U.p, R.p, lb_y[head].p, lb_s[head].p);
     launch_alm_m_update(ctx, m, tau, q1.p, q2.p, s.p, lam.p, b.p, rho, M1.p);
@@ -567,11 +574,45 @@ void Solver::alm_inner_back(double rho, double tau, double *lagNormSq, double *p
     }
     lb_head = (head + 1) % lbfgs_len;
     primal_infeasibility(R.p);
-    read_slots();
+}
+
+void Solver::finish_back(double *lagNormSq, double *pinf1) {
     *lagNormSq = sum_grad_sq(*this);
     dimac_pinf = std::sqrt(S_host[SL_PINF]) / (1 + bNrm1);
     dimac_gap = std::fabs(pObj - dObj) / (1 + std::fabs(pObj) + std::fabs(dObj));
     *pinf1 = dimac_pinf;
+}
+
+int Solver::alm_inner_front(double rho, long long counter, double *tau, double *p12, long long *rootNum) {
+    enqueue_front(rho, counter);
+    read_slots();
+    *rootNum = finish_front(rho, tau, p12);
+    return 0;
+}
+
+void Solver::alm_inner_back(double rho, double tau, double *lagNormSq, double *pinf1) {
+    enqueue_back(rho, tau);
+    read_slots();
+    finish_back(lagNormSq, pinf1);
+}
+
+// `iters` inner iterations at fixed rho with the pipelined schedule (benchmark / host-buffer entry points);
+// counter k = 0,1,2,... as in a fresh sub-problem.  Returns the number of iterations done.
+long long Solver::run_inner_iters(double rho, long long iters, double *out) {
+    double tau = 0.0, p12[2] = {0, 0}, lag = 0, pinf = 0;
+    long long done = 0;
+    if (iters > 0) { enqueue_front(rho, 0); read_slots(); }
+    for (long long k = 0; k < iters; ++k) {
+        const long long rn = finish_front(rho, &tau, p12);
+        if (rn == 0) break;
+        enqueue_back(rho, tau);
+        if (k + 1 < iters) enqueue_front(rho, k + 1);
+        read_slots();
+        finish_back(&lag, &pinf);
+        done++;
+    }
+    out[0] = tau; out[1] = lag; out[2] = pinf; out[3] = p12[0]; out[4] = p12[1]; out[5] = (double)done;
+    return done;
 }
 
 // ---------------------------------------------------------------------------------------------------

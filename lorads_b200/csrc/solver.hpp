@@ -154,6 +154,11 @@ struct Solver {
     void update_sdp_var(double rho, double tol, long long maxit);
     void update_dual_var(double rho);
     // phases
+    void enqueue_front(double rho, long long counter);
+    long long finish_front(double rho, double *tau, double *p12);
+    void enqueue_back(double rho, double tau);
+    void finish_back(double *lagNormSq, double *pinf1);
+    long long run_inner_iters(double rho, long long iters, double *out);
     int alm_inner_front(double rho, long long counter, double *tau, double *p12, long long *rootNum);
     void alm_inner_back(double rho, double tau, double *lagNormSq, double *pinf1);
     void update_dimacs_alm();
