@@ -110,6 +110,7 @@ void Solver::obj_scale_dualvar(double f) {
         launch_scale(ctx, K.C_onP.p, (long long)K.C_onP.n, f);
         const long long nobj = K.listAC.dev.n_items - K.obj_item_begin;
         if (nobj > 0) launch_scale(ctx, K.listAC.coef.p + K.obj_item_begin, nobj, f);
+        K.c_rank1 *= f;
     }
     launch_scale(ctx, lam.p, m, f);
 }
@@ -506,7 +507,10 @@ void Solver::dual_infeasibility() {
         auto vec = [&](int l) { return Vb.p + (size_t)l * np2; };
         auto matvec = [&](const double *in, double *out) {
             if (K.dense_path) launch_dense_symv(ctx, n, K.S.p, in, out);
-            else launch_spmv_sym(ctx, n, K.adj_ptr.p, K.adj_col.p, K.adj_pos.p, K.S.p, in, out);
+            else if (K.c_rank1 != 0.0) {
+                launch_sum(ctx, n, in, S.p, SL_DG);
+                launch_spmv_sym(ctx, n, K.adj_ptr.p, K.adj_col.p, K.adj_pos.p, K.S.p, in, out, K.c_rank1, S.p + SL_DG);
+            } else launch_spmv_sym(ctx, n, K.adj_ptr.p, K.adj_col.p, K.adj_pos.p, K.S.p, in, out);
         };
         double theta = 0.0;
         const double tol = 1e-2;

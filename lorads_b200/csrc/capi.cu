@@ -132,7 +132,9 @@ int lb2_host_presolve(lb2_int n, lb2_int m, const lb2_int *beg, const lb2_int *i
     LB2_TRY
     ConeLayout L = build_cone_layout(n, m, beg, idx, elem);
     info[0] = L.psize(); info[1] = L.dense_path; info[2] = L.dense_cone; info[3] = L.n_act;
+    if (L.c_rank1 != 0.0 && L.dense_path) L = build_cone_layout(n, m, beg, idx, elem, false);
     info[4] = L.nnzA; info[5] = L.nnzC; info[6] = L.n_nonzero_coeff; info[7] = (lb2_int)L.listAC.split_row.size();
+    info[0] = L.psize(); info[1] = L.dense_path;
     if (!L.dense_path && rows && cols)
         for (size_t p = 0; p < L.P_row.size(); ++p) { rows[p] = L.P_row[p]; cols[p] = L.P_col[p]; }
     LB2_CATCH
@@ -235,10 +237,12 @@ int lb2_auv(lb2_solver *s, lb2_int c, char u, char v, double *constrVal, double 
     Solver &S = s->impl;
     ConeDev &K = S.cones.at(c);
     const bool same = (u == v);
-    S.cone_auv(K, obj != nullptr, S.factor_ptr(u), S.factor_ptr(v), same, 1.0, K.t1.p);
+    LB2_CUDA(cudaMemsetAsync(S.S.p + SL_OBJ, 0, sizeof(double), S.ctx.stream));
+    S.cone_auv(K, obj != nullptr, S.factor_ptr(u), S.factor_ptr(v), same, 1.0, K.t1.p, obj ? S.S.p + SL_OBJ : nullptr);
+    if (obj && S.world > 1) S.allreduce(S.S.p + SL_OBJ, 1);
     S.expand_cv_from(K, K.t1.p, S.cvfull.p);
     LB2_CUDA(cudaMemcpyAsync(constrVal, S.cvfull.p, sizeof(double) * S.m, cudaMemcpyDeviceToHost, S.ctx.stream));
-    if (obj) LB2_CUDA(cudaMemcpyAsync(obj, K.t1.p + K.n_act, sizeof(double), cudaMemcpyDeviceToHost, S.ctx.stream));
+    if (obj) LB2_CUDA(cudaMemcpyAsync(obj, S.S.p + SL_OBJ, sizeof(double), cudaMemcpyDeviceToHost, S.ctx.stream));
     S.sync();
     LB2_CATCH
 }

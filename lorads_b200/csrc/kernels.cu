@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(kBlock) spmm_sym_kernel(long long n, int ld, c
                                                           const int *__restrict__ adj_pos, const double *__restrict__ S,
                                                           const double *__restrict__ X, double a, double b,
                                                           const double *__restrict__ Z, const double *__restrict__ Z2,
-                                                          double *__restrict__ Y, ReduceScratch rs, double *red) {
+                                                          double *__restrict__ Y, ReduceScratch rs, double *red,
+                                                          const double *__restrict__ cs, double c1) {
     constexpr int NG = kBlock / G;
     constexpr int UN = 4;
     const int g = threadIdx.x / G, gl = threadIdx.x % G;
@@ -326,7 +327,10 @@ __global__ void __launch_bounds__(kBlock) spmm_sym_kernel(long long n, int ld, c
     for (long long i = (long long)blockIdx.x * NG + g; i < n; i += (long long)gridDim.x * NG) {
         double2 acc[NP];
 #pragma unroll
-        for (int q = 0; q < NP; ++q) acc[q] = make_double2(0.0, 0.0);
+        for (int q = 0; q < NP; ++q) {
+            const int col = 2 * gl + 2 * G * q;
+            acc[q] = (cs && col < ld) ? make_double2(c1 * cs[col], c1 * cs[col + 1]) : make_double2(0.0, 0.0);
+        }
         const int ea = adj_ptr[i], eb = adj_ptr[i + 1];
         for (int e = ea; e < eb; e += UN) {
             int jn[UN];
@@ -380,31 +384,31 @@ __global__ void __launch_bounds__(kBlock) spmm_sym_kernel(long long n, int ld, c
 template <int G>
 static void launch_spmm_g(Ctx &c, int np, long long n, int ld, const int *ap, const int *ac, const int *apos,
                           const double *S, const double *X, double a, double b, const double *Z, const double *Z2,
-                          double *Y, double *red) {
+                          double *Y, double *red, const double *cs, double c1) {
     constexpr int NG = kBlock / G;
     long long blocks = (n + NG - 1) / NG;      // one row per lane group; the hardware balances the CTAs
     if (blocks > 8192) blocks = 8192;           // capacity of the reduction scratch (grid-stride beyond that)
     const int grid = (int)blocks;
     switch (np) {
-    case 1: spmm_sym_kernel<G, 1><<<grid, kBlock, 0, c.stream>>>(n, ld, ap, ac, apos, S, X, a, b, Z, Z2, Y, c.rs, red); break;
-    case 2: spmm_sym_kernel<G, 2><<<grid, kBlock, 0, c.stream>>>(n, ld, ap, ac, apos, S, X, a, b, Z, Z2, Y, c.rs, red); break;
-    case 3: spmm_sym_kernel<G, 3><<<grid, kBlock, 0, c.stream>>>(n, ld, ap, ac, apos, S, X, a, b, Z, Z2, Y, c.rs, red); break;
-    default: spmm_sym_kernel<G, 4><<<grid, kBlock, 0, c.stream>>>(n, ld, ap, ac, apos, S, X, a, b, Z, Z2, Y, c.rs, red); break;
+    case 1: spmm_sym_kernel<G, 1><<<grid, kBlock, 0, c.stream>>>(n, ld, ap, ac, apos, S, X, a, b, Z, Z2, Y, c.rs, red, cs, c1); break;
+    case 2: spmm_sym_kernel<G, 2><<<grid, kBlock, 0, c.stream>>>(n, ld, ap, ac, apos, S, X, a, b, Z, Z2, Y, c.rs, red, cs, c1); break;
+    case 3: spmm_sym_kernel<G, 3><<<grid, kBlock, 0, c.stream>>>(n, ld, ap, ac, apos, S, X, a, b, Z, Z2, Y, c.rs, red, cs, c1); break;
+    default: spmm_sym_kernel<G, 4><<<grid, kBlock, 0, c.stream>>>(n, ld, ap, ac, apos, S, X, a, b, Z, Z2, Y, c.rs, red, cs, c1); break;
     }
     LB2_LAUNCH_CHECK(c);
 }
 
 void launch_spmm(Ctx &c, long long n, int ld, const int *adj_ptr, const int *adj_col, const int *adj_pos,
                  const double *S, const double *X, double a, double b, const double *Z, const double *Z2, double *Y,
-                 double *red) {
+                 double *red, const double *cs, double c1) {
     if (ld > 256) throw std::runtime_error("rank above 256 is not supported by the SpMM kernel yet");
     int G = ld <= 32 ? 4 : (ld <= 64 ? 8 : (ld <= 128 ? 16 : 32));
     int np = (ld + 2 * G - 1) / (2 * G);
     switch (G) {
-    case 4: launch_spmm_g<4>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red); break;
-    case 8: launch_spmm_g<8>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red); break;
-    case 16: launch_spmm_g<16>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red); break;
-    default: launch_spmm_g<32>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red); break;
+    case 4: launch_spmm_g<4>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red, cs, c1); break;
+    case 8: launch_spmm_g<8>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red, cs, c1); break;
+    case 16: launch_spmm_g<16>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red, cs, c1); break;
+    default: launch_spmm_g<32>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red, cs, c1); break;
     }
 }
 
@@ -598,17 +602,18 @@ void launch_dense_symm(Ctx &c, long long n, int r, int ld, const double *Sp, con
 __global__ void __launch_bounds__(kBlock) spmv_sym_kernel(long long n, const int *__restrict__ adj_ptr,
                                                           const int *__restrict__ adj_col, const int *__restrict__ adj_pos,
                                                           const double *__restrict__ S, const double *__restrict__ x,
-                                                          double *__restrict__ y) {
+                                                          double *__restrict__ y, double c1, const double *sum_slot) {
+    const double shift = sum_slot ? c1 * (*sum_slot) : 0.0;
     for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
-        double acc = 0.0;
+        double acc = shift;
         for (int e = adj_ptr[i]; e < adj_ptr[i + 1]; ++e) acc = fma(S[adj_pos[e]], x[adj_col[e]], acc);
         y[i] = acc;
     }
 }
 
 void launch_spmv_sym(Ctx &c, long long n, const int *adj_ptr, const int *adj_col, const int *adj_pos, const double *S,
-                     const double *x, double *y) {
-    spmv_sym_kernel<<<grid_for(n, 1, c), kBlock, 0, c.stream>>>(n, adj_ptr, adj_col, adj_pos, S, x, y);
+                     const double *x, double *y, double c1, const double *sum_slot) {
+    spmv_sym_kernel<<<grid_for(n, 1, c), kBlock, 0, c.stream>>>(n, adj_ptr, adj_col, adj_pos, S, x, y, c1, sum_slot);
     LB2_LAUNCH_CHECK(c);
 }
 
@@ -694,22 +699,90 @@ void launch_axpby_dot(Ctx &c, long long n, double *out, Coef a, const double *x,
 }
 
 __global__ void __launch_bounds__(kBlock) dot_kernel(long long n, const double *__restrict__ x,
-                                                     const double *__restrict__ y, double *S, int slot, bool absx,
+                                                     const double *__restrict__ y, double *S, int slot, int mode,
                                                      ReduceScratch rs) {
-    double acc = 0.0;
+    double acc = 0.0;   // mode 0: sum x*y, 1: sum |x|, 2: sum x
     for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n; q += (long long)gridDim.x * kBlock)
-        acc += absx ? fabs(x[q]) : x[q] * y[q];
+        acc += mode == 0 ? x[q] * y[q] : (mode == 1 ? fabs(x[q]) : x[q]);
     double v[1] = {acc};
     if (grid_reduce<1>(v, rs) && threadIdx.x == 0) S[slot] = v[0];
 }
 
 void launch_dot(Ctx &c, long long n, const double *x, const double *y, double *S, int slot) {
-    dot_kernel<<<grid_for(n, 8, c), kBlock, 0, c.stream>>>(n, x, y, S, slot, false, c.rs);
+    dot_kernel<<<grid_for(n, 8, c), kBlock, 0, c.stream>>>(n, x, y, S, slot, 0, c.rs);
     LB2_LAUNCH_CHECK(c);
 }
 
 void launch_asum(Ctx &c, long long n, const double *x, double *S, int slot) {
-    dot_kernel<<<grid_for(n, 8, c), kBlock, 0, c.stream>>>(n, x, x, S, slot, true, c.rs);
+    dot_kernel<<<grid_for(n, 8, c), kBlock, 0, c.stream>>>(n, x, x, S, slot, 1, c.rs);
+    LB2_LAUNCH_CHECK(c);
+}
+
+void launch_sum(Ctx &c, long long n, const double *x, double *S, int slot) {
+    dot_kernel<<<grid_for(n, 8, c), kBlock, 0, c.stream>>>(n, x, x, S, slot, 2, c.rs);
+    LB2_LAUNCH_CHECK(c);
+}
+
+// column sums of a row-major n x ld factor: each warp walks rows (lane = column, coalesced), block partials are
+// combined in a fixed order by the last block
+__global__ void __launch_bounds__(kBlock) colsum_kernel(long long n, int ld, const double *__restrict__ X,
+                                                        double *__restrict__ out, double *__restrict__ scratch,
+                                                        unsigned int *ticket) {
+    __shared__ double sm[8][256];
+    __shared__ bool s_last;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+    for (long long i = (long long)blockIdx.x * 8 + w; i < n; i += (long long)gridDim.x * 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int col = lane + 32 * q;
+            if (col < ld) acc[q] += X[i * ld + col];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sm[w][lane + 32 * q] = acc[q];
+    __syncthreads();
+    for (int col = threadIdx.x; col < ld; col += kBlock) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][col];
+        scratch[(size_t)blockIdx.x * ld + col] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int col = threadIdx.x; col < ld; col += kBlock) {
+        double t = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) t += __ldcg(scratch + (size_t)b * ld + col);
+        out[col] = t;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+void launch_colsum(Ctx &c, long long n, int ld, const double *X, double *out, double *scratch) {
+    if (ld > 256) throw std::runtime_error("rank above 256 is not supported by the column-sum kernel yet");
+    long long blocks = (n + 7) / 8;
+    const long long cap = (long long)c.num_sms * 4;
+    if (blocks > cap) blocks = cap;
+    colsum_kernel<<<(unsigned)blocks, kBlock, 0, c.stream>>>(n, ld, X, out, scratch, c.ticket);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void rank1_obj_kernel(int ld, const double *csA, const double *csB, double k1, double *obj1, double k2, double *obj2) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < ld; ++k) { a = fma(csA[k], csB[k], a); b = fma(csB[k], csB[k], b); }
+    if (obj1) *obj1 += k1 * a;
+    if (obj2) *obj2 += k2 * b;
+}
+
+void launch_rank1_obj(Ctx &c, int ld, const double *csA, const double *csB, double k1, double *obj1, double k2, double *obj2) {
+    rank1_obj_kernel<<<1, 32, 0, c.stream>>>(ld, csA, csB, k1, obj1, k2, obj2);
     LB2_LAUNCH_CHECK(c);
 }
 

@@ -53,9 +53,16 @@ void launch_wsum(Ctx &c, double *S, long long np, const double *C_onP, const int
 
 // Y[i,:] = a * sum_{e in adj(i)} S[adj_pos[e]] * X[adj_col[e],:] + b * Z[i,:]   (Z may be null)
 // red[0] = sum Y.Y, red[1] = sum Y.Z2 (Z2 may be null) when red != nullptr.
+// cs != nullptr adds the rank-one part of the objective: S_eff = S + c1 * e e^T with cs = column sums of X.
 void launch_spmm(Ctx &c, long long n, int ld, const int *adj_ptr, const int *adj_col, const int *adj_pos,
                  const double *S, const double *X, double a, double b, const double *Z, const double *Z2,
-                 double *Y, double *red);
+                 double *Y, double *red, const double *cs = nullptr, double c1 = 0.0);
+
+// rank-one objective C = c1 * e e^T (+ sparse remainder): column sums of a factor, and the objective terms
+// out[k] = sum_i X[i,k]  (deterministic two-level sum; scratch >= 4*148*ld doubles)
+void launch_colsum(Ctx &c, long long n, int ld, const double *X, double *out, double *scratch);
+// *obj1 += k1 * <csA, csB> ; if obj2: *obj2 += k2 * <csB, csB>
+void launch_rank1_obj(Ctx &c, int ld, const double *csA, const double *csB, double k1, double *obj1, double k2, double *obj2);
 
 // ------------------------------------------------------------------------------------------------
 // dense path (cones whose scratch matrices are dense, lorads_sdp_conic.c:884-963)
@@ -74,8 +81,10 @@ void launch_dense_symm(Ctx &c, long long n, int r, int ld, const double *Sp, con
 
 // y = S x for one n-vector (dual infeasibility Lanczos; reference mv: dataMatSparseMV / dataMatDenseMV,
 // lorads_sdp_data.c:506-521,673-696)
+// when sum_slot != nullptr: y += c1 * (*sum_slot)   (rank-one part: c1 * e (e^T x), *sum_slot = sum of x)
 void launch_spmv_sym(Ctx &c, long long n, const int *adj_ptr, const int *adj_col, const int *adj_pos, const double *S,
-                     const double *x, double *y);
+                     const double *x, double *y, double c1 = 0.0, const double *sum_slot = nullptr);
+void launch_sum(Ctx &c, long long n, const double *x, double *S, int slot);   // S[slot] = sum x
 void launch_dense_symv(Ctx &c, long long n, const double *Sp, const double *x, double *y);
 
 // ------------------------------------------------------------------------------------------------

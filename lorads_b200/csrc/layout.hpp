@@ -53,6 +53,7 @@ struct ConeLayout {
     int64_t nnzA = 0, nnzC = 0;
     int64_t n_nonzero_coeff = 0;    // "nnzStat": number of non-zero constraint matrices (lorads_sdp_data.c:190)
     bool c_is_dense_type = false, any_dense_coeff = false;
+    double c_rank1 = 0.0;           // C = c_rank1 * e e^T + (sparse remainder stored as the objective column)
     double cNrm1 = 0, cNrm2Sq = 0, cNrmInf = 0;
 
     // sparse path
@@ -112,20 +113,20 @@ inline void finish_item_list(ItemList &L) {
 }
 
 // Build the layout of one cone from the reader's arrays (column 0 = C, column i = A_i).
-inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg, const int64_t *idx, const double *elem) {
+inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in, const int64_t *idx, const double *elem,
+                                    bool allow_rank_one = true) {
     ConeLayout L;
     L.n = n; L.m = m;
     const double packedSize = (double)(n * (n + 1) / 2);
-    const int64_t nnz_all = beg[m + 1];
-    if (nnz_all > (int64_t)2000000000) throw std::runtime_error("cone has more than 2^31 non-zeros");
+    if (beg_in[m + 1] > (int64_t)2000000000) throw std::runtime_error("cone has more than 2^31 non-zeros");
 
     // --- per-column sorted copies (dataMatCreateSparseImpl sorts when needed, lorads_sdp_data.c:106-108)
-    std::vector<int64_t> sidx(idx, idx + nnz_all);
-    std::vector<double> sval(elem, elem + nnz_all);
+    std::vector<int64_t> sidx(idx, idx + beg_in[m + 1]);
+    std::vector<double> sval(elem, elem + beg_in[m + 1]);
     {
         std::vector<int64_t> perm;
         for (int64_t c = 0; c <= m; ++c) {
-            int64_t a = beg[c], b = beg[c + 1];
+            int64_t a = beg_in[c], b = beg_in[c + 1];
             if (b - a < 2 || std::is_sorted(sidx.begin() + a, sidx.begin() + b)) continue;
             perm.resize(b - a);
             std::iota(perm.begin(), perm.end(), (int64_t)0);
@@ -133,6 +134,41 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg, co
             for (int64_t k = 0; k < b - a; ++k) { sidx[a + k] = idx[a + perm[k]]; sval[a + k] = elem[a + perm[k]]; }
         }
     }
+
+    // objective norms on the ORIGINAL C (dataMatSparseNrm1/Nrm2Square/NrmInf lorads_sdp_data.c:148-183; the dense
+    // variants :227-272 are the same sums over the packed array)
+    for (int64_t k = beg_in[0]; k < beg_in[1]; ++k) {
+        int64_t r_, c_; unpack_lower(n, sidx[k], r_, c_);
+        const double v = sval[k], a = std::fabs(v);
+        const bool diag = r_ == c_;
+        L.cNrm1 += diag ? a : 2 * a;
+        L.cNrm2Sq += diag ? v * v : 2 * v * v;
+        L.cNrmInf = std::max(L.cNrmInf, a);
+    }
+
+    // --- rank-one objective: a fully populated C whose entries are (almost) all one value c is stored as
+    // c * e e^T plus a sparse remainder (north_star "rank-one layouts"; e.g. C = -J of the Lovasz theta SDP).
+    // <c ee^T, sym(UV^T)> = c (e^T U)(V^T e) and (c ee^T) X = c e (e^T X) are evaluated from column sums, so the
+    // cone stays on the sparse scratch path instead of the O(n^2) dense one the reference takes.
+    std::vector<int64_t> vbeg(beg_in, beg_in + m + 2);
+    if (allow_rank_one && n >= 20 && vbeg[1] - vbeg[0] == n * (n + 1) / 2) {
+        const double v0 = sval[vbeg[0]];
+        int64_t same = 0;
+        for (int64_t k = vbeg[0]; k < vbeg[1]; ++k) same += (sval[k] == v0);
+        if ((double)same >= 0.9 * packedSize) {
+            L.c_rank1 = v0;
+            // compact the arrays: objective column keeps only the entries that differ from v0 (minus v0)
+            int64_t w = 0;
+            for (int64_t k = vbeg[0]; k < vbeg[1]; ++k)
+                if (sval[k] != v0) { sidx[w] = sidx[k]; sval[w] = sval[k] - v0; ++w; }
+            const int64_t removed = (vbeg[1] - vbeg[0]) - w;
+            for (int64_t k = vbeg[1]; k < vbeg[m + 1]; ++k) { sidx[k - removed] = sidx[k]; sval[k - removed] = sval[k]; }
+            for (int64_t c = 1; c <= m + 1; ++c) vbeg[c] -= removed;
+            sidx.resize(vbeg[m + 1]); sval.resize(vbeg[m + 1]);
+        }
+    }
+    const int64_t *beg = vbeg.data();
+    const int64_t nnz_all = beg[m + 1];
 
     // --- classification (lorads_sdp_data.c:818-824) and statistics
     auto is_dense_type = [&](int64_t nnz) { return (double)nnz > 0.1 * packedSize; };
@@ -169,15 +205,6 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg, co
                 ecol[k] = (int32_t)j;
             }
         }
-    }
-
-    // objective norms (dataMatSparseNrm1/Nrm2Square/NrmInf lorads_sdp_data.c:148-183; dense variants :227-272)
-    for (int64_t k = beg[0]; k < beg[1]; ++k) {
-        double v = sval[k], a = std::fabs(v);
-        bool diag = erow[k] == ecol[k];
-        L.cNrm1 += diag ? a : 2 * a;
-        L.cNrm2Sq += diag ? v * v : 2 * v * v;
-        L.cNrmInf = std::max(L.cNrmInf, a);
     }
 
     // --- scratch type decision (AConePresolveData, lorads_sdp_conic.c:884-989)

@@ -86,7 +86,11 @@ void Solver::preprocess() {
     for (long long c = 0; c < nCones; ++c) {
         if (!inputs[c].set) throw std::logic_error("cone data missing: call lb2_set_cone_data for every cone");
         ConeLayout L = build_cone_layout(blkDims[c], m, inputs[c].beg.data(), inputs[c].idx.data(), inputs[c].elem.data());
+        if (L.c_rank1 != 0.0 && L.dense_path)   // the dense scratch kernels take C as it is
+            L = build_cone_layout(blkDims[c], m, inputs[c].beg.data(), inputs[c].idx.data(), inputs[c].elem.data(), false);
         ConeDev &K = cones[c];
+        K.c_rank1 = L.c_rank1;
+        if (K.c_rank1 != 0.0) { K.csA.alloc(256); K.csB.alloc(256); K.cs_scratch.alloc((size_t)4 * ctx.num_sms * 256); }
         K.n = L.n; K.dense_path = L.dense_path; K.dense_cone = L.dense_cone; K.n_act = L.n_act;
         K.np = L.psize(); K.nnzA = L.nnzA; K.nnzC = L.nnzC; K.n_nonzero_coeff = L.n_nonzero_coeff;
         K.cNrm1 = L.cNrm1; K.cNrm2Sq = L.cNrm2Sq; K.cNrmInf = L.cNrmInf;
@@ -285,6 +289,12 @@ void Solver::cone_auv(ConeDev &K, bool with_obj, const double *Um, const double 
     // with column sharding the objective is summed over ranks by the caller (the slot is all-reduced once)
     launch_auv(ctx, same ? AUV_SAME : AUV_PAIR, L.dev, Um + K.off, Vm + K.off, K.ld, scale, 0.0, out, nullptr,
                K.carry1.p, nullptr, obj, nullptr);
+    if (with_obj && obj && K.c_rank1 != 0.0) {
+        // <c ee^T, sym(U V^T)> = c (e^T U)(V^T e)
+        launch_colsum(ctx, K.n, K.ld, Um + K.off, K.csA.p, K.cs_scratch.p);
+        if (!same) launch_colsum(ctx, K.n, K.ld, Vm + K.off, K.csB.p, K.cs_scratch.p);
+        launch_rank1_obj(ctx, K.ld, K.csA.p, same ? K.csA.p : K.csB.p, scale * K.c_rank1, obj, 0.0, nullptr);
+    }
     if (world > 1) allreduce(out, L.dev.n_rows);
 }
 
@@ -300,11 +310,17 @@ void Solver::cone_auv_dual(ConeDev &K, const double *Rm, const double *Dm, doubl
         return;
     }
     launch_auv(ctx, AUV_DUAL, L.dev, Rm + K.off, Dm + K.off, K.ld, 2.0, 1.0, out1, out2, K.carry1.p, K.carry2.p, obj1, obj2);
+    if (K.c_rank1 != 0.0 && obj1 && obj2) {
+        launch_colsum(ctx, K.n, K.ld, Rm + K.off, K.csA.p, K.cs_scratch.p);
+        launch_colsum(ctx, K.n, K.ld, Dm + K.off, K.csB.p, K.cs_scratch.p);
+        launch_rank1_obj(ctx, K.ld, K.csA.p, K.csB.p, 2.0 * K.c_rank1, obj1, K.c_rank1, obj2);
+    }
     if (world > 1) { allreduce(out1, L.dev.n_rows); allreduce(out2, L.dev.n_rows); }
 }
 
 void Solver::cone_wsum(ConeDev &K, const double *w, bool w_compact, bool addC) {
     const int *map = K.identity_act ? nullptr : K.act_idx.p;
+    K.S_has_C = addC;
     if (K.dense_path)
         launch_dense_wsum(ctx, K.S.p, K.np, K.C_onP.p, K.D_pos.p, K.n_pos, K.T_ptr.p, K.T_con.p, K.T_val.p, w, map,
                           w_compact, addC);
@@ -317,9 +333,12 @@ void Solver::cone_mul(ConeDev &K, const double *X, double a, double bcoef, const
     if (K.dense_path)
         launch_dense_symm(ctx, K.n, K.r, K.ld, K.S.p, X + K.off, a, bcoef, Z ? Z + K.off : nullptr,
                           Z2 ? Z2 + K.off : nullptr, Y + K.off, red);
-    else
+    else {
+        const bool r1 = K.c_rank1 != 0.0 && K.S_has_C;      // (S + c ee^T) X = S X + c e (e^T X)
+        if (r1) launch_colsum(ctx, K.n, K.ld, X + K.off, K.csA.p, K.cs_scratch.p);
         launch_spmm(ctx, K.n, K.ld, K.adj_ptr.p, K.adj_col.p, K.adj_pos.p, K.S.p, X + K.off, a, bcoef,
-                    Z ? Z + K.off : nullptr, Z2 ? Z2 + K.off : nullptr, Y + K.off, red);
+                    Z ? Z + K.off : nullptr, Z2 ? Z2 + K.off : nullptr, Y + K.off, red, r1 ? K.csA.p : nullptr, K.c_rank1);
+    }
 }
 
 void Solver::init_constr_val_all(const double *Um, const double *Vm, bool same) {

@@ -41,6 +41,9 @@ struct ConeDev {
     long long n_act = 0, np = 0, nnzA = 0, nnzC = 0, n_nonzero_coeff = 0, n_pos = 0;
     long long obj_item_begin = 0;   // first objective item of listAC
     double cNrm1 = 0, cNrm2Sq = 0, cNrmInf = 0;
+    double c_rank1 = 0.0;            // C = c_rank1 * e e^T + sparse remainder (0: no rank-one part)
+    bool S_has_C = false;            // the last weighted sum written to S included the objective
+    DBuf<double> csA, csB, cs_scratch;   // column sums of factors for the rank-one objective
     std::vector<int32_t> act_idx_h;
     std::vector<int32_t> P_row_h, P_col_h;          // kept for lb2_get_pattern / dual infeasibility
     DBuf<int> act_idx;

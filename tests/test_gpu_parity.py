@@ -123,7 +123,22 @@ EDGE_CASES = {
     # dense scratch path (C = -J), identity constraint with n entries among single-entry constraints
     "theta_dense": (lambda: sdpa.lovasz_theta(90, 500, 48), {}),
     "tiny_dense": (lambda: sdpa.maxcut(16, 40, 49), {}),
+    # C = -J is stored as a rank-one term: the cone stays on the sparse path although the reference goes dense
+    "theta_rank_one": (lambda: sdpa.lovasz_theta(300, 1500, 50), {}),
+    "theta_rank_one_plus_remainder": (lambda: _theta_with_remainder(260, 1200, 52), {}),
 }
+
+
+def _theta_with_remainder(n, e, seed):
+    """Lovasz-theta data whose objective is -J except for a few perturbed entries (rank-one + sparse remainder)."""
+    inst = sdpa.lovasz_theta(n, e, seed)
+    cone = inst.cones[0]
+    elem = cone.elem.copy()
+    rng = np.random.default_rng(seed)
+    k = rng.choice(cone.beg[1], size=40, replace=False)
+    elem[k] += rng.standard_normal(40)
+    inst.cones[0] = sdpa.Cone(n=cone.n, beg=cone.beg, idx=cone.idx, elem=elem)
+    return inst
 
 
 @pytest.mark.parametrize("case", sorted(EDGE_CASES))
@@ -133,10 +148,14 @@ def test_against_restatement(case):
     inst = make()
     G = gpu_solver(inst, **kw)
     O = restate.OracleSolver(inst, times_log_rank=kw.get("times_log_rank", 2.0))
-    assert G.rank() == O.rank() and G.info(6) == O.info(6)
+    assert G.rank() == O.rank()
+    if case.startswith("theta_rank_one"):
+        assert G.info(6) == 0 and O.info(6) == 1     # rank-one objective: sparse path here, dense in the reference
+    else:
+        assert G.info(6) == O.info(6)
     for f in "RUV":
         assert np.array_equal(G.get_factor(f), O.factor(f))
-    if not G.info(6):
+    if not G.info(6) and not O.info(6):
         assert all(np.array_equal(a, b) for a, b in zip(G.pattern(), O.pattern()))
     for u, v in (("R", "R"), ("U", "V"), ("V", "U")):
         a, o = G.auv(u, v, with_obj=True)
