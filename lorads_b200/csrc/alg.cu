@@ -106,6 +106,7 @@ bool Solver::aug_rank(double aug) {
 void Solver::obj_scale_dualvar(double f) {
     // objScale_dualvar, lorads_solver.c:1040-1052: C *= f on every cone, lambda *= f, scaleObjHis *= f
     scaleObjHis *= f;
+    drop_graphs();       // the rank-one objective coefficient is a by-value kernel argument of captured launches
     for (ConeDev &K : cones) {
         launch_scale(ctx, K.C_onP.p, (long long)K.C_onP.n, f);
         const long long nobj = K.listAC.dev.n_items - K.obj_item_begin;
@@ -189,7 +190,7 @@ alg_start:
             while (cert_val - cert_tol > P->endALMSubTol) {
                 if (reset_rule(localIter)) clearLBFGS = 0;
                 double p12[2];
-                if (!spec || spec_counter != clearLBFGS) { enqueue_front(alm.rho, clearLBFGS); read_slots(); }
+                if (!spec || spec_counter != clearLBFGS) { push_scalars(tau, alm.rho); enqueue_front(alm.rho, clearLBFGS); read_slots(); }
                 spec = false;
                 const long long rootNum = finish_front(alm.rho, &tau, p12);
                 if (rootNum == 0) { retcode = LB2_RET_NUM_ERR; jump = GO_END_ALM; goto after_loops; }
@@ -200,11 +201,9 @@ alg_start:
                     break;
                 }
                 double pinf1 = 0;
-                enqueue_back(alm.rho, tau);
                 spec_counter = reset_rule(localIter + 1) ? 0 : clearLBFGS + 1;
-                enqueue_front(alm.rho, spec_counter);      // next iteration's front half rides behind this one
+                iter_back_front(alm.rho, tau, spec_counter);   // back half + next iteration's front half, one graph
                 spec = true;
-                read_slots();
                 finish_back(&lagSq, &pinf1);
                 alm.pinf_1 = pinf1;
                 alm.pinf_inf = pinf1 * (1 + bNrm1) / (1 + bNrmInf);

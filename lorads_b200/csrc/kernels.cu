@@ -798,9 +798,10 @@ void launch_neg_if_nonneg(Ctx &c, long long n, double *D, const double *G, const
     LB2_LAUNCH_CHECK(c);
 }
 
-__global__ void __launch_bounds__(kBlock) alm_step_kernel(long long n, double tau, const double *__restrict__ G,
+__global__ void __launch_bounds__(kBlock) alm_step_kernel(long long n, const double *tau_p, const double *__restrict__ G,
                                                           const double *__restrict__ D, double *__restrict__ R,
                                                           double *__restrict__ y, double *__restrict__ s) {
+    const double tau = *tau_p;
     for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n; q += (long long)gridDim.x * kBlock) {
         const double d = D[q];
         y[q] = -G[q];
@@ -809,8 +810,8 @@ __global__ void __launch_bounds__(kBlock) alm_step_kernel(long long n, double ta
     }
 }
 
-void launch_alm_step(Ctx &c, long long n, double tau, const double *G, const double *D, double *R, double *y, double *s) {
-    alm_step_kernel<<<grid_for(n, 4, c), kBlock, 0, c.stream>>>(n, tau, G, D, R, y, s);
+void launch_alm_step(Ctx &c, long long n, const double *tau_p, const double *G, const double *D, double *R, double *y, double *s) {
+    alm_step_kernel<<<grid_for(n, 4, c), kBlock, 0, c.stream>>>(n, tau_p, G, D, R, y, s);
     LB2_LAUNCH_CHECK(c);
 }
 
@@ -838,10 +839,11 @@ void launch_cg_update(Ctx &c, long long n, double *x, double *r, const double *p
 
 __global__ void __launch_bounds__(kBlock) linesearch_dots_kernel(long long m, const double *__restrict__ b,
                                                                  const double *__restrict__ s,
-                                                                 const double *__restrict__ lam, double rhoInv,
+                                                                 const double *__restrict__ lam, const double *rho_p,
                                                                  const double *__restrict__ q1,
                                                                  const double *__restrict__ q2, double *S, int slot,
                                                                  ReduceScratch rs) {
+    const double rhoInv = 1.0 / (*rho_p);
     double v[5] = {0, 0, 0, 0, 0};
     for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < m; i += (long long)gridDim.x * kBlock) {
         const double q0 = fma(rhoInv, lam[i], b[i] - s[i]);
@@ -856,17 +858,18 @@ __global__ void __launch_bounds__(kBlock) linesearch_dots_kernel(long long m, co
         for (int k = 0; k < 5; ++k) S[slot + k] = v[k];
 }
 
-void launch_linesearch_dots(Ctx &c, long long m, const double *b, const double *s, const double *lam, double rho,
+void launch_linesearch_dots(Ctx &c, long long m, const double *b, const double *s, const double *lam, const double *rho_p,
                             const double *q1, const double *q2, double *S, int slot) {
-    linesearch_dots_kernel<<<grid_for(m, 4, c), kBlock, 0, c.stream>>>(m, b, s, lam, 1.0 / rho, q1, q2, S, slot, c.rs);
+    linesearch_dots_kernel<<<grid_for(m, 4, c), kBlock, 0, c.stream>>>(m, b, s, lam, rho_p, q1, q2, S, slot, c.rs);
     LB2_LAUNCH_CHECK(c);
 }
 
-__global__ void __launch_bounds__(kBlock) alm_m_update_kernel(long long m, double tau, const double *__restrict__ q1,
+__global__ void __launch_bounds__(kBlock) alm_m_update_kernel(long long m, const double *tau_p, const double *__restrict__ q1,
                                                               const double *__restrict__ q2, double *__restrict__ s,
                                                               const double *__restrict__ lam,
-                                                              const double *__restrict__ b, double rho,
+                                                              const double *__restrict__ b, const double *rho_p,
                                                               double *__restrict__ M1) {
+    const double tau = q1 ? *tau_p : 0.0, rho = *rho_p;
     const double t2 = tau * tau;
     for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < m; i += (long long)gridDim.x * kBlock) {
         double sv = s[i];
@@ -879,9 +882,9 @@ __global__ void __launch_bounds__(kBlock) alm_m_update_kernel(long long m, doubl
     }
 }
 
-void launch_alm_m_update(Ctx &c, long long m, double tau, const double *q1, const double *q2, double *s,
-                         const double *lam, const double *b, double rho, double *M1) {
-    alm_m_update_kernel<<<grid_for(m, 4, c), kBlock, 0, c.stream>>>(m, tau, q1, q2, s, lam, b, rho, M1);
+void launch_alm_m_update(Ctx &c, long long m, const double *tau_p, const double *q1, const double *q2, double *s,
+                         const double *lam, const double *b, const double *rho_p, double *M1) {
+    alm_m_update_kernel<<<grid_for(m, 4, c), kBlock, 0, c.stream>>>(m, tau_p, q1, q2, s, lam, b, rho_p, M1);
     LB2_LAUNCH_CHECK(c);
 }
 

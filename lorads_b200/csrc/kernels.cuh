@@ -111,18 +111,19 @@ void launch_asum(Ctx &c, long long n, const double *x, double *S, int slot);
 // if (S[cond_slot] >= 0) D = -G           (LBFGSDirectionUseGrad, lorads_alm.c:469-489)
 void launch_neg_if_nonneg(Ctx &c, long long n, double *D, const double *G, const double *S, int cond_slot);
 // y = -G ; s = tau*D ; R += tau*D         (SetyAsNegGrad :583, ALMupdateVar :619, first half of setlbfgsHisTwo :657)
-void launch_alm_step(Ctx &c, long long n, double tau, const double *G, const double *D, double *R, double *y, double *s);
+// tau is read from *tau_p (a device scalar slot) so that the launch can live in a replayed CUDA graph
+void launch_alm_step(Ctx &c, long long n, const double *tau_p, const double *G, const double *D, double *R, double *y, double *s);
 // x += alpha*p ; r -= alpha*Q ; S[slot_rr] = sum r*r  with alpha = S[slot_num]/S[slot_den]  (lorads_cgs.c:183-189)
 void launch_cg_update(Ctx &c, long long n, double *x, double *r, const double *p, const double *Q, double *S,
                       int slot_num, int slot_den, int slot_rr);
 
 // line-search sums over m (ALMLineSearch, lorads_alm.c:161-172): q0 = b - s + lambda/rho
 // S[slot+0]=|q2|^2  S[slot+1]=q1.q2  S[slot+2]=q0.q2  S[slot+3]=|q1|^2  S[slot+4]=q0.q1
-void launch_linesearch_dots(Ctx &c, long long m, const double *b, const double *s, const double *lam, double rho,
+void launch_linesearch_dots(Ctx &c, long long m, const double *b, const double *s, const double *lam, const double *rho_p,
                             const double *q1, const double *q2, double *S, int slot);
 // s += tau*q1 + tau^2*q2 (when q1 != nullptr) ; M1 = -lambda - rho*b + rho*s   (lorads_alm.c:1123-1124, 15-27)
-void launch_alm_m_update(Ctx &c, long long m, double tau, const double *q1, const double *q2, double *s,
-                         const double *lam, const double *b, double rho, double *M1);
+void launch_alm_m_update(Ctx &c, long long m, const double *tau_p, const double *q1, const double *q2, double *s,
+                         const double *lam, const double *b, const double *rho_p, double *M1);
 // S[slot] = sum (b - s)^2  (primalInfeasibility, lorads_alg_common.c:255-257)
 void launch_resid_sq(Ctx &c, long long m, const double *b, const double *s, double *S, int slot);
 // lambda = (lambda + rho*b) - rho*s  (LORADSUpdateDualVar, lorads_alg_common.c:319-332)

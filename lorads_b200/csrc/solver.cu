@@ -35,7 +35,20 @@ void ItemListBufs::upload(const ItemList &L) {
         if (L.ptr[r + 1] == L.ptr[r]) dev.has_empty_rows = true;
 }
 
+void Solver::drop_graphs() {
+    for (auto &kv : iter_graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    iter_graphs.clear();
+}
+
+void Solver::push_scalars(double tau, double rho) {
+    push_host[0] = tau; push_host[1] = rho;
+    LB2_CUDA(cudaMemcpyAsync(S.p + SL_TAU, push_host, 2 * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+}
+
 Solver::~Solver() {
+    drop_graphs();
+    if (push_host) cudaFreeHost(push_host);
     if (S_host) cudaFreeHost(S_host);
     if (ctx.stream) cudaStreamDestroy(ctx.stream);
 }
@@ -65,6 +78,8 @@ void Solver::create(long long nRows, long long nC, const lb2_int *dims, const do
     LB2_CUDA(cudaMallocHost((void **)&S_host, sizeof(double) * (kNumSlots + 2 * nC)));
     std::memset(S_host, 0, sizeof(double) * (kNumSlots + 2 * nC));
     S_host[SL_ONE] = 1.0;
+    LB2_CUDA(cudaMallocHost((void **)&push_host, sizeof(double) * 4));
+    use_graphs = (getenv("LORADS_B200_NO_GRAPH") == nullptr);
     LB2_CUDA(cudaMemcpy(S.p, S_host, sizeof(double) * (kNumSlots + 2 * nC), cudaMemcpyHostToDevice));
 }
 
@@ -151,6 +166,7 @@ void Solver::determine_rank(double timesRank) {
 }
 
 void Solver::alloc_vars() {
+    drop_graphs();      // captured launches hold the old buffer addresses
     N = 0;
     for (long long c = 0; c < nCones; ++c) {
         ConeDev &K = cones[c];
@@ -387,7 +403,8 @@ static double sum_grad_sq(Solver &S_) {
 
 double Solver::cal_grad(double rho) {
     // ALMSetGrad / ALMCalGrad, lorads_alm.c:9-54
-    launch_alm_m_update(ctx, m, 0.0, nullptr, nullptr, s.p, lam.p, b.p, rho, M1.p);
+    push_scalars(0.0, rho);
+    launch_alm_m_update(ctx, m, S.p + SL_TAU, nullptr, nullptr, s.p, lam.p, b.p, S.p + SL_RHO, M1.p);
     grad_from_M1(*this);
     if (world > 1) allreduce(S.p + kNumSlots, 2 * nCones);
     read_slots();
@@ -567,10 +584,11 @@ long long line_search(double rho, const double *sums, double p1, double p2, doub
 // front() only writes the direction U, Dtemp, q1, q2 and scalar slots, so a speculative front that turns out
 // not to be needed (loop exit) is simply discarded.
 void Solver::enqueue_front(double rho, long long counter) {
+    (void)rho;     // read by the kernels from S[SL_RHO] (push_scalars)
     lbfgs_direction(counter);
     q12p12();
     if (world > 1) allreduce(S.p + SL_P1, 2);
-    launch_linesearch_dots(ctx, m, b.p, s.p, lam.p, rho, q1.p, q2.p, S.p, SL_LS);
+    launch_linesearch_dots(ctx, m, b.p, s.p, lam.p, S.p + SL_RHO, q1.p, q2.p, S.p, SL_LS);
 }
 
 long long Solver::finish_front(double rho, double *tau, double *p12) {
@@ -579,9 +597,10 @@ long long Solver::finish_front(double rho, double *tau, double *p12) {
 }
 
 void Solver::enqueue_back(double rho, double tau) {
+    (void)rho; (void)tau;     // both are read from the scalar slots S[SL_RHO], S[SL_TAU] (push_scalars)
     const int head = lb_head;
-    launch_alm_step(ctx, N, tau, G.p, U.p, R.p, lb_y[head].p, lb_s[head].p);
-    launch_alm_m_update(ctx, m, tau, q1.p, q2.p, s.p, lam.p, b.p, rho, M1.p);
+    launch_alm_step(ctx, N, S.p + SL_TAU, G.p, U.p, R.p, lb_y[head].p, lb_s[head].p);
+    launch_alm_m_update(ctx, m, S.p + SL_TAU, q1.p, q2.p, s.p, lam.p, b.p, S.p + SL_RHO, M1.p);
     grad_from_M1(*this);
     if (world > 1) allreduce(S.p + kNumSlots, 2 * nCones);
     // setlbfgsHisTwo, lorads_alm.c:657-678: y += G_new, beta = 1/<y,s>, advance the ring
@@ -602,7 +621,51 @@ void Solver::finish_back(double *lagNormSq, double *pinf1) {
     *pinf1 = dimac_pinf;
 }
 
+void Solver::iter_back_front(double rho, double tau, long long next_counter) {
+    push_scalars(tau, rho);
+    const size_t slot_bytes = sizeof(double) * (kNumSlots + 2 * nCones);
+    if (!use_graphs || world > 1) {
+        enqueue_back(rho, tau);
+        if (next_counter >= 0) enqueue_front(rho, next_counter);
+        read_slots();
+        return;
+    }
+    const int depth = next_counter < 0 ? 63 : (int)std::min<long long>(next_counter, lbfgs_len);
+    const int key = lb_head * 64 + depth;
+    auto it = iter_graphs.find(key);
+    if (it == iter_graphs.end()) {
+        // first visit of this (ring head, history depth): record the launches once ...
+        IterGraph g;
+        const long long l0 = ctx.launches;
+        const int head0 = lb_head;
+        cudaGraph_t graph = nullptr;
+        LB2_CUDA(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            enqueue_back(rho, tau);
+            if (next_counter >= 0) enqueue_front(rho, next_counter);
+            LB2_CUDA(cudaMemcpyAsync(S_host, S.p, slot_bytes, cudaMemcpyDeviceToHost, ctx.stream));
+        } catch (...) {
+            cudaStreamEndCapture(ctx.stream, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        LB2_CUDA(cudaStreamEndCapture(ctx.stream, &graph));
+        LB2_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+        LB2_CUDA(cudaGraphDestroy(graph));
+        g.launches = ctx.launches - l0;
+        ctx.launches = l0;
+        lb_head = head0;                 // nothing has executed yet: the replay below advances the ring
+        it = iter_graphs.emplace(key, g).first;
+    }
+    // ... and replay them as one graph launch
+    LB2_CUDA(cudaGraphLaunch(it->second.exec, ctx.stream));
+    ctx.launches += it->second.launches;
+    lb_head = (lb_head + 1) % lbfgs_len;
+    LB2_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
 int Solver::alm_inner_front(double rho, long long counter, double *tau, double *p12, long long *rootNum) {
+    push_scalars(*tau, rho);
     enqueue_front(rho, counter);
     read_slots();
     *rootNum = finish_front(rho, tau, p12);
@@ -610,6 +673,7 @@ int Solver::alm_inner_front(double rho, long long counter, double *tau, double *
 }
 
 void Solver::alm_inner_back(double rho, double tau, double *lagNormSq, double *pinf1) {
+    push_scalars(tau, rho);
     enqueue_back(rho, tau);
     read_slots();
     finish_back(lagNormSq, pinf1);
@@ -620,13 +684,11 @@ void Solver::alm_inner_back(double rho, double tau, double *lagNormSq, double *p
 long long Solver::run_inner_iters(double rho, long long iters, double *out) {
     double tau = 0.0, p12[2] = {0, 0}, lag = 0, pinf = 0;
     long long done = 0;
-    if (iters > 0) { enqueue_front(rho, 0); read_slots(); }
+    if (iters > 0) { push_scalars(0.0, rho); enqueue_front(rho, 0); read_slots(); }
     for (long long k = 0; k < iters; ++k) {
         const long long rn = finish_front(rho, &tau, p12);
         if (rn == 0) break;
-        enqueue_back(rho, tau);
-        if (k + 1 < iters) enqueue_front(rho, k + 1);
-        read_slots();
+        iter_back_front(rho, tau, (k + 1 < iters) ? k + 1 : -1);
         finish_back(&lag, &pinf);
         done++;
     }

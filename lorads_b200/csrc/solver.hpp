@@ -1,5 +1,6 @@
 // solver.hpp -- device-resident solver state and the operators of the hot path.
 #pragma once
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -14,6 +15,7 @@ namespace lb2 {
 enum Slot : int {
     SL_ONE = 0, SL_ZERO = 1,
     SL_T0 = 2, SL_T1 = 3,
+    SL_TAU = 4, SL_RHO = 5,   // step length / penalty of the current inner iteration (written by the host)
     SL_LS = 8,            // 8..12 line-search sums
     SL_P1 = 13, SL_P2 = 14,
     SL_PINF = 17, SL_DG = 19, SL_OBJ = 20, SL_DOBJ = 21,
@@ -94,6 +96,15 @@ struct Solver {
     double *S_host = nullptr;          // pinned mirror
     DBuf<double> red_partials;
     DBuf<unsigned int> red_counter;
+    double *push_host = nullptr;       // pinned staging for {tau, rho}
+    // replayable CUDA graphs of the steady-state inner iteration, keyed by (L-BFGS ring head, history depth)
+    struct IterGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
+    std::map<int, IterGraph> iter_graphs;
+    bool use_graphs = true;
+    void drop_graphs();
+    void push_scalars(double tau, double rho);
+    // back half of iteration k (+ front half of k+1 when next_counter >= 0), then the scalar read-back and sync
+    void iter_back_front(double rho, double tau, long long next_counter);
 
     // ranks
     std::vector<long long> rank, rank_max;
