@@ -123,7 +123,8 @@ int lb2_comm_init(lb2_solver *s, const void *id128, int rank, int world);
 /* ---- host-only pieces (no GPU needed; used by the CPU test-suite) -------------------------------- */
 /* The pre-solve of one cone on the host (what lb2_preprocess runs before uploading).
  * info[0]=|P| (or n(n+1)/2) info[1]=dense scratch? info[2]=dense-constraint cone? info[3]=active constraints
- * info[4]=nnzA info[5]=nnzC info[6]=non-zero constraint matrices info[7]=#rows split over A(UV^T) tiles.
+ * info[4]=nnzA info[5]=nnzC info[6]=non-zero constraint matrices info[7]=#rows split over A(UV^T) tiles
+ * info[8]=1 if the objective is stored as c*ee^T + sparse remainder (info has room for 10 values).
  * rows/cols (capacity >= |P|, may be NULL) receive the union pattern of a sparse-scratch cone. */
 int lb2_host_presolve(lb2_int n, lb2_int m, const lb2_int *coneMatBeg, const lb2_int *coneMatIdx,
                       const double *coneMatElem, lb2_int *info, lb2_int *rows, lb2_int *cols);

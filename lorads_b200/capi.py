@@ -137,7 +137,7 @@ class Lb2Error(RuntimeError):
 def host_presolve(cone, m: int):
     """Host-only pre-solve of one cone: returns (info dict, pattern rows, pattern cols)."""
     lib = load_library()
-    info = np.zeros(8, np.int64)
+    info = np.zeros(10, np.int64)
     beg = np.ascontiguousarray(cone.beg, dtype=np.int64)
     idx = np.ascontiguousarray(cone.idx, dtype=np.int64)
     elem = np.ascontiguousarray(cone.elem, dtype=np.float64)
@@ -148,7 +148,7 @@ def host_presolve(cone, m: int):
     cols = np.zeros_like(rows)
     if not info[1]:
         lib.lb2_host_presolve(cone.n, m, _i(beg), _i(idx), _d(elem), _i(info), _i(rows), _i(cols))
-    keys = ["psize", "dense_path", "dense_cone", "n_act", "nnzA", "nnzC", "n_nonzero_coeff", "n_split_rows"]
+    keys = ["psize", "dense_path", "dense_cone", "n_act", "nnzA", "nnzC", "n_nonzero_coeff", "n_split_rows", "rank_one_objective"]
     return dict(zip(keys, info.tolist())), rows, cols
 
 

@@ -135,6 +135,7 @@ int lb2_host_presolve(lb2_int n, lb2_int m, const lb2_int *beg, const lb2_int *i
     if (L.c_rank1 != 0.0 && L.dense_path) L = build_cone_layout(n, m, beg, idx, elem, false);
     info[4] = L.nnzA; info[5] = L.nnzC; info[6] = L.n_nonzero_coeff; info[7] = (lb2_int)L.listAC.split_row.size();
     info[0] = L.psize(); info[1] = L.dense_path;
+    info[8] = (L.c_rank1 != 0.0) ? 1 : 0; info[9] = 0;
     if (!L.dense_path && rows && cols)
         for (size_t p = 0; p < L.P_row.size(); ++p) { rows[p] = L.P_row[p]; cols[p] = L.P_col[p]; }
     LB2_CATCH

@@ -10,7 +10,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["maxcut_n120", "maxcut_n800", "mcomp_60x50", "theta_n60", "twoblock"]
+GOLDEN_CASES = ["maxcut_n120", "maxcut_n800", "mcomp_60x50", "theta_n60", "twoblock", "theta_n200"]
 
 
 def pytest_configure(config):

@@ -84,8 +84,15 @@ def test_host_presolve_matches_reference(golden):
     name, g, inst = golden
     for c, cone in enumerate(inst.cones):
         info, rows, cols = capi.host_presolve(cone, inst.m)
-        assert info["dense_path"] == int(g[f"dense{c}"])
-        if not info["dense_path"]:
+        if info["rank_one_objective"]:
+            # C = c ee^T (+ remainder) keeps the cone on the sparse scratch although the reference goes dense
+            assert int(g[f"dense{c}"]) == 1 and info["dense_path"] == 0 and info["nnzC"] == 0
+            assert info["psize"] == cone.n + (inst.m - 1)      # theta: diagonal + one entry per edge
+        else:
+            assert info["dense_path"] == int(g[f"dense{c}"])
+        if info["rank_one_objective"]:
+            pass
+        elif not info["dense_path"]:
             assert info["psize"] == int(g[f"psize{c}"])
             assert np.array_equal(rows, g[f"prow{c}"]) and np.array_equal(cols, g[f"pcol{c}"])
         else:
