@@ -120,6 +120,24 @@ def kernel_bytes(S) -> dict:
     }
 
 
+class c_stdout_to_stderr:
+    """The reference prints progress with printf; keep our stdout to the single JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def cpu_reference_rate(inst, iters: int):
     """ALM inner iterations/s of the compiled reference (oracle/_ref, 64-bit build) on this host; 1 thread."""
     from lorads_b200 import sdpa
@@ -130,10 +148,12 @@ def cpu_reference_rate(inst, iters: int):
     d = tempfile.mkdtemp(prefix="lorads_bench_")
     path = os.path.join(d, inst.name + ".dat-s")
     sdpa.write_dat_s(inst, path)
-    R = ref.RefSolver(path, 64)
-    rho = R.dinfo(6)
-    sec = R.time_alm_inner_iters(rho, iters)
-    return iters / sec, sec, R.rank()
+    with c_stdout_to_stderr():
+        R = ref.RefSolver(path, 64)
+        rho = R.dinfo(6)
+        sec = R.time_alm_inner_iters(rho, iters)
+        rank = R.rank()
+    return iters / sec, sec, rank
 
 
 def run_reference(args):
