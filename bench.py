@@ -32,7 +32,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(kind="maxcut", n=100_000, edges=500_000, seed=3)
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on (default, fits one GPU)
+    "cfg2": dict(kind="maxcut", n=100_000, edges=500_000, seed=3, label="BASELINE.json configs[1]"),
+    # BASELINE.json configs[4]: n = 1e6, factors (224 MB each) no longer fit the 126 MB L2 (extra evidence only)
+    "cfg5": dict(kind="maxcut", n=1_000_000, edges=5_000_000, seed=5, label="BASELINE.json configs[4]"),
+}
+WORKLOAD = WORKLOADS["cfg2"]
 FALLBACK_HBM_GBS = 6650.0
 
 
@@ -105,6 +111,23 @@ def measured_peak_gbs():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel_label: str):
+    """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        table = json.load(open(p))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+    key = {"auv_items_kernel<DUAL>": "auv_items_kernel<2,", "auv_items_kernel<SAME>": "auv_items_kernel<0,",
+           "spmm_sym_kernel": "spmm_sym_kernel", "axpby_dot2_kernel": "axpby_dot2_kernel", "wsum_kernel": "wsum_kernel"}
+    for prefix, ncu_prefix in key.items():
+        if kernel_label.startswith(prefix):
+            for name, v in table.items():
+                if name.startswith(ncu_prefix):
+                    return v
+    return None
+
+
 def kernel_bytes(S) -> dict:
     """Algorithmic (compulsory) bytes per launch of each hot kernel; formulas in DESIGN.md section 4."""
     n, ld, m = S.dim(0), S.info(17), S.m
@@ -173,7 +196,7 @@ def run_reference(args):
         "impl": "reference", "metric": "alm_inner_iterations_per_second", "value": rate, "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 / rate, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"MaxCut SDP n=m={WORKLOAD['n']} edges={WORKLOAD['edges']} seed={WORKLOAD['seed']} rank={r} (BASELINE.json configs[1]); one step = one ALM inner iteration, lorads_alm.c:1073-1146"},
+        "config": {"workload": f"MaxCut SDP n=m={WORKLOAD['n']} edges={WORKLOAD['edges']} seed={WORKLOAD['seed']} rank={r} ({WORKLOAD['label']}); one step = one ALM inner iteration, lorads_alm.c:1073-1146"},
         "cpu_baseline": {"value": rate, "unit": "iterations/s", "cores": 1, "kind": "reference",
                          "sample": f"{warm + steps} inner iterations of the untouched reference (oracle/_ref, -DMAC_INT64, OpenBLAS 1 thread) from the srand(925) start, {sec:.1f} s; host has {os.cpu_count()} cores, the reference is single-threaded"},
         "e2e": {"value": rate, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -278,11 +301,14 @@ def run_ours(args):
     share = {w: kt[w] * mult[w] for w in kt}
     dom = max(share, key=share.get)
     kernels = {kb[w][0]: {"ms": kt[w], "alg_bytes": kb[w][1], "gbs": kb[w][1] / (kt[w] * 1e-3) / 1e9,
+                          "ncu_dram_bytes": ncu_traffic(kb[w][0]) if WORKLOAD is WORKLOADS["cfg2"] else None,
                           "frac_of_peak": kb[w][1] / (kt[w] * 1e-3) / 1e9 / peak,
                           "share_of_step": share[w] / (1e3 * sec / done)} for w in kb}
     achieved = kb[dom][1] / (kt[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": kb[dom][0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": kb[dom][1],
+                "frac": achieved / peak, "traffic": ncu_traffic(kb[dom][0]) if WORKLOAD is WORKLOADS["cfg2"] else None,
+                "traffic_source": "profiles/r01_ncu_traffic.json (ncu --set full, cold-cache replay, per launch)",
+                "peak_source": peak_src, "alg_bytes_per_launch": kb[dom][1],
                 "launch_ms": kt[dom], "kernels": kernels}
 
     # ---------------- CPU baseline (bounded sample) ----------------
@@ -303,7 +329,7 @@ def run_ours(args):
         "metric": "alm_inner_iterations_per_second", "value": value, "unit": "iterations/s", "n_gpus": world,
         "steps": done, "warmup": max(3, args.warmup), "ms_per_step": 1e3 * sec / done, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"MaxCut SDP n=m={WORKLOAD['n']} edges={WORKLOAD['edges']} seed={WORKLOAD['seed']} rank={r} (BASELINE.json configs[1]); one step = one ALM inner iteration, lorads_alm.c:1073-1146",
+        "config": {"workload": f"MaxCut SDP n=m={WORKLOAD['n']} edges={WORKLOAD['edges']} seed={WORKLOAD['seed']} rank={r} ({WORKLOAD['label']}); one step = one ALM inner iteration, lorads_alm.c:1073-1146",
                    "l2": "no explicit flush: the step streams ~12 factor-sized vectors (19 MB each) plus 30 MB of index data (> 126 MB L2 in total)",
                    "parallelism": "single GPU" if world == 1 else f"factor columns sharded over {world} GPUs, NCCL all-reduce per A() evaluation and per dot",
                    "setup_seconds": t_setup},
@@ -323,7 +349,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-iters", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
