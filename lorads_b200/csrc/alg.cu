@@ -65,6 +65,8 @@ bool Solver::check_all_rank_max(double aug) const {
 }
 
 bool Solver::aug_rank(double aug) {
+    // Column sharding: ownership is by global column index (k % world), so old columns stay where they are and the
+    // host arrays below are full-size with only the owned columns filled / uploaded.
     // AUG_RANK, lorads_solver.c:806-906: append columns to U, V, R, Grad (M2temp keeps its old columns), the new
     // block of columns carries 1/sqrt(min(n, #new)) on its leading diagonal (lpRandomDiag :776-786); CG work
     // vectors and the L-BFGS history are re-allocated (zeroed).
@@ -76,7 +78,6 @@ bool Solver::aug_rank(double aug) {
         hR[c].resize(sz); hU[c].resize(sz); hV[c].resize(sz); hG[c].resize(sz); hM[c].resize(sz);
         get_factor('R', c, hR[c].data()); get_factor('U', c, hU[c].data()); get_factor('V', c, hV[c].data());
         get_factor('G', c, hG[c].data()); get_factor('M', c, hM[c].data());
-        if (world > 1) throw std::runtime_error("rank growth with column sharding is not implemented yet");
     }
     for (long long c = 0; c < nCones; ++c) {
         const long long nr = (long long)std::min<double>(std::ceil((double)rank[c] * aug), (double)rank_max[c]);

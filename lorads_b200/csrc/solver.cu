@@ -148,8 +148,10 @@ void Solver::preprocess() {
         bNrmInf = std::fabs(b_h[std::min<long long>(arg + 1, m - 1)]);
     }
     single_identity = (nCones == 1 && cones[0].identity_act);
-    b.alloc((size_t)m + 1); lam.alloc((size_t)m + 1); s.alloc((size_t)m + 1); q1.alloc((size_t)m + 1);
-    q2.alloc((size_t)m + 1); M1.alloc((size_t)m + 1); cvfull.alloc((size_t)m + 1);
+    b.alloc((size_t)m + 1); lam.alloc((size_t)m + 1); s.alloc((size_t)m + 1);
+    const size_t mpad = ((size_t)m + 2) & ~(size_t)1;     // even stride keeps q2 16-byte aligned
+    q12.alloc(2 * mpad); q1.p = q12.p; q2.p = q12.p + mpad;
+    M1.alloc((size_t)m + 1); cvfull.alloc((size_t)m + 1);
     LB2_CUDA(cudaMemcpy(b.p, b_h.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
     preprocessed = true;
 }
@@ -331,7 +333,7 @@ void Solver::cone_auv_dual(ConeDev &K, const double *Rm, const double *Dm, doubl
         launch_colsum(ctx, K.n, K.ld, Dm + K.off, K.csB.p, K.cs_scratch.p);
         launch_rank1_obj(ctx, K.ld, K.csA.p, K.csB.p, 2.0 * K.c_rank1, obj1, K.c_rank1, obj2);
     }
-    if (world > 1) { allreduce(out1, L.dev.n_rows); allreduce(out2, L.dev.n_rows); }
+    if (world > 1 && !(out1 == q1.p && out2 == q2.p)) { allreduce(out1, L.dev.n_rows); allreduce(out2, L.dev.n_rows); }
 }
 
 void Solver::cone_wsum(ConeDev &K, const double *w, bool w_compact, bool addC) {
@@ -454,8 +456,10 @@ void Solver::q12p12() {
     // ALMCalq12p12, lorads_alm.c:540-560: q1 = 2 A(sym(R D^T)), p1 = 2 <C, sym(R D^T)>, q2 = A(D D^T), p2 = <C, D D^T>
     LB2_CUDA(cudaMemsetAsync(S.p + SL_P1, 0, 2 * sizeof(double), ctx.stream));
     if (single_identity) {
-        // row m of the outputs is the objective row; its value is also accumulated into the P1 / P2 slots
+        // row m of the outputs is the objective row; its value is also accumulated into the P1 / P2 slots.
+        // Sharded: q1 and q2 are contiguous, one all-reduce completes both (P1 / P2 are reduced by the caller).
         cone_auv_dual(cones[0], R.p, U.p, q1.p, q2.p, S.p + SL_P1, S.p + SL_P2);
+        if (world > 1) allreduce(q12.p, (long long)(q2.p - q1.p) + m + 1);
         return;
     }
     LB2_CUDA(cudaMemsetAsync(q1.p, 0, sizeof(double) * m, ctx.stream));
@@ -624,7 +628,9 @@ void Solver::finish_back(double *lagNormSq, double *pinf1) {
 void Solver::iter_back_front(double rho, double tau, long long next_counter) {
     push_scalars(tau, rho);
     const size_t slot_bytes = sizeof(double) * (kNumSlots + 2 * nCones);
-    if (!use_graphs || world > 1) {
+    // NCCL all-reduces are capturable; kept opt-in (LORADS_B200_GRAPH_NCCL=1) until validated on every pool
+    static const bool graph_nccl = getenv("LORADS_B200_GRAPH_NCCL") != nullptr;
+    if (!use_graphs || (world > 1 && !graph_nccl)) {
         enqueue_back(rho, tau);
         if (next_counter >= 0) enqueue_front(rho, next_counter);
         read_slots();

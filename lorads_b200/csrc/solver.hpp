@@ -85,7 +85,8 @@ struct Solver {
     bool single_identity = false;      // one cone whose active set is all constraints: no scatter passes
 
     // m-vectors (capacity m + 1: slot m receives the objective value of fused evaluations)
-    DBuf<double> b, lam, s, q1, q2, M1, cvfull;
+    DBuf<double> b, lam, s, q12, M1, cvfull;   // q12 = [q1 (m+1) | q2 (m+1)] contiguous: one all-reduce covers both
+    struct VecView { double *p = nullptr; } q1, q2;
     // N-vectors
     long long N = 0;
     DBuf<double> R, U, V, G, M2, Bls, cg_r, cg_p, cg_Q, Dtemp;

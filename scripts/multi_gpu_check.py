@@ -33,5 +33,17 @@ if rank == 0:
     print("auv rel", float(np.linalg.norm(a - a1) / np.linalg.norm(a1)))
     ok = all(abs(o["tau"] - o1["tau"]) < 1e-8 for o, o1 in zip(outs, outs1))
     print("MULTI_GPU_CHECK", "OK" if ok else "FAIL")
+# whole solve, sharded vs single GPU (rank growth + ADMM + dual infeasibility under column sharding)
+from lorads_b200.capi import default_params
+inst2 = sdpa.maxcut(3000, 15000, 4)
+Sm = Solver(inst2, device=local, comm=comm)
+rm = Sm.solve(default_params())
+if rank == 0:
+    r1 = Solver(inst2, device=local).solve(default_params())
+    keys = ("pObj", "dObj", "pInfeasL1", "pdGap", "dInfeasL1", "almInnerIter", "admmIter", "cgIter", "finalRank0", "status")
+    print("sharded:", {k: rm[k] for k in keys})
+    print("single :", {k: r1[k] for k in keys})
+    ok2 = rm["status"] in (1, 2) and abs(rm["pObj"] - r1["pObj"]) <= 1e-5 * abs(r1["pObj"])
+    print("MULTI_GPU_SOLVE", "OK" if ok2 else "FAIL")
 dist.barrier()
 dist.destroy_process_group()
