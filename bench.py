@@ -293,6 +293,7 @@ def run_ours(args):
         kt[which] = S.bench_kernel(which, 200)
     barrier()
     if rank != 0:
+        S.close()
         if dist is not None:
             dist.destroy_process_group()
         return 0
@@ -335,7 +336,8 @@ def run_ours(args):
                    "setup_seconds": t_setup},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    S.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -102,8 +102,12 @@ int lb2_determine_rank(lb2_solver *s, double t) { if (!s) return LB2_ERR_ARG; LB
 int lb2_init_vars(lb2_solver *s, lb2_int L, double initRho) { if (!s) return LB2_ERR_ARG; LB2_TRY s->impl.init_vars(L, initRho); LB2_CATCH }
 void lb2_destroy(lb2_solver *s) {
     if (!s) return;
-    if (s->impl.nccl && g_nccl.destroy) g_nccl.destroy(s->impl.nccl);
     cudaSetDevice(s->impl.device);
+    // captured graphs may hold NCCL kernels: release them and drain the stream before the communicator goes
+    s->impl.drop_graphs();
+    if (s->impl.ctx.stream) cudaStreamSynchronize(s->impl.ctx.stream);
+    if (s->impl.nccl && g_nccl.destroy) g_nccl.destroy(s->impl.nccl);
+    s->impl.nccl = nullptr;
     delete s;
 }
 

@@ -698,6 +698,111 @@ void launch_axpby_dot(Ctx &c, long long n, double *out, Coef a, const double *x,
     LB2_LAUNCH_CHECK(c);
 }
 
+__global__ void __launch_bounds__(kBlock) lbfgs_pair_kernel(long long n, bool update_y, double *__restrict__ ya,
+                                                            const double *__restrict__ G,
+                                                            const double *__restrict__ sa, const double *__restrict__ yb,
+                                                            const double *__restrict__ sb, double *S, int d_slot,
+                                                            int beta_slot, int yy_slot, bool finalize, ReduceScratch rs) {
+    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long n2 = n >> 1;
+    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n2; q += (long long)gridDim.x * kBlock) {
+        double2 y = ld2(ya + 2 * q);
+        const double2 g = ld2(G + 2 * q), s = ld2(sa + 2 * q);
+        if (update_y) {
+            y.x += g.x; y.y += g.y;
+            st2(ya + 2 * q, y);
+        }
+        v[0] = fma(y.x, s.x, v[0]); v[0] = fma(y.y, s.y, v[0]);
+        v[1] = fma(y.x, y.x, v[1]); v[1] = fma(y.y, y.y, v[1]);
+        v[4] = fma(s.x, g.x, v[4]); v[4] = fma(s.y, g.y, v[4]);
+        v[6] = fma(y.x, g.x, v[6]); v[6] = fma(y.y, g.y, v[6]);
+        if (yb) {
+            const double2 y2 = ld2(yb + 2 * q), s2 = ld2(sb + 2 * q);
+            v[2] = fma(y.x, y2.x, v[2]); v[2] = fma(y.y, y2.y, v[2]);
+            v[3] = fma(y.x, s2.x, v[3]); v[3] = fma(y.y, s2.y, v[3]);
+            v[5] = fma(s2.x, g.x, v[5]); v[5] = fma(s2.y, g.y, v[5]);
+            v[7] = fma(y2.x, g.x, v[7]); v[7] = fma(y2.y, g.y, v[7]);
+        }
+    }
+    if (grid_reduce<8>(v, rs) && threadIdx.x == 0) {
+        for (int k = 0; k < 8; ++k) S[d_slot + k] = v[k];
+        if (finalize) { S[beta_slot] = 1.0 / v[0]; S[yy_slot] = v[1]; }
+    }
+}
+
+void launch_lbfgs_pair(Ctx &c, long long n, bool update_y, double *ya, const double *G, const double *sa, const double *yb,
+                       const double *sb, double *S, int d_slot, int beta_slot, int yy_slot, bool finalize) {
+    if (n & 1) throw std::runtime_error("factor vectors have even length by construction");
+    lbfgs_pair_kernel<<<grid_for(n, 8, c), kBlock, 0, c.stream>>>(n, update_y, ya, G, sa, yb, sb, S, d_slot, beta_slot,
+                                                                  yy_slot, finalize, c.rs);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void lbfgs_pair_finalize_kernel(double *S, int d_slot, int beta_slot, int yy_slot) {
+    S[beta_slot] = 1.0 / S[d_slot];
+    S[yy_slot] = S[d_slot + 1];
+}
+
+void launch_lbfgs_pair_finalize(Ctx &c, double *S, int d_slot, int beta_slot, int yy_slot) {
+    lbfgs_pair_finalize_kernel<<<1, 1, 0, c.stream>>>(S, d_slot, beta_slot, yy_slot);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) lbfgs_dir_kernel(long long n, int depth, double *__restrict__ D,
+                                                           const double *__restrict__ G, const double *__restrict__ ya,
+                                                           const double *__restrict__ sa, const double *__restrict__ yb,
+                                                           const double *__restrict__ sb, const double *__restrict__ S,
+                                                           int d, int beta_a, int beta_b, int yy_b_slot,
+                                                           const double *__restrict__ gg_slots, int n_gg) {
+    // coefficients of the two-loop recursion in closed form (every thread evaluates the same ~30 flops)
+    double ca = 0.0, cb = 0.0, wa = 0.0, wb = 0.0;      // D = -(G - ca*ya - cb*yb + wb*sb + wa*sa)
+    bool use_grad = (depth == 0);
+    if (depth >= 1) {
+        const double ba = S[beta_a];
+        const double sag = S[d + 4], yag = S[d + 6], yaya = S[d + 1];
+        double gg = 0.0;
+        for (int k = 0; k < n_gg; ++k) gg += gg_slots[2 * k];
+        ca = ba * sag;                                              // alpha_a
+        double dg;
+        if (depth >= 2) {
+            const double bb = S[beta_b];
+            const double sbg = S[d + 5], ybg = S[d + 7], yayb = S[d + 2], yasb = S[d + 3], ybyb = S[yy_b_slot];
+            cb = bb * (sbg - ca * yasb);                            // alpha_b = beta_b * sb.(g - ca*ya)
+            wb = cb - bb * (ybg - ca * yayb - cb * ybyb);           // alpha_b - beta_b * yb.q2
+            wa = ca - ba * (yag - ca * yaya - cb * yayb + wb * yasb);   // alpha_a - beta_a * ya.q3
+            dg = -(gg - ca * yag - cb * ybg + wb * sbg + wa * sag);
+        } else {
+            wa = ca - ba * (yag - ca * yaya);
+            dg = -(gg - ca * yag + wa * sag);
+        }
+        use_grad = (dg >= 0.0);                                     // LBFGSDirectionUseGrad: fall back to -G
+    }
+    const long long n2 = n >> 1;
+    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n2; q += (long long)gridDim.x * kBlock) {
+        const double2 g = ld2(G + 2 * q);
+        double2 o = g;
+        if (!use_grad) {
+            const double2 y1 = ld2(ya + 2 * q), s1 = ld2(sa + 2 * q);
+            o.x = fma(-ca, y1.x, o.x); o.y = fma(-ca, y1.y, o.y);
+            if (depth >= 2) {
+                const double2 y2 = ld2(yb + 2 * q), s2 = ld2(sb + 2 * q);
+                o.x = fma(-cb, y2.x, o.x); o.y = fma(-cb, y2.y, o.y);
+                o.x = fma(wb, s2.x, o.x); o.y = fma(wb, s2.y, o.y);
+            }
+            o.x = fma(wa, s1.x, o.x); o.y = fma(wa, s1.y, o.y);
+        }
+        st2(D + 2 * q, make_double2(-o.x, -o.y));
+    }
+}
+
+void launch_lbfgs_dir(Ctx &c, long long n, int depth, double *D, const double *G, const double *ya, const double *sa,
+                      const double *yb, const double *sb, const double *S, int d_slot, int beta_a, int beta_b,
+                      int yy_b_slot, const double *gg_slots, int n_gg) {
+    lbfgs_dir_kernel<<<grid_for(n, 8, c), kBlock, 0, c.stream>>>(n, depth, D, G, ya, sa, yb, sb, S, d_slot, beta_a, beta_b,
+                                                                 yy_b_slot, gg_slots, n_gg);
+    LB2_LAUNCH_CHECK(c);
+}
+
 __global__ void __launch_bounds__(kBlock) dot_kernel(long long n, const double *__restrict__ x,
                                                      const double *__restrict__ y, double *S, int slot, int mode,
                                                      ReduceScratch rs) {

@@ -117,6 +117,23 @@ void launch_alm_step(Ctx &c, long long n, const double *tau_p, const double *G, 
 void launch_cg_update(Ctx &c, long long n, double *x, double *r, const double *p, const double *Q, double *S,
                       int slot_num, int slot_den, int slot_rr);
 
+// ---- vector-free L-BFGS (history length 2): all inner products of the two-loop recursion come from a small Gram
+// table, so the recursion needs two passes over the factor vectors instead of five, and one reduction.
+// Pair completion (setlbfgsHisTwo, lorads_alm.c:657-678, fused with the dots the next direction needs):
+//   ya += G ; S[d+0]=ya.sa (S[beta_slot]=1/that) S[d+1]=ya.ya S[d+2]=ya.yb S[d+3]=ya.sb
+//   S[d+4]=sa.G S[d+5]=sb.G S[d+6]=ya.G S[d+7]=yb.G          (yb, sb may be null: their dots are 0)
+// update_y = false leaves ya untouched and only refreshes the dots (G changed without a new pair).
+// finalize: also store S[beta_slot] = 1/(ya.sa) and S[yy_slot] = ya.ya (single GPU; sharded runs all-reduce the
+// eight dots first and call launch_lbfgs_pair_finalize).
+void launch_lbfgs_pair(Ctx &c, long long n, bool update_y, double *ya, const double *G, const double *sa, const double *yb,
+                       const double *sb, double *S, int d_slot, int beta_slot, int yy_slot, bool finalize);
+void launch_lbfgs_pair_finalize(Ctx &c, double *S, int d_slot, int beta_slot, int yy_slot);
+// Direction (LBFGSDirection + LBFGSDirectionUseGrad, lorads_alm.c:230-391,469-489) from the Gram table:
+// depth 0: D = -G; depth 1: newest pair a only; depth 2: pairs a (newest) and b.  gg_slot holds G.G.
+void launch_lbfgs_dir(Ctx &c, long long n, int depth, double *D, const double *G, const double *ya, const double *sa,
+                      const double *yb, const double *sb, const double *S, int d_slot, int beta_a, int beta_b,
+                      int yy_b_slot, const double *gg_slots, int n_gg);
+
 // line-search sums over m (ALMLineSearch, lorads_alm.c:161-172): q0 = b - s + lambda/rho
 // S[slot+0]=|q2|^2  S[slot+1]=q1.q2  S[slot+2]=q0.q2  S[slot+3]=|q1|^2  S[slot+4]=q0.q1
 void launch_linesearch_dots(Ctx &c, long long m, const double *b, const double *s, const double *lam, const double *rho_p,

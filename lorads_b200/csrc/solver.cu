@@ -80,6 +80,7 @@ void Solver::create(long long nRows, long long nC, const lb2_int *dims, const do
     S_host[SL_ONE] = 1.0;
     LB2_CUDA(cudaMallocHost((void **)&push_host, sizeof(double) * 4));
     use_graphs = (getenv("LORADS_B200_NO_GRAPH") == nullptr);
+    vf_lbfgs = (getenv("LORADS_B200_VF_LBFGS") != nullptr);
     LB2_CUDA(cudaMemcpy(S.p, S_host, sizeof(double) * (kNumSlots + 2 * nC), cudaMemcpyHostToDevice));
 }
 
@@ -409,6 +410,7 @@ double Solver::cal_grad(double rho) {
     launch_alm_m_update(ctx, m, S.p + SL_TAU, nullptr, nullptr, s.p, lam.p, b.p, S.p + SL_RHO, M1.p);
     grad_from_M1(*this);
     if (world > 1) allreduce(S.p + kNumSlots, 2 * nCones);
+    vf_valid = false;          // the gradient changed without a new (s, y) pair
     read_slots();
     return sum_grad_sq(*this);
 }
@@ -418,6 +420,20 @@ void Solver::lbfgs_direction(long long counter) {
     // LBFGSDirectionUseGrad, lorads_alm.c:469-489.  The search direction lives in U, as in the reference.
     const int L = lbfgs_len;
     double *D = U.p, *q = Dtemp.p;
+    if (vf_lbfgs && L == 2) {
+        // vector-free form: two passes over the factor vectors, every inner product from the Gram table
+        const int depth = (int)std::min<long long>(counter, 2);
+        const int a = (lb_head + 1) % 2, bnode = lb_head;       // a = newest pair, bnode = the older one
+        if (depth >= 1 && !vf_valid) {
+            launch_lbfgs_pair(ctx, N, false, lb_y[a].p, G.p, lb_s[a].p, lb_y[bnode].p, lb_s[bnode].p, S.p, SL_VF_D,
+                              SL_BETA0 + a, SL_VF_YY + a, world == 1);
+            if (world > 1) { allreduce(S.p + SL_VF_D, 8); launch_lbfgs_pair_finalize(ctx, S.p, SL_VF_D, SL_BETA0 + a, SL_VF_YY + a); }
+            vf_valid = true;
+        }
+        launch_lbfgs_dir(ctx, N, depth, D, G.p, lb_y[a].p, lb_s[a].p, lb_y[bnode].p, lb_s[bnode].p, S.p, SL_VF_D,
+                         SL_BETA0 + a, SL_BETA0 + bnode, SL_VF_YY + bnode, S.p + kNumSlots, (int)nCones);
+        return;
+    }
     if (counter == 0) {
         // D = -G; the <D,G> >= 0 test of LBFGSDirectionUseGrad can only fire for G = 0, where it is a no-op
         launch_axpby_dot(ctx, N, D, coef_const(-1.0), G.p, coef_const(0.0), nullptr, nullptr, S.p, SL_DG, false);
@@ -608,11 +624,22 @@ void Solver::enqueue_back(double rho, double tau) {
     grad_from_M1(*this);
     if (world > 1) allreduce(S.p + kNumSlots, 2 * nCones);
     // setlbfgsHisTwo, lorads_alm.c:657-678: y += G_new, beta = 1/<y,s>, advance the ring
-    launch_axpby_dot(ctx, N, lb_y[head].p, coef_const(1.0), lb_y[head].p, coef_const(1.0), G.p, lb_s[head].p, S.p,
-                     SL_BETA0 + head, world == 1);
-    if (world > 1) {
-        allreduce(S.p + SL_BETA0 + head, 1);
-        launch_recip(ctx, S.p, SL_BETA0 + head);
+    if (vf_lbfgs && lbfgs_len == 2) {
+        const int other = (head + 1) % 2;
+        launch_lbfgs_pair(ctx, N, true, lb_y[head].p, G.p, lb_s[head].p, lb_y[other].p, lb_s[other].p, S.p, SL_VF_D,
+                          SL_BETA0 + head, SL_VF_YY + head, world == 1);
+        if (world > 1) {
+            allreduce(S.p + SL_VF_D, 8);
+            launch_lbfgs_pair_finalize(ctx, S.p, SL_VF_D, SL_BETA0 + head, SL_VF_YY + head);
+        }
+        vf_valid = true;
+    } else {
+        launch_axpby_dot(ctx, N, lb_y[head].p, coef_const(1.0), lb_y[head].p, coef_const(1.0), G.p, lb_s[head].p, S.p,
+                         SL_BETA0 + head, world == 1);
+        if (world > 1) {
+            allreduce(S.p + SL_BETA0 + head, 1);
+            launch_recip(ctx, S.p, SL_BETA0 + head);
+        }
     }
     lb_head = (head + 1) % lbfgs_len;
     primal_infeasibility(R.p);
@@ -628,8 +655,8 @@ void Solver::finish_back(double *lagNormSq, double *pinf1) {
 void Solver::iter_back_front(double rho, double tau, long long next_counter) {
     push_scalars(tau, rho);
     const size_t slot_bytes = sizeof(double) * (kNumSlots + 2 * nCones);
-    // NCCL all-reduces are capturable; kept opt-in (LORADS_B200_GRAPH_NCCL=1) until validated on every pool
-    static const bool graph_nccl = getenv("LORADS_B200_GRAPH_NCCL") != nullptr;
+    // NCCL all-reduces are captured into the graph too (validated at 2 ranks); LORADS_B200_NO_GRAPH_NCCL=1 opts out
+    static const bool graph_nccl = getenv("LORADS_B200_NO_GRAPH_NCCL") == nullptr;
     if (!use_graphs || (world > 1 && !graph_nccl)) {
         enqueue_back(rho, tau);
         if (next_counter >= 0) enqueue_front(rho, next_counter);

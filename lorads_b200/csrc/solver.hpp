@@ -23,7 +23,9 @@ enum Slot : int {
     SL_CG_RR_A = 26, SL_CG_RR_B = 27, SL_CG_BN = 28,
     SL_NEGALPHA0 = 32,    // 32..47  -alpha of the L-BFGS two-loop, per history node
     SL_BETA0 = 48,        // 48..63  beta = 1/<y,s> per history node
-    kNumSlots = 64        // followed by 2 slots per cone: sum G.G and sum G.Z2 of that cone
+    SL_VF_D = 64,         // 64..71 Gram dots of the vector-free L-BFGS (see launch_lbfgs_pair)
+    SL_VF_YY = 72,        // 72..73 y.y of the two history nodes
+    kNumSlots = 80        // followed by 2 slots per cone: sum G.G and sum G.Z2 of that cone
 };
 constexpr int kMaxLbfgs = 16;
 
@@ -92,6 +94,8 @@ struct Solver {
     DBuf<double> R, U, V, G, M2, Bls, cg_r, cg_p, cg_Q, Dtemp;
     std::vector<DBuf<double>> lb_s, lb_y;
     int lbfgs_len = 2, lb_head = 0;
+    bool vf_lbfgs = false;     // vector-free (Gram) L-BFGS for history length 2
+    bool vf_valid = false;     // the G-dots in the Gram table belong to the current gradient
     // scalars
     DBuf<double> S;
     double *S_host = nullptr;          // pinned mirror

@@ -9,13 +9,20 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 lib = load_library()
-uid = torch.zeros(128, dtype=torch.uint8)
-if rank == 0:
-    buf = (C.c_char * 128)()
-    assert lib.lb2_comm_unique_id(buf) == 0
-    uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-uid = uid.cuda(); dist.broadcast(uid, 0)
-comm = (C.create_string_buffer(bytes(uid.cpu().numpy().tobytes()), 128), rank, world)
+
+
+def new_comm():
+    """A fresh NCCL id per communicator: rank 0 creates it, everybody receives it."""
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = (C.c_char * 128)()
+        assert lib.lb2_comm_unique_id(buf) == 0
+        uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    uid = uid.cuda(); dist.broadcast(uid, 0)
+    return (C.create_string_buffer(bytes(uid.cpu().numpy().tobytes()), 128), rank, world)
+
+
+comm = new_comm()
 inst = sdpa.maxcut(20000, 100000, 2)
 S = Solver(inst, device=local, comm=comm)
 rho = S.dinfo(6)
@@ -36,7 +43,8 @@ if rank == 0:
 # whole solve, sharded vs single GPU (rank growth + ADMM + dual infeasibility under column sharding)
 from lorads_b200.capi import default_params
 inst2 = sdpa.maxcut(3000, 15000, 4)
-Sm = Solver(inst2, device=local, comm=comm)
+S.close()
+Sm = Solver(inst2, device=local, comm=new_comm())
 rm = Sm.solve(default_params())
 if rank == 0:
     r1 = Solver(inst2, device=local).solve(default_params())
@@ -45,5 +53,6 @@ if rank == 0:
     print("single :", {k: r1[k] for k in keys})
     ok2 = rm["status"] in (1, 2) and abs(rm["pObj"] - r1["pObj"]) <= 1e-5 * abs(r1["pObj"])
     print("MULTI_GPU_SOLVE", "OK" if ok2 else "FAIL")
+Sm.close()
 dist.barrier()
 dist.destroy_process_group()
