@@ -120,6 +120,20 @@ void lb2_destroy(lb2_solver *s);
 int lb2_comm_unique_id(void *id128);
 int lb2_comm_init(lb2_solver *s, const void *id128, int rank, int world);
 
+/* ---- SDPA .dat-s ingest (host only) -------------------------------------------------------------------- */
+/* Fast replacement of LReadSDPA (lorads_file_io.c:21-418) with the same output convention: per PSD block a CSC
+ * matrix with m+1 columns over the packed lower-triangular index, column 0 = objective (negated), entries
+ * |v| < 1e-12 dropped, a trailing negative dimension = LP block (reported through info 4; the device layer
+ * does not take LP blocks yet).  The arrays can be passed straight to lb2_set_cone_data. */
+typedef struct lb2_sdpa lb2_sdpa;
+int lb2_read_sdpa(const char *path, lb2_sdpa **out);
+/* what: 0 nConstrs, 1 number of PSD blocks, 2 dimension of block k, 3 non-zeros of block k, 4 nLpCols, 5 nElems */
+lb2_int lb2_sdpa_info(const lb2_sdpa *s, int what, lb2_int k);
+/* copies block k (beg: m+2, idx/elem: nnz) and/or the right-hand side (m); pass k = -1 for the rhs only */
+int lb2_sdpa_get(const lb2_sdpa *s, lb2_int k, lb2_int *coneMatBeg, lb2_int *coneMatIdx, double *coneMatElem, double *rowRHS);
+void lb2_sdpa_free(lb2_sdpa *s);
+const char *lb2_sdpa_last_error(void);
+
 /* ---- host-only pieces (no GPU needed; used by the CPU test-suite) -------------------------------- */
 /* The pre-solve of one cone on the host (what lb2_preprocess runs before uploading).
  * info[0]=|P| (or n(n+1)/2) info[1]=dense scratch? info[2]=dense-constraint cone? info[3]=active constraints

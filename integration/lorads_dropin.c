@@ -1,13 +1,13 @@
 /* integration/lorads_dropin.c -- the reference-side binding of the B200 kernel layer.
  *
  * LoRADS has no plugin / FFI layer: the seam is link time.  This translation unit is
- * what a LoRADS maintainer compiles INSTEAD OF src_semi/data/*.c, src_semi/linalg/*.c and
- * src_semi/lorads_alg/*.c: it defines, with the reference's own signatures (it includes the reference's own
+ * what a LoRADS maintainer compiles INSTEAD OF every .c file of src_semi/data, src_semi/linalg and
+ * src_semi/lorads_alg: it defines, with the reference's own signatures (it includes the reference's own
  * headers, which stay where they are), every function the UNMODIFIED driver src_semi/main.c calls from those
  * three subsystems, and forwards each one to the C ABI of liblorads_b200.so (include/lorads_b200.h).
  *
  *   gcc -DINT32 -I$REF -I$REF/data -I$REF/lorads_alg -I$REF/linalg -I$REF/io -Iinclude \
- *       $REF/main.c $REF/lorads_utils.c $REF/io/*.c integration/lorads_dropin.c \
+ *       $REF/main.c $REF/lorads_utils.c $REF/io/{lorads_cs,lorads_file_io,lorads_user_data}.c integration/lorads_dropin.c \
  *       -Llorads_b200 -llorads_b200 -lm -o lorads_gpu          (oracle/Makefile target `dropin`)
  *
  * Ownership follows the reference: the reader's arrays are borrowed (main.c frees them through
@@ -33,8 +33,6 @@
 int MAX_ALM_SUB_ITER;               /* the reference's global (lorads.h:66); the library keeps its own copy */
 
 static lb2_solver *g_h = NULL;      /* the reference is single-instance and not re-entrant */
-static lorads_int *g_blk = NULL;
-static double g_t0 = 0.0;
 
 static void die(const char *what)
 {
@@ -117,7 +115,7 @@ extern void LORADSInitSolver(lorads_solver *S, lorads_int nRows, lorads_int nCon
     LORADS_INIT(S->rowRHS, double, nRows);
     LORADS_INIT(S->dimacError, double, 5);
     LORADS_INIT(S->var->rankElem, lorads_int, nCones);
-    g_blk = blkDims;
+    (void)blkDims;
 }
 
 extern void LORADSSetDualObjective(lorads_solver *S, double *dObj) { LORADS_MEMCPY(S->rowRHS, dObj, double, S->nRows); }
@@ -203,7 +201,6 @@ extern void initial_solver_state(lorads_params *params, lorads_solver *S, lorads
     c->l_1_norm_b = S->bRHSNrm1; c->l_2_norm_b = S->bRHSNrm2; c->l_inf_norm_b = S->bRHSNrmInf;
     memset(alm, 0, sizeof(*alm)); memset(admm, 0, sizeof(*admm));
     pull_state(S, alm, admm);
-    g_t0 = LUtilGetTimeStamp();
 }
 
 extern void LORADS_ALMtoADMM(lorads_solver *S, lorads_params *params, lorads_alm_state *alm, lorads_admm_state *admm)

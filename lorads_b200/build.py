@@ -11,8 +11,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblorads_b200.so")
-SOURCES = ["kernels.cu", "solver.cu", "alg.cu", "capi.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "layout.hpp", "solver.hpp", os.path.join("..", "..", "include", "lorads_b200.h")]
+CLI = os.path.join(HERE, "lorads_b200_cli")
+SOURCES = ["kernels.cu", "solver.cu", "alg.cu", "capi.cu", "sdpa_reader.cpp"]
+HEADERS = ["common.cuh", "kernels.cuh", "layout.hpp", "solver.hpp", "main_cli.cpp", os.path.join("..", "..", "include", "lorads_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC,-O2", "--shared", "-Wno-deprecated-gpu-targets",
@@ -20,7 +21,7 @@ NVCC_FLAGS = [
 
 
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(CLI):
         return True
     t = os.path.getmtime(LIB)
     for f in SOURCES + HEADERS + [os.path.join("..", "build.py")]:
@@ -40,6 +41,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building liblorads_b200.so")
     if verbose:
         sys.stderr.write(proc.stderr)
+    # the stand-alone command-line driver (host only, links the library)
+    cli = subprocess.run(["g++", "-O2", "-std=c++17", os.path.join(CSRC, "main_cli.cpp"), "-o", CLI, "-L" + HERE, "-llorads_b200",
+                          "-Wl,--disable-new-dtags,-rpath,$ORIGIN"], capture_output=True, text=True)
+    if cli.returncode != 0:
+        sys.stderr.write(cli.stdout + cli.stderr)
+        raise RuntimeError("g++ failed building lorads_b200_cli")
     return LIB
 
 

@@ -53,6 +53,7 @@ EXPORTS = [
     "lb2_alm_cal_grad", "lb2_cg_matvec", "lb2_update_sdp_var_one", "lb2_alm_prepare", "lb2_alm_inner_iter",
     "lb2_time_alm_inner_iters", "lb2_alm_run_host", "lb2_bench_kernel", "lb2_alm_optimize", "lb2_alm_to_admm", "lb2_admm_optimize", "lb2_dual_infeasibility",
     "lb2_solve", "lb2_get_solution", "lb2_reopt", "lb2_average_uv", "lb2_copy_r_to_v", "lb2_get_state", "lb2_set_state", "lb2_host_presolve", "lb2_host_line_search", "lb2_host_rank_rule",
+    "lb2_read_sdpa", "lb2_sdpa_info", "lb2_sdpa_get", "lb2_sdpa_free", "lb2_sdpa_last_error",
 ]
 
 _lib = None
@@ -110,6 +111,13 @@ def load_library():
     lib.lb2_host_line_search.argtypes = [C.c_double, _dp, C.c_double, C.c_double, _dp]
     lib.lb2_host_rank_rule.restype = C.c_int64
     lib.lb2_host_rank_rule.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_double, _ip]
+    lib.lb2_read_sdpa.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.lb2_sdpa_info.restype = C.c_int64
+    lib.lb2_sdpa_info.argtypes = [C.c_void_p, C.c_int, C.c_int64]
+    lib.lb2_sdpa_get.argtypes = [C.c_void_p, C.c_int64, _ip, _ip, _dp, _dp]
+    lib.lb2_sdpa_free.argtypes = [C.c_void_p]
+    lib.lb2_sdpa_free.restype = None
+    lib.lb2_sdpa_last_error.restype = C.c_char_p
     _lib = lib
     return lib
 
@@ -150,6 +158,31 @@ def host_presolve(cone, m: int):
         lib.lb2_host_presolve(cone.n, m, _i(beg), _i(idx), _d(elem), _i(info), _i(rows), _i(cols))
     keys = ["psize", "dense_path", "dense_cone", "n_act", "nnzA", "nnzC", "n_nonzero_coeff", "n_split_rows", "rank_one_objective"]
     return dict(zip(keys, info.tolist())), rows, cols
+
+
+def read_sdpa(path: str) -> Instance:
+    """Fast .dat-s ingest through the library (same arrays as the reference's LReadSDPA)."""
+    from .sdpa import Cone
+    lib = load_library()
+    h = C.c_void_p()
+    if lib.lb2_read_sdpa(path.encode(), C.byref(h)) != 0:
+        raise Lb2Error(lib.lb2_sdpa_last_error().decode())
+    try:
+        if lib.lb2_sdpa_info(h, 4, 0) > 0:
+            raise ValueError("LP / diagonal blocks are out of scope for the device data layer")
+        m = int(lib.lb2_sdpa_info(h, 0, 0))
+        nblk = int(lib.lb2_sdpa_info(h, 1, 0))
+        b = np.zeros(m)
+        lib.lb2_sdpa_get(h, -1, None, None, None, _d(b))
+        cones = []
+        for k in range(nblk):
+            n, nnz = int(lib.lb2_sdpa_info(h, 2, k)), int(lib.lb2_sdpa_info(h, 3, k))
+            beg, idx, elem = np.zeros(m + 2, np.int64), np.zeros(nnz, np.int64), np.zeros(nnz)
+            lib.lb2_sdpa_get(h, k, _i(beg), _i(idx), _d(elem), None)
+            cones.append(Cone(n=n, beg=beg, idx=idx, elem=elem))
+        return Instance(m=m, b=b, cones=cones, name=path)
+    finally:
+        lib.lb2_sdpa_free(h)
 
 
 def host_line_search(rho: float, sums, p1: float, p2: float, tau0: float = 0.0):

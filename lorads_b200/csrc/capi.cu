@@ -389,8 +389,7 @@ int lb2_bench_kernel(lb2_solver *s, int which, lb2_int reps, double *ms) {
 
 int lb2_alm_optimize(lb2_solver *s, lb2_params *p, double timeSolveStart) {
     if (!s || !p) return LB2_ERR_ARG;
-    int rc = 0;
-    LB2_TRY rc = s->impl.alm_optimize(p, 0.0, timeSolveStart, false, false, 0.0); (void)rc; LB2_CATCH
+    LB2_TRY s->impl.alm_optimize(p, 0.0, timeSolveStart, false, false, 0.0); LB2_CATCH
 }
 int lb2_alm_to_admm(lb2_solver *s, lb2_params *p) { if (!s || !p) return LB2_ERR_ARG; LB2_TRY s->impl.alm_to_admm(p); LB2_CATCH }
 int lb2_admm_optimize(lb2_solver *s, lb2_params *p, lb2_int iterCelling, double timeSolveStart) {

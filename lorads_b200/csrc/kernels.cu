@@ -1045,17 +1045,6 @@ void launch_recip(Ctx &c, double *S, int slot) {
     LB2_LAUNCH_CHECK(c);
 }
 
-__global__ void set_scalar_kernel(double *S, int slot, double v) { S[slot] = v; }
-
-void launch_set_scalar(Ctx &c, double *S, int slot, double v) {
-    set_scalar_kernel<<<1, 1, 0, c.stream>>>(S, slot, v);
-    LB2_LAUNCH_CHECK(c);
-}
-
-__global__ void __launch_bounds__(kBlock) fill_kernel(double *__restrict__ x, long long n, double v) {
-    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n; q += (long long)gridDim.x * kBlock) x[q] = v;
-}
-
 __global__ void __launch_bounds__(kBlock) scale_kernel(double *__restrict__ x, long long n, double f) {
     for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n; q += (long long)gridDim.x * kBlock) x[q] *= f;
 }
@@ -1063,11 +1052,6 @@ __global__ void __launch_bounds__(kBlock) scale_kernel(double *__restrict__ x, l
 void launch_scale(Ctx &c, double *x, long long n, double f) {
     if (n <= 0) return;
     scale_kernel<<<grid_for(n, 4, c), kBlock, 0, c.stream>>>(x, n, f);
-    LB2_LAUNCH_CHECK(c);
-}
-
-void launch_fill(Ctx &c, double *x, long long n, double v) {
-    fill_kernel<<<grid_for(n, 4, c), kBlock, 0, c.stream>>>(x, n, v);
     LB2_LAUNCH_CHECK(c);
 }
 

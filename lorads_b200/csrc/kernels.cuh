@@ -149,9 +149,7 @@ void launch_dual_update(Ctx &c, long long m, double rho, const double *b, const 
 // constraint vector expanded to length m (may be null)
 void launch_admm_m1(Ctx &c, long long m, const double *b, const double *s, const double *cv, const double *lam,
                     double rho, double *M1);
-void launch_set_scalar(Ctx &c, double *S, int slot, double v);
 void launch_recip(Ctx &c, double *S, int slot);   // S[slot] = 1/S[slot]
-void launch_fill(Ctx &c, double *x, long long n, double v);
 void launch_scale(Ctx &c, double *x, long long n, double f);   // x *= f
 
 }  // namespace lb2

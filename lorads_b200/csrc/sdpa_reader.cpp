@@ -1,0 +1,194 @@
+// sdpa_reader.cpp -- fast SDPA sparse-format (.dat-s) ingest with the output convention of the reference reader
+// LReadSDPA (src_semi/io/lorads_file_io.c:21-418): per PSD block a CSC matrix with m+1 columns over the packed
+// lower-triangular index PACK_IDX(n, max(i,j), min(i,j)) (lorads_utils.h:45), column 0 = objective block NEGATED
+// (:279-281), entries with |v| < 1e-12 dropped (:250-256), a trailing negative block dimension = LP block (:149-151),
+// duplicates not summed, entries of a column kept in file order (dcs_compress is a stable counting sort).
+// The reference parses with fgets + sscanf per line and CSparse triplet growth; here the file is read once into
+// memory, numbers are parsed in place and the CSC arrays are filled by a two-pass counting sort.
+#include <cerrno>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/lorads_b200.h"
+
+struct lb2_sdpa {
+    lb2_int m = 0, nLpCols = 0;
+    std::vector<lb2_int> dims;
+    std::vector<double> rhs;
+    struct Block { std::vector<lb2_int> beg, idx; std::vector<double> elem; };
+    std::vector<Block> blocks;
+    Block lp;      // LP block as CSC over columns 0..m (row = LP column index), kept for completeness
+    lb2_int nElems = 0;
+};
+
+namespace {
+
+thread_local std::string g_reader_err;
+
+inline void skip_ws(const char *&p, const char *end) {
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+}
+inline void skip_line(const char *&p, const char *end) {
+    while (p < end && *p != '\n') ++p;
+    if (p < end) ++p;
+}
+inline bool parse_int(const char *&p, const char *end, long long &v) {
+    skip_ws(p, end);
+    if (p >= end) return false;
+    char *q = nullptr;
+    errno = 0;
+    v = std::strtoll(p, &q, 10);
+    if (q == p) return false;
+    p = q;
+    return true;
+}
+inline bool parse_double(const char *&p, const char *end, double &v) {
+    skip_ws(p, end);
+    if (p >= end) return false;
+    char *q = nullptr;
+    v = std::strtod(p, &q);
+    if (q == p) return false;
+    p = q;
+    return true;
+}
+inline bool is_punct(char c) { return c == '{' || c == '}' || c == '(' || c == ')' || c == ',' || c == '\''; }
+
+}  // namespace
+
+extern "C" {
+
+const char *lb2_sdpa_last_error(void) { return g_reader_err.c_str(); }
+
+int lb2_read_sdpa(const char *path, lb2_sdpa **out) {
+    if (!path || !out) return LB2_ERR_ARG;
+    *out = nullptr;
+    FILE *f = std::fopen(path, "rb");
+    if (!f) { g_reader_err = std::string("cannot open ") + path; return LB2_ERR_ARG; }
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    std::vector<char> buf((size_t)sz + 1);
+    if (sz > 0 && std::fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { std::fclose(f); g_reader_err = "short read"; return LB2_ERR_ARG; }
+    std::fclose(f);
+    buf[(size_t)sz] = '\0';
+    const char *p = buf.data(), *end = buf.data() + sz;
+    try {
+        lb2_sdpa *S = new lb2_sdpa();
+        std::unique_ptr<lb2_sdpa> guard(S);
+        // comments: lines starting with '*' or '"'
+        while (p < end && (*p == '*' || *p == '"')) skip_line(p, end);
+        long long v;
+        if (!parse_int(p, end, v) || v <= 0) throw std::runtime_error("bad constraint count");
+        S->m = v;
+        skip_line(p, end);
+        if (!parse_int(p, end, v) || v <= 0) throw std::runtime_error("bad block count");
+        long long nblk = v;
+        skip_line(p, end);
+        // block dimensions, possibly decorated with { } ( ) , '
+        std::vector<long long> dims;
+        while ((long long)dims.size() < nblk && p < end) {
+            skip_ws(p, end);
+            if (p < end && (is_punct(*p) || *p == '\n')) { ++p; continue; }
+            if (!parse_int(p, end, v)) throw std::runtime_error("bad block dimension");
+            dims.push_back(v);
+        }
+        if ((long long)dims.size() != nblk) throw std::runtime_error("missing block dimensions");
+        skip_line(p, end);
+        for (long long k = 0; k < nblk; ++k) {
+            if (dims[k] < 0 && k == nblk - 1) { S->nLpCols = -dims[k]; }
+            else if (dims[k] <= 0) throw std::runtime_error("only one diagonal (LP) block is supported and it must be the last one");
+            else S->dims.push_back(dims[k]);
+        }
+        const long long nsdp = (long long)S->dims.size();
+        // right-hand side
+        S->rhs.resize((size_t)S->m);
+        for (lb2_int i = 0; i < S->m; ++i) {
+            skip_ws(p, end);
+            while (p < end && (is_punct(*p) || *p == '\n')) { ++p; skip_ws(p, end); }
+            if (!parse_double(p, end, S->rhs[(size_t)i])) throw std::runtime_error("bad right-hand side");
+        }
+        skip_line(p, end);
+        // entries: first pass collects triplets per block
+        struct Trip { lb2_int con, pos; double val; };
+        std::vector<std::vector<Trip>> trips((size_t)nsdp);
+        std::vector<Trip> lptrips;
+        while (p < end) {
+            skip_ws(p, end);
+            if (p >= end) break;
+            if (*p == '\n') { ++p; continue; }
+            long long con, blk, i, j;
+            double val;
+            const char *line = p;
+            if (!parse_int(p, end, con) || !parse_int(p, end, blk) || !parse_int(p, end, i) || !parse_int(p, end, j) || !parse_double(p, end, val)) {
+                if (std::strncmp(line, "BEGIN.COMMENT", 13) == 0) break;
+                throw std::runtime_error("malformed entry line");
+            }
+            skip_line(p, end);
+            if (con < 0 || con > S->m || blk < 1 || blk > nblk) throw std::runtime_error("entry index out of range");
+            if (std::fabs(val) < 1e-12) continue;
+            if (con == 0) val = -val;
+            blk -= 1; i -= 1; j -= 1;
+            if (S->nLpCols > 0 && blk == nsdp) {
+                lptrips.push_back({(lb2_int)con, (lb2_int)i, val});
+            } else {
+                const long long n = S->dims[(size_t)blk];
+                const long long hi = i > j ? i : j, lo = i > j ? j : i;
+                if (lo < 0 || hi >= n) throw std::runtime_error("matrix index out of range");
+                trips[(size_t)blk].push_back({(lb2_int)con, (lb2_int)((2 * n - lo - 1) * lo / 2 + hi), val});
+            }
+            S->nElems += 1;
+        }
+        auto compress = [&](const std::vector<Trip> &t, lb2_sdpa::Block &B) {
+            B.beg.assign((size_t)S->m + 2, 0);
+            for (const Trip &e : t) B.beg[(size_t)e.con + 1]++;
+            for (lb2_int c = 0; c <= S->m; ++c) B.beg[(size_t)c + 1] += B.beg[(size_t)c];
+            B.idx.resize(t.size()); B.elem.resize(t.size());
+            std::vector<lb2_int> cur(B.beg.begin(), B.beg.end() - 1);
+            for (const Trip &e : t) { lb2_int q = cur[(size_t)e.con]++; B.idx[(size_t)q] = e.pos; B.elem[(size_t)q] = e.val; }
+        };
+        S->blocks.resize((size_t)nsdp);
+        for (long long k = 0; k < nsdp; ++k) compress(trips[(size_t)k], S->blocks[(size_t)k]);
+        if (S->nLpCols > 0) compress(lptrips, S->lp);
+        *out = guard.release();
+    } catch (const std::exception &e) {
+        g_reader_err = e.what();
+        return LB2_ERR_ARG;
+    }
+    return LB2_OK;
+}
+
+lb2_int lb2_sdpa_info(const lb2_sdpa *s, int what, lb2_int k) {
+    if (!s) return -1;
+    switch (what) {
+    case 0: return s->m;
+    case 1: return (lb2_int)s->dims.size();
+    case 4: return s->nLpCols;
+    case 5: return s->nElems;
+    }
+    if (k < 0 || k >= (lb2_int)s->dims.size()) return -1;
+    if (what == 2) return s->dims[(size_t)k];
+    if (what == 3) return (lb2_int)s->blocks[(size_t)k].idx.size();
+    return -1;
+}
+
+int lb2_sdpa_get(const lb2_sdpa *s, lb2_int k, lb2_int *beg, lb2_int *idx, double *elem, double *rhs) {
+    if (!s) return LB2_ERR_ARG;
+    if (rhs) std::memcpy(rhs, s->rhs.data(), sizeof(double) * s->rhs.size());
+    if (k < 0) return LB2_OK;
+    if (k >= (lb2_int)s->dims.size()) return LB2_ERR_ARG;
+    const lb2_sdpa::Block &B = s->blocks[(size_t)k];
+    if (beg) std::memcpy(beg, B.beg.data(), sizeof(lb2_int) * B.beg.size());
+    if (idx) std::memcpy(idx, B.idx.data(), sizeof(lb2_int) * B.idx.size());
+    if (elem) std::memcpy(elem, B.elem.data(), sizeof(double) * B.elem.size());
+    return LB2_OK;
+}
+
+void lb2_sdpa_free(lb2_sdpa *s) { delete s; }
+
+}  // extern "C"

@@ -44,3 +44,18 @@ def test_reference_driver_runs_on_the_cuda_library(tmp_path):
         c = parse(cpu.stdout)
         assert abs(got["pobj"] - c["pobj"]) <= 1e-6 * (1 + abs(c["pobj"]))
         assert abs(got["dobj"] - c["dobj"]) <= 1e-6 * (1 + abs(c["dobj"]))
+
+
+def test_standalone_cli_solves_a_file(tmp_path):
+    """lorads_b200_cli: the library's own reader + solve, no reference tree involved."""
+    cli = os.path.join(ROOT, "lorads_b200", "lorads_b200_cli")
+    assert os.path.exists(cli), "build with python -m lorads_b200.build"
+    g, inst = load_golden("maxcut_n120")
+    path = str(tmp_path / "mc120.dat-s")
+    sdpa.write_dat_s(inst, path)
+    out = subprocess.run([cli, path, "--quiet"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = parse(out.stdout)
+    ref = json.loads(str(g["solve"]))
+    assert abs(got["pobj"] - ref["pobj"]) <= 1e-6 * (1 + abs(ref["pobj"]))
+    assert abs(got["dobj"] - ref["dobj"]) <= 1e-6 * (1 + abs(ref["dobj"]))

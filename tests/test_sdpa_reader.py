@@ -1,0 +1,79 @@
+"""The library's .dat-s reader (lb2_read_sdpa) against the Python reader, the generators and -- where oracle/_ref
+is present -- the reference's own LReadSDPA output."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from lorads_b200 import capi, sdpa
+
+
+def same_csc(a, b, m):
+    assert a.n == b.n and np.array_equal(a.beg, b.beg)
+    for c in range(m + 1):
+        s, e = a.beg[c], a.beg[c + 1]
+        oa, ob = np.argsort(a.idx[s:e], kind="stable"), np.argsort(b.idx[s:e], kind="stable")
+        assert np.array_equal(a.idx[s:e][oa], b.idx[s:e][ob])
+        assert np.array_equal(a.elem[s:e][oa], b.elem[s:e][ob])
+
+
+@pytest.mark.parametrize("make", [
+    lambda: sdpa.maxcut(60, 200, 1),
+    lambda: sdpa.lovasz_theta(15, 30, 2),
+    lambda: sdpa.matrix_completion(12, 9, 40, 2, 3),
+    lambda: sdpa.multi_block([sdpa.maxcut(10, 20, 4), sdpa.maxcut(10, 25, 5)]),
+])
+def test_matches_generator_and_python_reader(tmp_path, make):
+    inst = make()
+    path = str(tmp_path / "x.dat-s")
+    sdpa.write_dat_s(inst, path)
+    got = capi.read_sdpa(path)
+    ref = sdpa.read_dat_s(path)
+    assert got.m == inst.m and np.array_equal(got.b, inst.b)
+    for a, b, c in zip(got.cones, inst.cones, ref.cones):
+        same_csc(a, b, inst.m)
+        same_csc(a, c, inst.m)
+
+
+def test_format_variants(tmp_path):
+    p = tmp_path / "v.dat-s"
+    p.write_text('"a comment\n* another\n2 = m\n1 = nblocks\n{3}\n{1.5, -2}\n0 1 1 1 2.0\n0 1 2 1 1e-13\n1 1 3 1 0.5\n1 1 2 2 -1\n2 1 3 3 4\n')
+    inst = capi.read_sdpa(str(p))
+    assert inst.m == 2 and inst.blk_dims == [3] and inst.b.tolist() == [1.5, -2.0]
+    c = inst.cones[0]
+    assert c.beg.tolist() == [0, 1, 3, 4]          # the 1e-13 entry is dropped
+    assert c.elem.tolist() == [-2.0, 0.5, -1.0, 4.0]   # objective negated
+    assert c.idx.tolist() == [0, 2, 3, 5]          # PACK_IDX(3, row, col): (0,0)=0 (2,0)=2 (1,1)=3 (2,2)=5
+
+
+def test_lp_block_is_reported(tmp_path):
+    p = tmp_path / "lp.dat-s"
+    p.write_text("1\n2\n2 -3\n1.0\n0 1 1 1 1.0\n1 1 1 1 1.0\n1 2 2 2 1.0\n")
+    with pytest.raises(ValueError):
+        capi.read_sdpa(str(p))
+
+
+def test_errors(tmp_path):
+    with pytest.raises(capi.Lb2Error):
+        capi.read_sdpa(str(tmp_path / "missing.dat-s"))
+    p = tmp_path / "bad.dat-s"
+    p.write_text("2\n1\n3\n1 2\n0 1 5 1 1.0\n")
+    with pytest.raises(capi.Lb2Error):
+        capi.read_sdpa(str(p))
+
+
+def test_against_reference_reader_and_speed(tmp_path):
+    from oracle import ref
+    if not ref.available(32):
+        pytest.skip("oracle/_ref not built")
+    inst = sdpa.maxcut(3000, 20000, 8)
+    path = str(tmp_path / "r.dat-s")
+    sdpa.write_dat_s(inst, path)
+    t0 = time.perf_counter()
+    got = capi.read_sdpa(path)
+    t_lib = time.perf_counter() - t0
+    R = ref.RefSolver(path, 32)
+    beg, idx, elem = R.reader_csc()
+    same_csc(got.cones[0], sdpa.Cone(n=3000, beg=beg, idx=idx, elem=elem), inst.m)
+    assert t_lib < 1.0
