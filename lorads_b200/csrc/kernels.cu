@@ -17,6 +17,9 @@
 #include "kernels.cuh"
 #include "layout.hpp"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace lb2 {
 
 static inline int grid_for(long long n, int per_thread, const Ctx &c) {
@@ -419,12 +422,30 @@ constexpr int kDT = 32;   // tile edge
 
 __device__ __forceinline__ long long packed_col_start(long long n, long long j) { return j * n - j * (j - 1) / 2; }
 
-// One CTA per lower tile (bi >= bj): Z[i,j] = (U_i.V_j + U_j.V_i)/2 ; optional second output D_i.D_j
+// ---- FP64 tensor-core (DMMA) versions -----------------------------------------------------------------
+// mma.sync.aligned.m8n8k4.row.col.f64: A 8x4 (lane holds A[lane/4][lane%4]), B 4x8 (lane holds B[lane%4][lane/4]),
+// C/D 8x8 (lane holds C[lane/4][2*(lane%4)] and the element right of it).
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+struct DenseObj {
+    const double *Cp = nullptr;     // packed dense objective (nullptr: no objective)
+    double s1 = 0.0, s2 = 0.0;      // scales applied to <C,Z1>, <C,Z2>
+    double *obj1 = nullptr, *obj2 = nullptr;
+    double *partials = nullptr;
+    unsigned int *ticket = nullptr;
+};
+
+// One CTA per lower 32x32 tile of Z = sym(U V^T) (packed).  The four factor tiles are staged in shared memory,
+// each warp owns two 8x8 sub-tiles and runs ld/4 DMMA k-steps per product; results are staged back through
+// shared memory so that the packed columns are written with the row index fastest (coalesced).
 template <bool SAME, bool DUAL>
-__global__ void __launch_bounds__(kBlock) dense_uvt_kernel(long long n, int r, int ld, const double *__restrict__ U,
-                                                           const double *__restrict__ V, double *__restrict__ Z1,
-                                                           double *__restrict__ Z2, int nb) {
-    // linear tile id -> (bi, bj) with bi >= bj
+__global__ void __launch_bounds__(kBlock) dense_uvt_dmma_kernel(long long n, int ld, const double *__restrict__ U,
+                                                                const double *__restrict__ V, double *__restrict__ Z1,
+                                                                double *__restrict__ Z2, DenseObj ob) {
     long long t = blockIdx.x;
     int bi = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) / 2.0);
     while ((long long)(bi + 1) * (bi + 2) / 2 <= t) ++bi;
@@ -433,6 +454,7 @@ __global__ void __launch_bounds__(kBlock) dense_uvt_kernel(long long n, int r, i
     extern __shared__ double sm[];
     const int lds = ld + 1;
     double *Ui = sm, *Uj = Ui + kDT * lds, *Vi = Uj + kDT * lds, *Vj = Vi + kDT * lds;
+    double *Zt1 = Vj + kDT * lds, *Zt2 = Zt1 + kDT * (kDT + 1);
     const long long i0 = (long long)bi * kDT, j0 = (long long)bj * kDT;
     for (int q = threadIdx.x; q < kDT * ld; q += kBlock) {
         const int rr = q / ld, cc = q % ld;
@@ -445,49 +467,217 @@ __global__ void __launch_bounds__(kBlock) dense_uvt_kernel(long long n, int r, i
         }
     }
     __syncthreads();
-    // thread -> 4 entries of the 32x32 tile; consecutive threads walk i (contiguous in packed storage)
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fr = lane >> 2, fk = lane & 3;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int sub = 2 * w + h, si = sub >> 2, sj = sub & 3;
+        double p1a = 0, p1b = 0, p2a = 0, p2b = 0, p3a = 0, p3b = 0;
+        const double *ai = Ui + (8 * si + fr) * lds + fk, *bj_ = (SAME ? Uj : Vj) + (8 * sj + fr) * lds + fk;
+        const double *avi = Vi + (8 * si + fr) * lds + fk, *buj = Uj + (8 * sj + fr) * lds + fk;
+        for (int k = 0; k < ld; k += 4) {
+            dmma884(p1a, p1b, ai[k], bj_[k]);                 // U_I V_J^T  (U_I U_J^T when SAME)
+            if (!SAME) {
+                dmma884(p2a, p2b, avi[k], buj[k]);            // V_I U_J^T
+                if (DUAL) dmma884(p3a, p3b, avi[k], bj_[k]);  // V_I V_J^T
+            }
+        }
+        const int row = 8 * si + fr, col = 8 * sj + 2 * fk;
+        const bool d0 = (i0 + row == j0 + col), d1 = (i0 + row == j0 + col + 1);
+        Zt1[row * (kDT + 1) + col] = (SAME || d0) ? p1a : (0.5 * p1a + 0.5 * p2a);
+        Zt1[row * (kDT + 1) + col + 1] = (SAME || d1) ? p1b : (0.5 * p1b + 0.5 * p2b);
+        if (DUAL) { Zt2[row * (kDT + 1) + col] = p3a; Zt2[row * (kDT + 1) + col + 1] = p3b; }
+    }
+    __syncthreads();
     const int li = threadIdx.x % kDT;
+    double o1 = 0.0, o2 = 0.0;
     for (int q = 0; q < kDT * kDT / kBlock; ++q) {
         const int lj = threadIdx.x / kDT + q * (kBlock / kDT);
         const long long gi = i0 + li, gj = j0 + lj;
         if (gi >= n || gj >= n || gi < gj) continue;
-        double a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        if (SAME) {
-            for (int k = 0; k < r; ++k) a1 = fma(Ui[li * lds + k], Uj[lj * lds + k], a1);
-            Z1[packed_col_start(n, gj) + (gi - gj)] = a1;
-        } else {
-            for (int k = 0; k < r; ++k) {
-                a1 = fma(Ui[li * lds + k], Vj[lj * lds + k], a1);
-                a2 = fma(Uj[lj * lds + k], Vi[li * lds + k], a2);
-                if (DUAL) a3 = fma(Vi[li * lds + k], Vj[lj * lds + k], a3);
-            }
-            const long long pos = packed_col_start(n, gj) + (gi - gj);
-            Z1[pos] = (gi == gj) ? a1 : (0.5 * a1 + 0.5 * a2);
-            if (DUAL) Z2[pos] = a3;
+        const long long pos = packed_col_start(n, gj) + (gi - gj);
+        const double z1 = Zt1[li * (kDT + 1) + lj];
+        Z1[pos] = z1;
+        if (DUAL) Z2[pos] = Zt2[li * (kDT + 1) + lj];
+        if (ob.Cp) {
+            const double cw = (gi == gj) ? ob.Cp[pos] : 2.0 * ob.Cp[pos];
+            o1 = fma(cw, z1, o1);
+            if (DUAL) o2 = fma(cw, Zt2[li * (kDT + 1) + lj], o2);
+        }
+    }
+    if (ob.Cp) {
+        // <C, Z> fused here (objAUV for a dense objective): per-tile partials, last CTA adds them in tile order
+        __shared__ double rsm[8];
+        __shared__ bool last;
+        o1 = block_sum(o1, rsm);
+        if (DUAL) o2 = block_sum(o2, rsm);
+        if (threadIdx.x == 0) {
+            ob.partials[2 * (size_t)blockIdx.x] = o1;
+            if (DUAL) ob.partials[2 * (size_t)blockIdx.x + 1] = o2;
+        }
+        __threadfence();
+        if (threadIdx.x == 0) last = (atomicAdd(ob.ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (!last) return;
+        __threadfence();
+        double t1 = 0.0, t2 = 0.0;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += kBlock) {
+            t1 += __ldcg(ob.partials + 2 * (size_t)b);
+            if (DUAL) t2 += __ldcg(ob.partials + 2 * (size_t)b + 1);
+        }
+        t1 = block_sum(t1, rsm);
+        if (DUAL) t2 = block_sum(t2, rsm);
+        if (threadIdx.x == 0) {
+            if (ob.obj1) *ob.obj1 += ob.s1 * t1;
+            if (DUAL && ob.obj2) *ob.obj2 += ob.s2 * t2;
+            *ob.ticket = 0u;
         }
     }
 }
 
-void launch_dense_uvt(Ctx &c, long long n, int r, int ld, const double *U, const double *V, double *Zp, bool same) {
+// Split-K symmetric product: CTA (x = 64-row block, y = split) accumulates its share of column blocks with DMMA
+// (warp w owns rows 8w..8w+7 and every 8-column sub-tile of X) and writes a partial n x ldp block; the finish
+// kernel adds the partials in split order and applies the epilogue (deterministic).
+constexpr int kSymRows = 64, kSymMaxSub = 12;   // ld <= 96 on this path
+__global__ void __launch_bounds__(kBlock) dense_symm_dmma_kernel(long long n, int ld, int ldp, const double *__restrict__ Sp,
+                                                                 const double *__restrict__ X, double *__restrict__ part,
+                                                                 int jb_per_split) {
+    extern __shared__ double sm[];
+    double *St = sm;                                   // kSymRows x (kDT + 1)
+    double *Xt = sm + kSymRows * (kDT + 1);            // kDT x (ldp + 1)
+    const int ldx = ldp + 1, nsub = ldp / 8;
+    const long long i0 = (long long)blockIdx.x * kSymRows;
+    const int nb = (int)((n + kDT - 1) / kDT);
+    const int jb0 = blockIdx.y * jb_per_split, jb1 = min(nb, jb0 + jb_per_split);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, fr = lane >> 2, fk = lane & 3;
+    double acc[kSymMaxSub][2];
+#pragma unroll
+    for (int q = 0; q < kSymMaxSub; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+    // The S tile of the NEXT column block is fetched into registers (8 independent loads per thread) while the
+    // tensor-core loop works on the current one: one global round trip per tile instead of eight.
+    constexpr int kPer = kSymRows * kDT / kBlock;
+    double sreg[kPer];
+    auto fetch = [&](int jb) {
+        const long long j0 = (long long)jb * kDT;
+        if (i0 >= j0 + kDT) {            // below the diagonal: S[i][j] = packed(col j)[i - j], row index fastest
+#pragma unroll
+            for (int u = 0; u < kPer; ++u) {
+                const int q = threadIdx.x + u * kBlock, x = q % kSymRows, y = q / kSymRows;
+                const long long gi = i0 + x, gj = j0 + y;
+                sreg[u] = (gi < n && gj < n) ? __ldg(Sp + packed_col_start(n, gj) + (gi - gj)) : 0.0;
+            }
+        } else if (i0 + kSymRows <= j0) { // above: S[i][j] = packed(col i)[j - i], column index fastest
+#pragma unroll
+            for (int u = 0; u < kPer; ++u) {
+                const int q = threadIdx.x + u * kBlock, x = q % kDT, y = q / kDT;
+                const long long gi = i0 + y, gj = j0 + x;
+                sreg[u] = (gi < n && gj < n) ? __ldg(Sp + packed_col_start(n, gi) + (gj - gi)) : 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kPer; ++u) {
+                const int q = threadIdx.x + u * kBlock, x = q % kSymRows, y = q / kSymRows;
+                const long long gi = i0 + x, gj = j0 + y;
+                double v = 0.0;
+                if (gi < n && gj < n)
+                    v = (gi >= gj) ? __ldg(Sp + packed_col_start(n, gj) + (gi - gj)) : __ldg(Sp + packed_col_start(n, gi) + (gj - gi));
+                sreg[u] = v;
+            }
+        }
+    };
+    auto stash = [&](int jb) {
+        const long long j0 = (long long)jb * kDT;
+        const bool above = (i0 + kSymRows <= j0) && !(i0 >= j0 + kDT);
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int q = threadIdx.x + u * kBlock;
+            if (above) St[(q / kDT) * (kDT + 1) + (q % kDT)] = sreg[u];
+            else St[(q % kSymRows) * (kDT + 1) + (q / kSymRows)] = sreg[u];
+        }
+    };
+    if (jb0 < jb1) fetch(jb0);
+    for (int jb = jb0; jb < jb1; ++jb) {
+        const long long j0 = (long long)jb * kDT;
+        __syncthreads();
+        stash(jb);
+        for (int q = threadIdx.x; q < kDT * ldp; q += kBlock) {
+            const int rr = q / ldp, cc = q % ldp;
+            Xt[rr * ldx + cc] = ((j0 + rr) < n && cc < ld) ? X[(j0 + rr) * ld + cc] : 0.0;
+        }
+        __syncthreads();
+        if (jb + 1 < jb1) fetch(jb + 1);
+#pragma unroll
+        for (int ks = 0; ks < kDT / 4; ++ks) {
+            const double a = St[(8 * w + fr) * (kDT + 1) + 4 * ks + fk];
+            const double *xb = Xt + (4 * ks + fk) * ldx + fr;
+#pragma unroll
+            for (int q = 0; q < kSymMaxSub; ++q)
+                if (q < nsub) dmma884(acc[q][0], acc[q][1], a, xb[8 * q]);
+        }
+    }
+    const long long gi = i0 + 8 * w + fr;
+    if (gi < n) {
+        double *dst = part + ((size_t)blockIdx.y * n + gi) * ldp + 2 * fk;
+#pragma unroll
+        for (int q = 0; q < kSymMaxSub; ++q)
+            if (q < nsub) { dst[8 * q] = acc[q][0]; dst[8 * q + 1] = acc[q][1]; }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) dense_symm_finish_kernel(long long n, int r, int ld, int ldp, int nsplit,
+                                                                   const double *__restrict__ part, double a, double b,
+                                                                   const double *__restrict__ Z, const double *__restrict__ Z2,
+                                                                   double *__restrict__ Y, ReduceScratch rs, double *red) {
+    double ryy = 0.0, ryz = 0.0;
+    const long long total = n * ld;
+    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < total; q += (long long)gridDim.x * kBlock) {
+        const long long i = q / ld;
+        const int col = (int)(q % ld);
+        double acc = 0.0;
+        for (int sidx = 0; sidx < nsplit; ++sidx) acc += part[((size_t)sidx * n + i) * ldp + col];
+        double y = a * acc;
+        if (Z) y = fma(b, Z[q], y);
+        if (col >= r) y = 0.0;
+        Y[q] = y;
+        ryy = fma(y, y, ryy);
+        if (Z2) ryz = fma(y, Z2[q], ryz);
+    }
+    if (red) {
+        double v[2] = {ryy, ryz};
+        if (grid_reduce<2>(v, rs) && threadIdx.x == 0) { red[0] = v[0]; red[1] = v[1]; }
+    }
+}
+
+void launch_dense_uvt(Ctx &c, long long n, int r, int ld, const double *U, const double *V, double *Zp, bool same,
+                      const double *Cp, double scale, double *obj) {
+    DenseObj ob;
+    if (Cp && obj) { ob.Cp = Cp; ob.s1 = scale; ob.obj1 = obj; ob.partials = c.dense_part; ob.ticket = c.ticket; }
     const int nb = (int)((n + kDT - 1) / kDT);
     const long long tiles = (long long)nb * (nb + 1) / 2;
-    const size_t smem = sizeof(double) * 4 * kDT * (ld + 1);
+    const size_t smem = sizeof(double) * (4 * kDT * (ld + 1) + 2 * kDT * (kDT + 1));
     if (same) {
-        LB2_CUDA(cudaFuncSetAttribute(dense_uvt_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dense_uvt_kernel<true, false><<<(unsigned)tiles, kBlock, smem, c.stream>>>(n, r, ld, U, V, Zp, nullptr, nb);
+        LB2_CUDA(cudaFuncSetAttribute(dense_uvt_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dense_uvt_dmma_kernel<true, false><<<(unsigned)tiles, kBlock, smem, c.stream>>>(n, ld, U, V, Zp, nullptr, ob);
     } else {
-        LB2_CUDA(cudaFuncSetAttribute(dense_uvt_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dense_uvt_kernel<false, false><<<(unsigned)tiles, kBlock, smem, c.stream>>>(n, r, ld, U, V, Zp, nullptr, nb);
+        LB2_CUDA(cudaFuncSetAttribute(dense_uvt_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dense_uvt_dmma_kernel<false, false><<<(unsigned)tiles, kBlock, smem, c.stream>>>(n, ld, U, V, Zp, nullptr, ob);
     }
+    (void)r;
     LB2_LAUNCH_CHECK(c);
 }
 
-void launch_dense_uvt_dual(Ctx &c, long long n, int r, int ld, const double *R, const double *D, double *Z1, double *Z2) {
+void launch_dense_uvt_dual(Ctx &c, long long n, int r, int ld, const double *R, const double *D, double *Z1, double *Z2,
+                           const double *Cp, double s1, double s2, double *obj1, double *obj2) {
+    DenseObj ob;
+    if (Cp && (obj1 || obj2)) {
+        ob.Cp = Cp; ob.s1 = s1; ob.s2 = s2; ob.obj1 = obj1; ob.obj2 = obj2; ob.partials = c.dense_part; ob.ticket = c.ticket;
+    }
     const int nb = (int)((n + kDT - 1) / kDT);
     const long long tiles = (long long)nb * (nb + 1) / 2;
-    const size_t smem = sizeof(double) * 4 * kDT * (ld + 1);
-    LB2_CUDA(cudaFuncSetAttribute(dense_uvt_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dense_uvt_kernel<false, true><<<(unsigned)tiles, kBlock, smem, c.stream>>>(n, r, ld, R, D, Z1, Z2, nb);
+    const size_t smem = sizeof(double) * (4 * kDT * (ld + 1) + 2 * kDT * (kDT + 1));
+    LB2_CUDA(cudaFuncSetAttribute(dense_uvt_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dense_uvt_dmma_kernel<false, true><<<(unsigned)tiles, kBlock, smem, c.stream>>>(n, ld, R, D, Z1, Z2, ob);
+    (void)r;
     LB2_LAUNCH_CHECK(c);
 }
 
@@ -592,6 +782,28 @@ __global__ void __launch_bounds__(kBlock) dense_symm_kernel(long long n, int r, 
 void launch_dense_symm(Ctx &c, long long n, int r, int ld, const double *Sp, const double *X, double a, double b,
                        const double *Z, const double *Z2, double *Y, double *red) {
     if (ld > 256) throw std::runtime_error("rank above 256 is not supported by the dense symm kernel yet");
+    if (ld <= 8 * kSymMaxSub && c.dense_part) {
+        // FP64 tensor-core path: split-K grid of (64-row blocks) x (splits), partials added in a fixed order
+        const int ldp = ((ld + 7) / 8) * 8;
+        const int nb = (int)((n + kDT - 1) / kDT), nrb = (int)((n + kSymRows - 1) / kSymRows);
+        int nsplit = (8 * c.num_sms + nrb - 1) / nrb;
+        nsplit = std::max(1, std::min(nsplit, std::min(nb, 32)));
+        while ((size_t)nsplit * n * ldp > c.dense_part_cap && nsplit > 1) --nsplit;
+        if ((size_t)nsplit * n * ldp <= c.dense_part_cap) {
+            const int jbps = (nb + nsplit - 1) / nsplit;
+            nsplit = (nb + jbps - 1) / jbps;
+            // (a register-tiled DFMA version of this kernel measured 136 us / 414 us at n = 3000, ld = 20 / 68 against
+            //  90 us / 119 us for DMMA on the B200: the FP64 tensor pipe is the faster FP64 path on this part)
+            const size_t smem = sizeof(double) * (kSymRows * (kDT + 1) + kDT * (ldp + 1));
+            LB2_CUDA(cudaFuncSetAttribute(dense_symm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dense_symm_dmma_kernel<<<dim3(nrb, nsplit), kBlock, smem, c.stream>>>(n, ld, ldp, Sp, X, c.dense_part, jbps);
+            LB2_LAUNCH_CHECK(c);
+            dense_symm_finish_kernel<<<grid_for(n * ld, 1, c), kBlock, 0, c.stream>>>(n, r, ld, ldp, nsplit, c.dense_part, a, b, Z, Z2,
+                                                                                   Y, c.rs, red);
+            LB2_LAUNCH_CHECK(c);
+            return;
+        }
+    }
     const int nb = (int)((n + kDT - 1) / kDT);
     const size_t smem = sizeof(double) * (kDT * (kDT + 1) + kDT * ld);
     LB2_CUDA(cudaFuncSetAttribute(dense_symm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -9,6 +9,8 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     ReduceScratch rs{nullptr, nullptr};
     unsigned int *ticket = nullptr;    // zero-initialised counter for "last block finishes" kernels
+    double *dense_part = nullptr;      // split-K partials of the dense symmetric product (dense-scratch cones only)
+    size_t dense_part_cap = 0;         // capacity of dense_part in doubles
     int num_sms = 148;
     long long launches = 0;
 };
@@ -68,9 +70,12 @@ void launch_rank1_obj(Ctx &c, int ld, const double *csA, const double *csB, doub
 // dense path (cones whose scratch matrices are dense, lorads_sdp_conic.c:884-963)
 // ------------------------------------------------------------------------------------------------
 // Zp (packed lower, column-major as the reference) = sym(U V^T);  replaces dsyr2k + repack (lorads_alg_common.c:50-67)
-void launch_dense_uvt(Ctx &c, long long n, int r, int ld, const double *U, const double *V, double *Zp, bool same);
+void launch_dense_uvt(Ctx &c, long long n, int r, int ld, const double *U, const double *V, double *Zp, bool same,
+                      const double *Cp = nullptr, double scale = 0.0, double *obj = nullptr);
 // dual variant: Z1 = sym(R D^T), Z2 = D D^T
-void launch_dense_uvt_dual(Ctx &c, long long n, int r, int ld, const double *R, const double *D, double *Z1, double *Z2);
+void launch_dense_uvt_dual(Ctx &c, long long n, int r, int ld, const double *R, const double *D, double *Z1, double *Z2,
+                           const double *Cp = nullptr, double s1 = 0.0, double s2 = 0.0, double *obj1 = nullptr,
+                           double *obj2 = nullptr);
 // Sp = (addC ? Cp : 0) then Sp[D_pos[u]] += sum_k w[..] T_val[k]
 void launch_dense_wsum(Ctx &c, double *Sp, long long psize, const double *Cp, const long long *D_pos, long long n_pos,
                        const int *T_ptr, const int *T_con, const double *T_val, const double *w, const int *act_idx,

@@ -179,6 +179,16 @@ void Solver::alloc_vars() {
         N += K.n * K.ld;
     }
     for (DBuf<double> *v : {&R, &U, &V, &G, &M2, &Bls, &cg_r, &cg_p, &cg_Q, &Dtemp}) v->alloc((size_t)N);
+    {
+        // split-K scratch of the dense symmetric product: up to 32 partial n x ldp blocks of the largest dense cone
+        size_t need = 0;
+        for (const ConeDev &K : cones)
+            if (K.dense_path) need = std::max(need, (size_t)32 * (size_t)K.n * (size_t)(((K.ld + 7) / 8) * 8));
+        need = std::min(need, (size_t)1 << 28);     // cap at 2 GiB of doubles; the launcher lowers the split count
+        dense_part.alloc(need, false);
+        ctx.dense_part = dense_part.p;
+        ctx.dense_part_cap = need;
+    }
     lb_s.clear(); lb_y.clear();
     lb_s.resize(lbfgs_len); lb_y.resize(lbfgs_len);
     for (int k = 0; k < lbfgs_len; ++k) { lb_s[k].alloc((size_t)N); lb_y[k].alloc((size_t)N); }
@@ -299,10 +309,13 @@ void Solver::cone_auv(ConeDev &K, bool with_obj, const double *Um, const double 
                       double *obj) {
     ItemListBufs &L = with_obj ? K.listAC : K.listA;
     if (K.dense_path) {
-        if (world > 1 && myrank != 0) obj = nullptr;   // Z is all-reduced first: only one rank may feed the slot
-        launch_dense_uvt(ctx, K.n, K.r, K.ld, Um + K.off, Vm + K.off, K.Z1.p, same);
+        // <C,Z> is taken inside the tile kernel from this rank's share of Z (the slot is summed over ranks by the
+        // caller); the constraint rows come from the A-only item list over the all-reduced Z
+        launch_dense_uvt(ctx, K.n, K.r, K.ld, Um + K.off, Vm + K.off, K.Z1.p, same, with_obj ? K.C_onP.p : nullptr, scale,
+                         with_obj ? obj : nullptr);
         if (world > 1) allreduce(K.Z1.p, K.np);
-        launch_auv(ctx, AUV_FROMZ, L.dev, K.Z1.p, nullptr, K.ld, scale, 0.0, out, nullptr, K.carry1.p, nullptr, obj, nullptr);
+        launch_auv(ctx, AUV_FROMZ, K.listA.dev, K.Z1.p, nullptr, K.ld, scale, 0.0, out, nullptr, K.carry1.p, nullptr, nullptr,
+                   nullptr);
         return;
     }
     // with column sharding the objective is summed over ranks by the caller (the slot is all-reduced once)
@@ -321,11 +334,12 @@ void Solver::cone_auv_dual(ConeDev &K, const double *Rm, const double *Dm, doubl
                            double *obj2) {
     ItemListBufs &L = K.listAC;
     if (K.dense_path) {
-        if (world > 1 && myrank != 0) { obj1 = nullptr; obj2 = nullptr; }
-        launch_dense_uvt_dual(ctx, K.n, K.r, K.ld, Rm + K.off, Dm + K.off, K.Z1.p, K.Z2.p);
+        launch_dense_uvt_dual(ctx, K.n, K.r, K.ld, Rm + K.off, Dm + K.off, K.Z1.p, K.Z2.p, K.C_onP.p, 2.0, 1.0, obj1, obj2);
         if (world > 1) { allreduce(K.Z1.p, K.np); allreduce(K.Z2.p, K.np); }
-        launch_auv(ctx, AUV_FROMZ, L.dev, K.Z1.p, nullptr, K.ld, 2.0, 0.0, out1, nullptr, K.carry1.p, nullptr, obj1, nullptr);
-        launch_auv(ctx, AUV_FROMZ, L.dev, K.Z2.p, nullptr, K.ld, 1.0, 0.0, out2, nullptr, K.carry1.p, nullptr, obj2, nullptr);
+        launch_auv(ctx, AUV_FROMZ, K.listA.dev, K.Z1.p, nullptr, K.ld, 2.0, 0.0, out1, nullptr, K.carry1.p, nullptr, nullptr,
+                   nullptr);
+        launch_auv(ctx, AUV_FROMZ, K.listA.dev, K.Z2.p, nullptr, K.ld, 1.0, 0.0, out2, nullptr, K.carry1.p, nullptr, nullptr,
+                   nullptr);
         return;
     }
     launch_auv(ctx, AUV_DUAL, L.dev, Rm + K.off, Dm + K.off, K.ld, 2.0, 1.0, out1, out2, K.carry1.p, K.carry2.p, obj1, obj2);

@@ -99,7 +99,7 @@ struct Solver {
     // scalars
     DBuf<double> S;
     double *S_host = nullptr;          // pinned mirror
-    DBuf<double> red_partials;
+    DBuf<double> red_partials, dense_part;
     DBuf<unsigned int> red_counter;
     double *push_host = nullptr;       // pinned staging for {tau, rho}
     // replayable CUDA graphs of the steady-state inner iteration, keyed by (L-BFGS ring head, history depth)
