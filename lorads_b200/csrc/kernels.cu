@@ -66,11 +66,19 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
         for (int k = t0 + tid; k < t1; k += kBlock) sp1[k - t0] = scale1 * L.coef[k] * U[L.irow[k]];
     } else {
         constexpr int NG = kBlock / G;          // groups per block
+        constexpr int IPG = TILE / NG;          // consecutive items per group
         const int g = tid / G, gl = tid % G;
-        // warp-uniform trip count: every lane reaches the shuffles of every iteration (tail lanes idle)
+        // A group walks IPG CONSECUTIVE items.  Items of the objective are in column-major pattern order, so the
+        // column-side rows (U_j, V_j) usually repeat from one item to the next: they stay in registers and are
+        // gathered again only when the column (or, for the row side, the row) changes.  This halves the L1/L2
+        // wavefronts of the gather.  The trip count is warp-uniform (every lane reaches every shuffle).
+        int pi = -1, pj = -1;
+        double2 x[NP], y[NP], p[NP], qv[NP];    // U_i, V_j (U_j when SAME), U_j, V_i
+#pragma unroll
+        for (int q = 0; q < NP; ++q) x[q] = y[q] = p[q] = qv[q] = make_double2(0.0, 0.0);
 #pragma unroll 1
-        for (int base = t0; base < t1; base += NG) {
-            const int k = base + g;
+        for (int s_ = 0; s_ < IPG; ++s_) {
+            const int k = t0 + g * IPG + s_;
             const bool live = k < t1;
             double a1 = 0.0, a2 = 0.0, a3 = 0.0, cf = 0.0;
             bool diag = true;
@@ -80,27 +88,39 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
                 diag = (i == j);
                 const double *ui = U + (size_t)i * ld + 2 * gl, *uj = U + (size_t)j * ld + 2 * gl;
                 if constexpr (MODE == AUV_SAME) {
-                    double2 x[NP], y[NP];
+                    if (i != pi) {
 #pragma unroll
-                    for (int q = 0; q < NP; ++q) {
-                        const bool in = (2 * gl + 2 * G * q) < ld;
-                        x[q] = in ? ld2(ui + 2 * G * q) : make_double2(0.0, 0.0);
-                        y[q] = (in && !diag) ? ld2(uj + 2 * G * q) : x[q];
+                        for (int q = 0; q < NP; ++q)
+                            x[q] = ((2 * gl + 2 * G * q) < ld) ? ld2(ui + 2 * G * q) : make_double2(0.0, 0.0);
+                    }
+                    if (j != pj) {
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            if (diag) y[q] = x[q];
+                            else y[q] = ((2 * gl + 2 * G * q) < ld) ? ld2(uj + 2 * G * q) : make_double2(0.0, 0.0);
+                        }
                     }
 #pragma unroll
                     for (int q = 0; q < NP; ++q) { a1 = fma(x[q].x, y[q].x, a1); a1 = fma(x[q].y, y[q].y, a1); }
                 } else {
                     const double *vi = V + (size_t)i * ld + 2 * gl, *vj = V + (size_t)j * ld + 2 * gl;
-                    double2 x[NP], y[NP], p[NP], qv[NP];
+                    if (i != pi) {
 #pragma unroll
-                    for (int q = 0; q < NP; ++q) {
-                        const bool in = (2 * gl + 2 * G * q) < ld;
-                        x[q] = in ? ld2(ui + 2 * G * q) : make_double2(0.0, 0.0);      // U_i
-                        qv[q] = in ? ld2(vi + 2 * G * q) : make_double2(0.0, 0.0);     // V_i
-                        if (!diag) {
-                            y[q] = in ? ld2(vj + 2 * G * q) : make_double2(0.0, 0.0);  // V_j
-                            p[q] = in ? ld2(uj + 2 * G * q) : make_double2(0.0, 0.0);  // U_j
-                        } else { y[q] = qv[q]; p[q] = x[q]; }
+                        for (int q = 0; q < NP; ++q) {
+                            const bool in = (2 * gl + 2 * G * q) < ld;
+                            x[q] = in ? ld2(ui + 2 * G * q) : make_double2(0.0, 0.0);      // U_i
+                            qv[q] = in ? ld2(vi + 2 * G * q) : make_double2(0.0, 0.0);     // V_i
+                        }
+                    }
+                    if (j != pj) {
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            const bool in = (2 * gl + 2 * G * q) < ld;
+                            if (!diag) {
+                                y[q] = in ? ld2(vj + 2 * G * q) : make_double2(0.0, 0.0);  // V_j
+                                p[q] = in ? ld2(uj + 2 * G * q) : make_double2(0.0, 0.0);  // U_j
+                            } else { y[q] = qv[q]; p[q] = x[q]; }
+                        }
                     }
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
@@ -109,6 +129,7 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
                         if constexpr (DUAL) { a3 = fma(qv[q].x, y[q].x, a3); a3 = fma(qv[q].y, y[q].y, a3); }  // V_i . V_j
                     }
                 }
+                pi = i; pj = j;
             }
             a1 = group_sum<G>(a1);
             if constexpr (MODE != AUV_SAME) a2 = group_sum<G>(a2);
