@@ -103,6 +103,16 @@ int lb2_create(lb2_solver **out, lb2_int nRows, lb2_int nCones, const lb2_int *b
 /* LORADSInitConeData (lorads_solver.c:130) for one PSD block; arrays are borrowed during the call only. */
 int lb2_set_cone_data(lb2_solver *s, lb2_int iCone, const lb2_int *coneMatBeg,
                       const lb2_int *coneMatIdx, const double *coneMatElem);
+/* The LP cone of the problem (LORADSSetLpCone, lorads_lp_conic.c:217-237, called from LORADSInitConeData
+ * lorads_solver.c:135-137): the reader's LpMatBeg / LpMatIdx / LpMatElem, i.e. a CSC matrix with m+1 columns
+ * (column 0 = objective, column i+1 = constraint i) whose row index is the LP column.  Call before lb2_preprocess;
+ * nLpCols = 0 clears it.  The LP variables ride behind the PSD factors in every factor-sized vector. */
+int lb2_set_lp_data(lb2_solver *s, lb2_int nLpCols, const lb2_int *LpMatBeg, const lb2_int *LpMatIdx,
+                    const double *LpMatElem);
+/* LP vectors (nLpCols doubles): 'R' rLp, 'U' uLp, 'V' vLp, 'G' gradLp (def_lorads_solver.h lorads_variable),
+ * 'x' the product represented in constrValLP, 'c' the (scaled) LP objective (get only). */
+int lb2_get_lp_vec(lb2_solver *s, char which, double *out);
+int lb2_set_lp_vec(lb2_solver *s, char which, const double *in);
 /* LORADSPreprocess (lorads_solver.c:189): AConeProcData + AConePresolveData (lorads_sdp_conic.c:758,868):
  * coefficient classification, union pattern, index maps; then the device layouts are built and uploaded. */
 int lb2_preprocess(lb2_solver *s);
@@ -123,8 +133,9 @@ int lb2_comm_init(lb2_solver *s, const void *id128, int rank, int world);
 /* ---- SDPA .dat-s ingest (host only) -------------------------------------------------------------------- */
 /* Fast replacement of LReadSDPA (lorads_file_io.c:21-418) with the same output convention: per PSD block a CSC
  * matrix with m+1 columns over the packed lower-triangular index, column 0 = objective (negated), entries
- * |v| < 1e-12 dropped, a trailing negative dimension = LP block (reported through info 4; the device layer
- * does not take LP blocks yet).  The arrays can be passed straight to lb2_set_cone_data. */
+ * |v| < 1e-12 dropped, a trailing negative dimension = LP block (info 4 = nLpCols; block index k = number of PSD
+ * blocks addresses it in info 3 / lb2_sdpa_get, output = LpMatBeg/Idx/Elem for lb2_set_lp_data).
+ * The arrays can be passed straight to lb2_set_cone_data. */
 typedef struct lb2_sdpa lb2_sdpa;
 int lb2_read_sdpa(const char *path, lb2_sdpa **out);
 /* what: 0 nConstrs, 1 number of PSD blocks, 2 dimension of block k, 3 non-zeros of block k, 4 nLpCols, 5 nElems */
@@ -185,6 +196,12 @@ int lb2_cg_matvec(lb2_solver *s, lb2_int iCone, char noUpdate, const double *x, 
 /* LORADSUpdateSDPVarOne (lorads_admm.c:428) = RHS build + CGSolve (lorads_cgs.c:81), all on device. */
 int lb2_update_sdp_var_one(lb2_solver *s, lb2_int iCone, char upd, char noupd, double rho,
                            double cgTol, lb2_int cgMaxIter, lb2_int *cgIters);
+/* Head of LORADSADMMOptimize (lorads_admm.c:47-48): constrVal of every block and constrValSum from (U, V), LP columns
+ * included (LORADSInitConstrValAllLP / LORADSInitConstrValSumLP). */
+int lb2_admm_init_constr(lb2_solver *s);
+/* One Gauss-Seidel sweep over every block: LORADSUpdateSDPVar, and with an LP block LORADSUpdateSDPLPVar
+ * (lorads_alg_common.c:187-249). */
+int lb2_admm_update_var(lb2_solver *s, double rho, double cgTol, lb2_int cgMaxIter);
 /* state at ALG_START of LORADS_ALMOptimize (lorads_alm.c:1004-1014); returns sum ||Grad||^2 */
 int lb2_alm_prepare(lb2_solver *s, double rho, double *lagNormSquare);
 /* one ALM inner iteration, the loop body lorads_alm.c:1073-1146.

@@ -110,7 +110,6 @@ extern lorads_int csp_nnz_cols(lorads_int n, lorads_int *Ap)
 /* ---- lorads_solver.h ------------------------------------------------------------------------- */
 extern void LORADSInitSolver(lorads_solver *S, lorads_int nRows, lorads_int nCones, lorads_int *blkDims, lorads_int nLpCols)
 {
-    if (nLpCols > 0) { fprintf(stderr, "lorads_b200 drop-in: LP cones are not supported by the device layer yet\n"); exit(2); }
     S->nLpCols = nLpCols; S->nRows = nRows; S->nCones = nCones;
     LORADS_INIT(S->rowRHS, double, nRows);
     LORADS_INIT(S->dimacError, double, 5);
@@ -124,7 +123,7 @@ extern void LORADSInitConeData(lorads_solver *S, user_data **SDPDatas, double **
                                lorads_int **coneMatIdx, lorads_int *BlkDims, lorads_int nConstrs, lorads_int nBlks,
                                lorads_int nLpCols, lorads_int *LpMatBeg, lorads_int *LpMatIdx, double *LpMatElem)
 {
-    (void)SDPDatas; (void)nLpCols; (void)LpMatBeg; (void)LpMatIdx; (void)LpMatElem;
+    (void)SDPDatas;
     lb2_int *dims = (lb2_int *)malloc(sizeof(lb2_int) * nBlks);
     for (lorads_int i = 0; i < nBlks; ++i) dims[i] = BlkDims[i];
     const char *dev = getenv("LORADS_B200_DEVICE");
@@ -137,6 +136,16 @@ extern void LORADSInitConeData(lorads_solver *S, user_data **SDPDatas, double **
         for (lorads_int i = 0; i < nConstrs + 2; ++i) beg[i] = coneMatBeg[k][i];
         for (lorads_int i = 0; i < nnz; ++i) idx[i] = coneMatIdx[k][i];
         if (lb2_set_cone_data(g_h, k, beg, idx, coneMatElem[k]) != LB2_OK) die("lb2_set_cone_data");
+        free(beg); free(idx);
+    }
+    if (nLpCols > 0) {
+        /* LORADSSetLpCone (lorads_solver.c:135-137): the reader's LP arrays go to the device layer as they are */
+        const lorads_int nnz = LpMatBeg[nConstrs + 1];
+        lb2_int *beg = (lb2_int *)malloc(sizeof(lb2_int) * (nConstrs + 2));
+        lb2_int *idx = (lb2_int *)malloc(sizeof(lb2_int) * (nnz + 1));
+        for (lorads_int i = 0; i < nConstrs + 2; ++i) beg[i] = LpMatBeg[i];
+        for (lorads_int i = 0; i < nnz; ++i) idx[i] = LpMatIdx[i];
+        if (lb2_set_lp_data(g_h, nLpCols, beg, idx, LpMatElem) != LB2_OK) die("lb2_set_lp_data");
         free(beg); free(idx);
     }
 }
@@ -172,22 +181,22 @@ static lorads_sdp_dense *shell(lorads_int n, lorads_int r)
 extern void LORADSInitALMVars(lorads_solver *S, lorads_int *rankElem, lorads_int *BlkDims, lorads_int nBlks, lorads_int nLpCols,
                               lorads_int lbfgsHis)
 {
-    (void)nLpCols;
     LORADS_INIT(S->var->R, lorads_sdp_dense *, nBlks);
     LORADS_INIT(S->var->Grad, lorads_sdp_dense *, nBlks);
     LORADS_INIT(S->var->rLp, lorads_lp_dense, 1);
     LORADS_INIT(S->var->gradLp, lorads_lp_dense, 1);
+    S->var->rLp->nCols = nLpCols; S->var->gradLp->nCols = nLpCols;     /* values are device resident (lb2_get_lp_vec) */
     for (lorads_int i = 0; i < nBlks; ++i) { S->var->R[i] = shell(BlkDims[i], rankElem[i]); S->var->Grad[i] = shell(BlkDims[i], rankElem[i]); }
     S->hisRecT = lbfgsHis;
 }
 
 extern void LORADSInitADMMVars(lorads_solver *S, lorads_int *rankElem, lorads_int *BlkDims, lorads_int nBlks, lorads_int nLpCols)
 {
-    (void)nLpCols;
     LORADS_INIT(S->var->U, lorads_sdp_dense *, nBlks);
     LORADS_INIT(S->var->V, lorads_sdp_dense *, nBlks);
     LORADS_INIT(S->var->uLp, lorads_lp_dense, 1);
     LORADS_INIT(S->var->vLp, lorads_lp_dense, 1);
+    S->var->uLp->nCols = nLpCols; S->var->vLp->nCols = nLpCols;
     for (lorads_int i = 0; i < nBlks; ++i) { S->var->U[i] = shell(BlkDims[i], rankElem[i]); S->var->V[i] = shell(BlkDims[i], rankElem[i]); }
 }
 
@@ -317,6 +326,8 @@ extern void averageUV(lorads_sdp_dense *U, lorads_sdp_dense *V, lorads_sdp_dense
     (void)U; (void)V; (void)UVavg;               /* device state: R = (U + V) / 2 for every cone (idempotent per call) */
     if (lb2_average_uv(g_h) != LB2_OK) die("lb2_average_uv");
 }
+/* lb2_average_uv / lb2_copy_r_to_v act on the whole [cones | LP] vector, so the LP variants need no work of their
+ * own: main.c always calls them next to the cone versions (main.c:438-447) */
 extern void averageUVLP(lorads_lp_dense *u, lorads_lp_dense *v, lorads_lp_dense *avg) { (void)u; (void)v; (void)avg; }
 extern void copyRtoV(lorads_lp_dense *r, lorads_lp_dense *v, lorads_sdp_dense **R, lorads_sdp_dense **V, lorads_int nCones)
 {

@@ -53,6 +53,7 @@ EXPORTS = [
     "lb2_alm_cal_grad", "lb2_cg_matvec", "lb2_update_sdp_var_one", "lb2_alm_prepare", "lb2_alm_inner_iter",
     "lb2_time_alm_inner_iters", "lb2_alm_run_host", "lb2_bench_kernel", "lb2_alm_optimize", "lb2_alm_to_admm", "lb2_admm_optimize", "lb2_dual_infeasibility",
     "lb2_solve", "lb2_get_solution", "lb2_reopt", "lb2_average_uv", "lb2_copy_r_to_v", "lb2_get_state", "lb2_set_state", "lb2_host_presolve", "lb2_host_line_search", "lb2_host_rank_rule",
+    "lb2_set_lp_data", "lb2_get_lp_vec", "lb2_set_lp_vec", "lb2_admm_init_constr", "lb2_admm_update_var",
     "lb2_read_sdpa", "lb2_sdpa_info", "lb2_sdpa_get", "lb2_sdpa_free", "lb2_sdpa_last_error",
 ]
 
@@ -74,6 +75,11 @@ def load_library():
     lib.lb2_default_params.argtypes = [C.POINTER(Params)]
     lib.lb2_create.argtypes = [C.POINTER(C.c_void_p), C.c_int64, C.c_int64, _ip, _dp, C.c_int]
     lib.lb2_set_cone_data.argtypes = [C.c_void_p, C.c_int64, _ip, _ip, _dp]
+    lib.lb2_set_lp_data.argtypes = [C.c_void_p, C.c_int64, _ip, _ip, _dp]
+    lib.lb2_get_lp_vec.argtypes = [C.c_void_p, C.c_char, _dp]
+    lib.lb2_set_lp_vec.argtypes = [C.c_void_p, C.c_char, _dp]
+    lib.lb2_admm_init_constr.argtypes = [C.c_void_p]
+    lib.lb2_admm_update_var.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int64]
     lib.lb2_preprocess.argtypes = [C.c_void_p]
     lib.lb2_determine_rank.argtypes = [C.c_void_p, C.c_double]
     lib.lb2_init_vars.argtypes = [C.c_void_p, C.c_int64, C.c_double]
@@ -168,8 +174,6 @@ def read_sdpa(path: str) -> Instance:
     if lib.lb2_read_sdpa(path.encode(), C.byref(h)) != 0:
         raise Lb2Error(lib.lb2_sdpa_last_error().decode())
     try:
-        if lib.lb2_sdpa_info(h, 4, 0) > 0:
-            raise ValueError("LP / diagonal blocks are out of scope for the device data layer")
         m = int(lib.lb2_sdpa_info(h, 0, 0))
         nblk = int(lib.lb2_sdpa_info(h, 1, 0))
         b = np.zeros(m)
@@ -180,7 +184,15 @@ def read_sdpa(path: str) -> Instance:
             beg, idx, elem = np.zeros(m + 2, np.int64), np.zeros(nnz, np.int64), np.zeros(nnz)
             lib.lb2_sdpa_get(h, k, _i(beg), _i(idx), _d(elem), None)
             cones.append(Cone(n=n, beg=beg, idx=idx, elem=elem))
-        return Instance(m=m, b=b, cones=cones, name=path)
+        lp = None
+        n_lp = int(lib.lb2_sdpa_info(h, 4, 0))
+        if n_lp > 0:
+            from .sdpa import LpBlock
+            nnz = int(lib.lb2_sdpa_info(h, 3, nblk))
+            beg, idx, elem = np.zeros(m + 2, np.int64), np.zeros(nnz, np.int64), np.zeros(nnz)
+            lib.lb2_sdpa_get(h, nblk, _i(beg), _i(idx), _d(elem), None)
+            lp = LpBlock(n=n_lp, beg=beg, idx=idx, elem=elem)
+        return Instance(m=m, b=b, cones=cones, name=path, lp=lp)
     finally:
         lib.lb2_sdpa_free(h)
 
@@ -216,6 +228,13 @@ class Solver:
             idx = np.ascontiguousarray(cone.idx, dtype=np.int64)
             elem = np.ascontiguousarray(cone.elem, dtype=np.float64)
             self._ck(self.lib.lb2_set_cone_data(self.h, k, _i(beg), _i(idx), _d(elem)))
+        self.n_lp = 0
+        if getattr(inst, "lp", None) is not None:
+            lp = inst.lp
+            self.n_lp = int(lp.n)
+            self._ck(self.lib.lb2_set_lp_data(self.h, lp.n, _i(np.ascontiguousarray(lp.beg, dtype=np.int64)),
+                                              _i(np.ascontiguousarray(lp.idx, dtype=np.int64)),
+                                              _d(np.ascontiguousarray(lp.elem, dtype=np.float64))))
         self._ck(self.lib.lb2_preprocess(self.h))
         self._ck(self.lib.lb2_determine_rank(self.h, float(times_log_rank)))
         if comm is not None:
@@ -285,6 +304,17 @@ class Solver:
         self._ck(self.lib.lb2_get_vec(self.h, which.encode(), _d(v)))
         return v
 
+    def get_lp(self, which: str) -> np.ndarray:
+        """LP vectors: 'R' rLp, 'U' uLp, 'V' vLp, 'G' gradLp, 'x' product held in constrValLP, 'c' objective."""
+        v = np.zeros(self.n_lp)
+        self._ck(self.lib.lb2_get_lp_vec(self.h, which.encode(), _d(v)))
+        return v
+
+    def set_lp(self, which: str, v: np.ndarray):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        assert v.shape == (self.n_lp,)
+        self._ck(self.lib.lb2_set_lp_vec(self.h, which.encode(), _d(v)))
+
     # ---- hot-path operators (names follow oracle/ref.py, i.e. the reference functions)
     def auv(self, u: str, v: str, cone=0, with_obj=False):
         out = np.zeros(self.m)
@@ -316,6 +346,12 @@ class Solver:
         it = C.c_int64(0)
         self._ck(self.lib.lb2_update_sdp_var_one(self.h, cone, upd.encode(), noupd.encode(), rho, tol, maxit, C.byref(it)))
         return it.value
+
+    def admm_init_constr(self):
+        self._ck(self.lib.lb2_admm_init_constr(self.h))
+
+    def admm_update_var(self, rho: float, tol: float, maxit: int):
+        self._ck(self.lib.lb2_admm_update_var(self.h, rho, tol, maxit))
 
     def alm_prepare(self, rho: float) -> float:
         lag = C.c_double(0.0)

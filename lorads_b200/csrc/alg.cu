@@ -79,6 +79,9 @@ bool Solver::aug_rank(double aug) {
         get_factor('R', c, hR[c].data()); get_factor('U', c, hU[c].data()); get_factor('V', c, hV[c].data());
         get_factor('G', c, hG[c].data()); get_factor('M', c, hM[c].data());
     }
+    // the LP vectors are separate arrays in the reference and survive AUG_RANK untouched
+    std::vector<double> lpR((size_t)nLp), lpU((size_t)nLp), lpV((size_t)nLp), lpG((size_t)nLp);
+    get_lp_vec('R', lpR.data()); get_lp_vec('U', lpU.data()); get_lp_vec('V', lpV.data()); get_lp_vec('G', lpG.data());
     for (long long c = 0; c < nCones; ++c) {
         const long long nr = (long long)std::min<double>(std::ceil((double)rank[c] * aug), (double)rank_max[c]);
         rank[c] = nr;
@@ -101,6 +104,7 @@ bool Solver::aug_rank(double aug) {
         set_factor('U', c, hU[c].data()); set_factor('V', c, hV[c].data()); set_factor('R', c, hR[c].data());
         set_factor('G', c, hG[c].data()); set_factor('M', c, hM[c].data());
     }
+    set_lp_vec('R', lpR.data()); set_lp_vec('U', lpU.data()); set_lp_vec('V', lpV.data()); set_lp_vec('G', lpG.data());
     return check_all_rank_max(aug);
 }
 
@@ -114,6 +118,7 @@ void Solver::obj_scale_dualvar(double f) {
         if (nobj > 0) launch_scale(ctx, K.listAC.coef.p + K.obj_item_begin, nobj, f);
         K.c_rank1 *= f;
     }
+    if (nLp > 0) launch_scale(ctx, lp_c.p, nLp, f);      // lp_cone_scalObj, lorads_lp_conic.c:197-202
     launch_scale(ctx, lam.p, m, f);
 }
 
@@ -303,8 +308,8 @@ after_loops:
 
 void Solver::alm_to_admm(lb2_params *P) {
     // LORADS_ALMtoADMM, lorads_solver.c:968-1004: U = V = R, state hand-off, rho heuristic
-    LB2_CUDA(cudaMemcpyAsync(V.p, R.p, sizeof(double) * N, cudaMemcpyDeviceToDevice, ctx.stream));
-    LB2_CUDA(cudaMemcpyAsync(U.p, R.p, sizeof(double) * N, cudaMemcpyDeviceToDevice, ctx.stream));
+    LB2_CUDA(cudaMemcpyAsync(V.p, R.p, sizeof(double) * Nt, cudaMemcpyDeviceToDevice, ctx.stream));
+    LB2_CUDA(cudaMemcpyAsync(U.p, R.p, sizeof(double) * Nt, cudaMemcpyDeviceToDevice, ctx.stream));
     admm.dinf_1 = alm.dinf_1; admm.pinf_1 = alm.pinf_1; admm.dinf_2 = alm.dinf_2; admm.dinf_inf = alm.dinf_inf;
     admm.pinf_inf = alm.pinf_inf; admm.pinf_2 = alm.pinf_2; admm.gap = alm.gap;
     admm.rho = alm.rho * P->heuristicFactor;
@@ -484,6 +489,12 @@ void Solver::dual_infeasibility() {
     // the host reads two scalars (alpha, |w|^2) and solves the small tridiagonal eigenproblem per restart cycle.
     launch_axpby_dot(ctx, m, M1.p, coef_const(-1.0), lam.p, coef_const(0.0), nullptr, nullptr, S.p, SL_T1, false);
     double total = 0.0;
+    if (nLp > 0) {
+        // LP columns first (lorads_solver.c:1015-1023): sum_j |min(c_j - a_j^T lambda, 0)|
+        launch_lp_dinf(ctx, lp, M1.p, S.p, SL_T0);
+        read_slots();
+        total += S_host[SL_T0];
+    }
     for (long long c = 0; c < nCones; ++c) {
         ConeDev &K = cones[c];
         cone_wsum(K, M1.p, false, true);
@@ -618,7 +629,7 @@ int Solver::solve(lb2_params *P, lb2_result *res) {
                 if (P->verbose) printf("******  reopt parameter:%.3f\n", reopt_param);
                 reopt(P, &reopt_param, &reopt_alm_iter, &reopt_admm_iter, t0, &admm_bad_iter_flag, 2);
                 average_uv();                                                        // main.c:441-443
-                LB2_CUDA(cudaMemcpyAsync(V.p, R.p, sizeof(double) * N, cudaMemcpyDeviceToDevice, ctx.stream));   // copyRtoV
+                LB2_CUDA(cudaMemcpyAsync(V.p, R.p, sizeof(double) * Nt, cudaMemcpyDeviceToDevice, ctx.stream));   // copyRtoV / copyRtoVLP
                 dual_infeasibility();
                 refresh();
                 dual_cnt += 1;

@@ -116,9 +116,30 @@ int lb2_comm_unique_id(void *id128) {
     return g_nccl.get_uid((nccl_uid *)id128) == 0 ? LB2_OK : LB2_ERR_CUDA;
 }
 
+int lb2_set_lp_data(lb2_solver *s, lb2_int nLpCols, const lb2_int *beg, const lb2_int *idx, const double *elem) {
+    if (!s || (nLpCols > 0 && (!beg || !idx || !elem))) { g_err = "null argument"; return LB2_ERR_ARG; }
+    LB2_TRY s->impl.set_lp(nLpCols, beg, idx, elem); LB2_CATCH
+}
+int lb2_get_lp_vec(lb2_solver *s, char which, double *out) {
+    if (!s || !out) return LB2_ERR_ARG;
+    LB2_TRY
+    if (!s->impl.vars_ready) throw std::logic_error("call lb2_init_vars first");
+    s->impl.get_lp_vec(which, out);
+    LB2_CATCH
+}
+int lb2_set_lp_vec(lb2_solver *s, char which, const double *in) {
+    if (!s || !in) return LB2_ERR_ARG;
+    LB2_TRY
+    if (!s->impl.vars_ready) throw std::logic_error("call lb2_init_vars first");
+    if (which == 'c') throw std::invalid_argument("the LP objective is read-only");
+    s->impl.set_lp_vec(which, in);
+    LB2_CATCH
+}
+
 int lb2_comm_init(lb2_solver *s, const void *id128, int rank, int world) {
     if (!s || world < 1 || rank < 0 || rank >= world) { g_err = "lb2_comm_init: bad argument"; return LB2_ERR_ARG; }
     if (world == 1) return LB2_OK;
+    if (s->impl.nLp > 0) { g_err = "column sharding with an LP block is not supported"; return LB2_ERR_UNSUPPORTED; }
     if (!g_nccl.load()) { g_err = "NCCL library not found"; return LB2_ERR_UNSUPPORTED; }
     LB2_TRY
     LB2_CUDA(cudaSetDevice(s->impl.device));
@@ -187,6 +208,7 @@ lb2_int lb2_info(const lb2_solver *s, int what, lb2_int c) {
     case 16: return K.listA.dev.n_items;
     case 17: return K.ld;
     case 18: return S.N;
+    case 19: return S.nLp;
     }
     return -1;
 }
@@ -280,6 +302,25 @@ int lb2_cg_matvec(lb2_solver *s, lb2_int c, char noUpdate, const double *x, doub
     LB2_CATCH
 }
 
+int lb2_admm_init_constr(lb2_solver *s) {
+    if (!s) return LB2_ERR_ARG;
+    LB2_TRY
+    Solver &S = s->impl;
+    if (!S.vars_ready) throw std::logic_error("call lb2_init_vars first");
+    S.init_constr_val_all(S.U.p, S.V.p, false);
+    S.constr_val_sum();
+    S.sync();
+    LB2_CATCH
+}
+int lb2_admm_update_var(lb2_solver *s, double rho, double cgTol, lb2_int cgMaxIter) {
+    if (!s) return LB2_ERR_ARG;
+    LB2_TRY
+    Solver &S = s->impl;
+    if (!S.vars_ready) throw std::logic_error("call lb2_init_vars first");
+    S.update_sdp_var(rho, cgTol, cgMaxIter);
+    S.sync();
+    LB2_CATCH
+}
 int lb2_update_sdp_var_one(lb2_solver *s, lb2_int c, char upd, char noupd, double rho, double tol, lb2_int maxit, lb2_int *iters) {
     if (!s) return LB2_ERR_ARG;
     LB2_TRY
@@ -420,7 +461,7 @@ int lb2_copy_r_to_v(lb2_solver *s) {
     if (!s) return LB2_ERR_ARG;
     LB2_TRY
     Solver &S = s->impl;
-    LB2_CUDA(cudaMemcpyAsync(S.V.p, S.R.p, sizeof(double) * S.N, cudaMemcpyDeviceToDevice, S.ctx.stream));
+    LB2_CUDA(cudaMemcpyAsync(S.V.p, S.R.p, sizeof(double) * S.Nt, cudaMemcpyDeviceToDevice, S.ctx.stream));
     S.sync();
     LB2_CATCH
 }

@@ -1288,4 +1288,153 @@ void launch_scale(Ctx &c, double *x, long long n, double f) {
     LB2_LAUNCH_CHECK(c);
 }
 
+// =================================================================================================
+// LP cone
+// =================================================================================================
+__global__ void __launch_bounds__(kBlock) lp_prod_kernel(long long n, const double *__restrict__ u, const double *__restrict__ v,
+                                                         double *__restrict__ x) {
+    for (long long j = blockIdx.x * (long long)kBlock + threadIdx.x; j < n; j += (long long)gridDim.x * kBlock) x[j] = u[j] * v[j];
+}
+
+void launch_lp_prod(Ctx &c, long long n, const double *u, const double *v, double *x) {
+    lp_prod_kernel<<<grid_for(n, 1, c), kBlock, 0, c.stream>>>(n, u, v, x);
+    LB2_LAUNCH_CHECK(c);
+}
+
+// one warp per constraint row; lanes stride the row's LP entries, fixed shuffle tree -> deterministic
+__global__ void __launch_bounds__(kBlock) lp_rows_kernel(LpDev L, const double *__restrict__ u, const double *__restrict__ v,
+                                                         double s1, double *__restrict__ out1, double s2,
+                                                         double *__restrict__ out2) {
+    const int lane = threadIdx.x & 31;
+    const long long w0 = (blockIdx.x * (long long)kBlock + threadIdx.x) >> 5, nw = ((long long)gridDim.x * kBlock) >> 5;
+    for (long long i = w0; i < L.m; i += nw) {
+        const int a = L.rbeg[i], b = L.rbeg[i + 1];
+        if (a == b) continue;                       // warp-uniform
+        double t1 = 0.0, t2 = 0.0;
+        for (int k = a + lane; k < b; k += 32) {
+            const int j = L.rcol[k];
+            const double av = L.rval[k], vj = v ? v[j] : 1.0;
+            t1 = fma(av, u[j] * vj, t1);
+            if (out2) t2 = fma(av, vj * vj, t2);
+        }
+        t1 = warp_sum(t1);
+        if (out2) t2 = warp_sum(t2);
+        if (lane == 0) {
+            out1[i] += s1 * t1;
+            if (out2) out2[i] += s2 * t2;
+        }
+    }
+}
+
+void launch_lp_rows(Ctx &c, const LpDev &L, const double *u, const double *v, double s1, double *out1, double s2, double *out2) {
+    lp_rows_kernel<<<grid_for(L.m * 32, 1, c), kBlock, 0, c.stream>>>(L, u, v, s1, out1, s2, out2);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) lp_obj_kernel(LpDev L, const double *__restrict__ u, const double *__restrict__ v, double s1,
+                                                        double *obj1, double s2, double *obj2, ReduceScratch rs) {
+    double t[2] = {0.0, 0.0};
+    for (long long j = blockIdx.x * (long long)kBlock + threadIdx.x; j < L.n; j += (long long)gridDim.x * kBlock) {
+        const double cj = L.c[j], vj = v[j];
+        t[0] = fma(cj, u[j] * vj, t[0]);
+        t[1] = fma(cj, vj * vj, t[1]);
+    }
+    if (grid_reduce<2>(t, rs) && threadIdx.x == 0) {
+        if (obj1) *obj1 += s1 * t[0];
+        if (obj2) *obj2 += s2 * t[1];
+    }
+}
+
+void launch_lp_obj(Ctx &c, const LpDev &L, const double *u, const double *v, double s1, double *obj1, double s2, double *obj2) {
+    lp_obj_kernel<<<grid_for(L.n, 4, c), kBlock, 0, c.stream>>>(L, u, v, s1, obj1, s2, obj2, c.rs);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) lp_grad_kernel(LpDev L, const double *__restrict__ w, const double *__restrict__ r,
+                                                         double *__restrict__ g, double *red, ReduceScratch rs) {
+    double t[1] = {0.0};
+    for (long long j = blockIdx.x * (long long)kBlock + threadIdx.x; j < L.n; j += (long long)gridDim.x * kBlock) {
+        double sum = L.c[j];
+        for (int k = L.cbeg[j]; k < L.cbeg[j + 1]; ++k) sum += L.cval[k] * w[L.crow[k]];   // same order as LPdataMatSparseWeightSum
+        const double gj = 2 * sum * r[j];
+        g[j] = gj;
+        t[0] = fma(gj, gj, t[0]);
+    }
+    if (grid_reduce<1>(t, rs) && threadIdx.x == 0 && red) red[0] = t[0];
+}
+
+void launch_lp_grad(Ctx &c, const LpDev &L, const double *w, const double *r, double *g, double *red) {
+    lp_grad_kernel<<<grid_for(L.n, 1, c), kBlock, 0, c.stream>>>(L, w, r, g, red, c.rs);
+    LB2_LAUNCH_CHECK(c);
+}
+
+// The reference walks the columns one after the other and each column reads constrValSum as left by its
+// predecessors.  Columns that share no constraint row commute exactly, so the columns are grouped into levels
+// (level(j) = 1 + max level of an earlier column sharing a row with j, built on the host); one CTA runs the
+// levels in order, one warp per column inside a level.  Every column sees exactly the values it would see in
+// the sequential sweep.
+__device__ __forceinline__ void lp_update_one(const LpDev &L, int j, int lane, double rho, const double *b, const double *lam,
+                                              double *cvs, double *x, double *upd, const double *noupd) {
+    const int a = L.cbeg[j], e = L.cbeg[j + 1];
+    const double xo = x[j], nu = noupd[j];
+    double t = 0.0;
+    for (int k = a + lane; k < e; k += 32) {
+        const int i = L.crow[k];
+        const double av = L.cval[k];
+        const double m1 = ((cvs[i] - b[i]) - av * xo) * rho - lam[i];     // lorads_admm.c:603-616
+        t = fma(av, m1, t);
+    }
+    t = warp_sum(t);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    const double wsum = L.c[j] + t;
+    double M2 = wsum * nu;
+    M2 = M2 - rho * nu;
+    const double blin = -1.0 * M2 / rho;
+    const double un = blin / (1 + L.nrm2sq[j] * nu * nu);                 // lorads_admm.c:622-627
+    const double xn = (upd == noupd) ? un * un : un * nu;
+    for (int k = a + lane; k < e; k += 32) {
+        const int i = L.crow[k];
+        const double av = L.cval[k];
+        cvs[i] = (cvs[i] - av * xo) + av * xn;                            // lorads_alg_common.c:235-237
+    }
+    __syncwarp();
+    if (lane == 0) { upd[j] = un; x[j] = xn; }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kBlock) lp_sweep_kernel(LpDev L, double rho, const double *__restrict__ b,
+                                                          const double *__restrict__ lam, double *cvs, double *x, double *u,
+                                                          double *v) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int lv = 0; lv < L.n_lvl; ++lv) {
+        for (int q = L.lvl_ptr[lv] + w; q < L.lvl_ptr[lv + 1]; q += kBlock / 32) {
+            const int j = L.lvl_col[q];
+            lp_update_one(L, j, lane, rho, b, lam, cvs, x, u, v);
+            lp_update_one(L, j, lane, rho, b, lam, cvs, x, v, u);
+        }
+        __syncthreads();
+    }
+}
+
+void launch_lp_sweep(Ctx &c, const LpDev &L, double rho, const double *b, const double *lam, double *cvs, double *x,
+                     double *u, double *v) {
+    lp_sweep_kernel<<<1, kBlock, 0, c.stream>>>(L, rho, b, lam, cvs, x, u, v);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) lp_dinf_kernel(LpDev L, const double *__restrict__ w, double *S, int slot, ReduceScratch rs) {
+    double t[1] = {0.0};
+    for (long long j = blockIdx.x * (long long)kBlock + threadIdx.x; j < L.n; j += (long long)gridDim.x * kBlock) {
+        double sum = L.c[j];
+        for (int k = L.cbeg[j]; k < L.cbeg[j + 1]; ++k) sum += L.cval[k] * w[L.crow[k]];
+        t[0] += fabs(fmin(sum, 0.0));
+    }
+    if (grid_reduce<1>(t, rs) && threadIdx.x == 0) S[slot] = t[0];
+}
+
+void launch_lp_dinf(Ctx &c, const LpDev &L, const double *w, double *S, int slot) {
+    lp_dinf_kernel<<<grid_for(L.n, 1, c), kBlock, 0, c.stream>>>(L, w, S, slot, c.rs);
+    LB2_LAUNCH_CHECK(c);
+}
+
 }  // namespace lb2

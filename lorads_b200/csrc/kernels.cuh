@@ -154,6 +154,39 @@ void launch_dual_update(Ctx &c, long long m, double rho, const double *b, const 
 // constraint vector expanded to length m (may be null)
 void launch_admm_m1(Ctx &c, long long m, const double *b, const double *s, const double *cv, const double *lam,
                     double rho, double *M1);
+// ------------------------------------------------------------------------------------------------
+// LP cone (diagonal block of the SDPA file): x_j = u_j * v_j, columns a_j of the m x nLp constraint matrix
+// (reference: data/lorads_lp_conic.c, lorads_lp_data.c and the *LP function set, lorads_solver.c:717-735)
+// ------------------------------------------------------------------------------------------------
+struct LpDev {
+    long long n = 0, m = 0;                   // LP columns, constraints
+    const double *c = nullptr;                // objective coefficients (scaled with the objective)
+    const int *rbeg = nullptr, *rcol = nullptr;   // by constraint row (CSR)
+    const double *rval = nullptr;
+    const int *cbeg = nullptr, *crow = nullptr;   // by LP column (CSC), rows ascending inside a column
+    const double *cval = nullptr;
+    const double *nrm2sq = nullptr;           // |a_j|^2
+    const int *lvl_ptr = nullptr, *lvl_col = nullptr;   // level schedule of the Gauss-Seidel sweep
+    int n_lvl = 0;
+};
+// x[j] = u[j] * v[j]
+void launch_lp_prod(Ctx &c, long long n, const double *u, const double *v, double *x);
+// out1[i] += s1 * sum_j a_ij u_j v_j ; if out2: out2[i] += s2 * sum_j a_ij v_j v_j   (v == nullptr: factor 1)
+// (lp_cone_AUV lorads_lp_conic.c:164-167 for every column + the add into constrValSum / q1 / q2,
+//  lorads_alg_common.c:144-158, lorads_alm.c:525-537)
+void launch_lp_rows(Ctx &c, const LpDev &L, const double *u, const double *v, double s1, double *out1, double s2, double *out2);
+// *obj1 += s1 * sum c_j u_j v_j ; if obj2: *obj2 += s2 * sum c_j v_j v_j   (lp_cone_objAUV lorads_lp_conic.c:186-195)
+void launch_lp_obj(Ctx &c, const LpDev &L, const double *u, const double *v, double s1, double *obj1, double s2, double *obj2);
+// g_j = 2 (c_j + a_j^T w) r_j ; red[0] = sum g_j^2   (ALMSetGradLP / ALMCalGradLP, lorads_alm.c:56-99)
+void launch_lp_grad(Ctx &c, const LpDev &L, const double *w, const double *r, double *g, double *red);
+// One Gauss-Seidel sweep over the LP columns, u_j then v_j, with constrValSum kept current
+// (LORADSUpdateSDPLPVar + LORADSUpdateLPVarOne, lorads_alg_common.c:225-249, lorads_admm.c:595-628);
+// x[j] is the product currently represented in constrValSum for column j (constrValLP[j] = a_j x[j]).
+void launch_lp_sweep(Ctx &c, const LpDev &L, double rho, const double *b, const double *lam, double *cvs, double *x,
+                     double *u, double *v);
+// S[slot] = sum_j |min(c_j + a_j^T w, 0)|   (calculate_dual_infeasibility_solver, lorads_solver.c:1015-1023; w = -lambda)
+void launch_lp_dinf(Ctx &c, const LpDev &L, const double *w, double *S, int slot);
+
 void launch_recip(Ctx &c, double *S, int slot);   // S[slot] = 1/S[slot]
 void launch_scale(Ctx &c, double *x, long long n, double f);   // x *= f
 

@@ -62,8 +62,8 @@ int main(int argc, char **argv) {
     lb2_sdpa *F = nullptr;
     if (lb2_read_sdpa(fname, &F) != LB2_OK) { std::fprintf(stderr, "cannot read %s: %s\n", fname, lb2_sdpa_last_error()); return 2; }
     const lb2_int m = lb2_sdpa_info(F, 0, 0), nblk = lb2_sdpa_info(F, 1, 0);
-    if (lb2_sdpa_info(F, 4, 0) > 0) { std::fprintf(stderr, "LP blocks are not supported by the device layer yet\n"); return 2; }
-    std::printf("nConstrs = %lld, sdp nBlks = %lld, lp Cols = 0\n", (long long)m, (long long)nblk);
+    const lb2_int nlp = lb2_sdpa_info(F, 4, 0);
+    std::printf("nConstrs = %lld, sdp nBlks = %lld, lp Cols = %lld\n", (long long)m, (long long)nblk, (long long)nlp);
     std::vector<lb2_int> dims((size_t)nblk);
     for (lb2_int k = 0; k < nblk; ++k) dims[(size_t)k] = lb2_sdpa_info(F, 2, k);
     std::vector<double> rhs((size_t)m);
@@ -76,6 +76,13 @@ int main(int argc, char **argv) {
         std::vector<double> el((size_t)nnz + 1);
         lb2_sdpa_get(F, k, beg.data(), ix.data(), el.data(), nullptr);
         if (lb2_set_cone_data(S, k, beg.data(), ix.data(), el.data()) != LB2_OK) fail("lb2_set_cone_data");
+    }
+    if (nlp > 0) {
+        const lb2_int nnz = lb2_sdpa_info(F, 3, nblk);
+        std::vector<lb2_int> beg((size_t)m + 2), ix((size_t)nnz + 1);
+        std::vector<double> el((size_t)nnz + 1);
+        lb2_sdpa_get(F, nblk, beg.data(), ix.data(), el.data(), nullptr);
+        if (lb2_set_lp_data(S, nlp, beg.data(), ix.data(), el.data()) != LB2_OK) fail("lb2_set_lp_data");
     }
     lb2_sdpa_free(F);
     if (lb2_preprocess(S) != LB2_OK) fail("lb2_preprocess");

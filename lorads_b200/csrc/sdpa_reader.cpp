@@ -171,6 +171,7 @@ lb2_int lb2_sdpa_info(const lb2_sdpa *s, int what, lb2_int k) {
     case 4: return s->nLpCols;
     case 5: return s->nElems;
     }
+    if (what == 3 && k == (lb2_int)s->dims.size() && s->nLpCols > 0) return (lb2_int)s->lp.idx.size();   // the LP block
     if (k < 0 || k >= (lb2_int)s->dims.size()) return -1;
     if (what == 2) return s->dims[(size_t)k];
     if (what == 3) return (lb2_int)s->blocks[(size_t)k].idx.size();
@@ -181,8 +182,9 @@ int lb2_sdpa_get(const lb2_sdpa *s, lb2_int k, lb2_int *beg, lb2_int *idx, doubl
     if (!s) return LB2_ERR_ARG;
     if (rhs) std::memcpy(rhs, s->rhs.data(), sizeof(double) * s->rhs.size());
     if (k < 0) return LB2_OK;
-    if (k >= (lb2_int)s->dims.size()) return LB2_ERR_ARG;
-    const lb2_sdpa::Block &B = s->blocks[(size_t)k];
+    const bool want_lp = (k == (lb2_int)s->dims.size() && s->nLpCols > 0);
+    if (k >= (lb2_int)s->dims.size() && !want_lp) return LB2_ERR_ARG;
+    const lb2_sdpa::Block &B = want_lp ? s->lp : s->blocks[(size_t)k];
     if (beg) std::memcpy(beg, B.beg.data(), sizeof(lb2_int) * B.beg.size());
     if (idx) std::memcpy(idx, B.idx.data(), sizeof(lb2_int) * B.idx.size());
     if (elem) std::memcpy(elem, B.elem.data(), sizeof(double) * B.elem.size());

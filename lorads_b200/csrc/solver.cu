@@ -74,14 +74,14 @@ void Solver::create(long long nRows, long long nC, const lb2_int *dims, const do
     ctx.rs.partials = red_partials.p;
     ctx.rs.counter = red_counter.p;
     ctx.ticket = red_counter.p + 1;
-    S.alloc(kNumSlots + 2 * nC);
-    LB2_CUDA(cudaMallocHost((void **)&S_host, sizeof(double) * (kNumSlots + 2 * nC)));
-    std::memset(S_host, 0, sizeof(double) * (kNumSlots + 2 * nC));
+    S.alloc(kNumSlots + 2 * (nC + 1));
+    LB2_CUDA(cudaMallocHost((void **)&S_host, sizeof(double) * (kNumSlots + 2 * (nC + 1))));
+    std::memset(S_host, 0, sizeof(double) * (kNumSlots + 2 * (nC + 1)));
     S_host[SL_ONE] = 1.0;
     LB2_CUDA(cudaMallocHost((void **)&push_host, sizeof(double) * 4));
     use_graphs = (getenv("LORADS_B200_NO_GRAPH") == nullptr);
     vf_lbfgs = (getenv("LORADS_B200_VF_LBFGS") != nullptr);
-    LB2_CUDA(cudaMemcpy(S.p, S_host, sizeof(double) * (kNumSlots + 2 * nC), cudaMemcpyHostToDevice));
+    LB2_CUDA(cudaMemcpy(S.p, S_host, sizeof(double) * (kNumSlots + 2 * (nC + 1)), cudaMemcpyHostToDevice));
 }
 
 void Solver::set_cone(long long i, const lb2_int *beg, const lb2_int *idx, const double *elem) {
@@ -91,6 +91,88 @@ void Solver::set_cone(long long i, const lb2_int *beg, const lb2_int *idx, const
     in.idx.assign(idx, idx + beg[m + 1]);
     in.elem.assign(elem, elem + beg[m + 1]);
     in.set = true;
+}
+
+void Solver::set_lp(long long nLpCols, const lb2_int *beg, const lb2_int *idx, const double *elem) {
+    if (preprocessed) throw std::logic_error("set the LP block before lb2_preprocess");
+    if (nLpCols < 0) throw std::invalid_argument("negative number of LP columns");
+    nLp = nLpCols;
+    lp_input = ConeInput();
+    if (nLp == 0) return;
+    lp_input.beg.assign(beg, beg + m + 2);
+    lp_input.idx.assign(idx, idx + beg[m + 1]);
+    lp_input.elem.assign(elem, elem + beg[m + 1]);
+    lp_input.set = true;
+}
+
+void Solver::build_lp() {
+    // lp_cone_proc + lp_cone_presolve, lorads_lp_conic.c:14-113.  Input: CSC by constraint (column 0 = objective,
+    // column i+1 = constraint i), entries (LP column, value).  Output: objective vector, the constraint matrix by
+    // constraint (CSR) and by LP column (CSC, rows ascending as the reference builds them), |a_j|^2.
+    // Deviation (DESIGN.md "reference quirks"): the reference's dense column type (nnz >= m/4) reads an
+    // uninitialised row count and ends up as an all-zero column; here every column keeps its entries.
+    if (!lp_input.set) throw std::logic_error("LP data missing");
+    const std::vector<int64_t> &beg = lp_input.beg, &idx = lp_input.idx;
+    const std::vector<double> &val = lp_input.elem;
+    lp_c_h.assign((size_t)nLp, 0.0);
+    for (int64_t k = beg[0]; k < beg[1]; ++k) {
+        if (idx[k] < 0 || idx[k] >= nLp) throw std::invalid_argument("LP column index out of range");
+        lp_c_h[(size_t)idx[k]] = val[k];
+    }
+    const int64_t nnz = beg[m + 1] - beg[1];
+    if (nnz > 0x7fffffffLL) throw std::invalid_argument("LP block too large");
+    std::vector<int> rbeg((size_t)m + 1), rcol((size_t)nnz), cbeg((size_t)nLp + 1, 0), crow((size_t)nnz);
+    std::vector<double> rval((size_t)nnz), cval((size_t)nnz), n2((size_t)nLp, 0.0);
+    for (long long i = 0; i <= m; ++i) rbeg[(size_t)i] = (int)(beg[(size_t)i + 1] - beg[1]);
+    for (int64_t k = 0; k < nnz; ++k) {
+        const int64_t j = idx[(size_t)(beg[1] + k)];
+        if (j < 0 || j >= nLp) throw std::invalid_argument("LP column index out of range");
+        rcol[(size_t)k] = (int)j; rval[(size_t)k] = val[(size_t)(beg[1] + k)];
+        cbeg[(size_t)j + 1]++;
+    }
+    for (long long j = 0; j < nLp; ++j) cbeg[(size_t)j + 1] += cbeg[(size_t)j];
+    {
+        std::vector<int> cur(cbeg.begin(), cbeg.end() - 1);
+        for (long long i = 0; i < m; ++i)
+            for (int k = rbeg[(size_t)i]; k < rbeg[(size_t)i + 1]; ++k) {
+                const int q = cur[(size_t)rcol[(size_t)k]]++;
+                crow[(size_t)q] = (int)i; cval[(size_t)q] = rval[(size_t)k];
+            }
+    }
+    for (long long j = 0; j < nLp; ++j) {
+        // nrm2 then squared, as lp_cone_presolve does (lorads_lp_conic.c:97-98)
+        double ss = 0.0;
+        for (int k = cbeg[(size_t)j]; k < cbeg[(size_t)j + 1]; ++k) ss += cval[(size_t)k] * cval[(size_t)k];
+        const double nr = std::sqrt(ss);
+        n2[(size_t)j] = nr * nr;
+        if (cbeg[(size_t)j] == cbeg[(size_t)j + 1])
+            printf("File [%30s] Line [%d]\n", "lorads_b200 lp column without entries", (int)j);   // LP_COEFF_ZERO trace
+    }
+    // level schedule of the Gauss-Seidel sweep: a column waits for every earlier column that shares a row with it
+    std::vector<int> row_level((size_t)m, 0), level((size_t)nLp, 0);
+    int n_lvl = 0;
+    for (long long j = 0; j < nLp; ++j) {
+        int lv = 0;
+        for (int k = cbeg[(size_t)j]; k < cbeg[(size_t)j + 1]; ++k) lv = std::max(lv, row_level[(size_t)crow[(size_t)k]]);
+        level[(size_t)j] = lv;
+        for (int k = cbeg[(size_t)j]; k < cbeg[(size_t)j + 1]; ++k) row_level[(size_t)crow[(size_t)k]] = lv + 1;
+        n_lvl = std::max(n_lvl, lv + 1);
+    }
+    std::vector<int> lptr((size_t)n_lvl + 1, 0), lcol((size_t)nLp);
+    for (long long j = 0; j < nLp; ++j) lptr[(size_t)level[(size_t)j] + 1]++;
+    for (int l = 0; l < n_lvl; ++l) lptr[(size_t)l + 1] += lptr[(size_t)l];
+    {
+        std::vector<int> cur(lptr.begin(), lptr.end() - 1);
+        for (long long j = 0; j < nLp; ++j) lcol[(size_t)cur[(size_t)level[(size_t)j]]++] = (int)j;
+    }
+    lp_c.upload(lp_c_h); lp_rbeg.upload(rbeg); lp_rcol.upload(rcol); lp_rval.upload(rval);
+    lp_cbeg.upload(cbeg); lp_crow.upload(crow); lp_cval.upload(cval); lp_nrm2sq.upload(n2);
+    lp_lvl_ptr.upload(lptr); lp_lvl_col.upload(lcol);
+    lp_x.alloc((size_t)nLp);
+    lp.n = nLp; lp.m = m; lp.c = lp_c.p; lp.rbeg = lp_rbeg.p; lp.rcol = lp_rcol.p; lp.rval = lp_rval.p;
+    lp.cbeg = lp_cbeg.p; lp.crow = lp_crow.p; lp.cval = lp_cval.p; lp.nrm2sq = lp_nrm2sq.p;
+    lp.lvl_ptr = lp_lvl_ptr.p; lp.lvl_col = lp_lvl_col.p; lp.n_lvl = n_lvl;
+    lp_input = ConeInput();
 }
 
 void Solver::preprocess() {
@@ -132,6 +214,20 @@ void Solver::preprocess() {
         K.cv.alloc((size_t)K.n_act + 1); K.t1.alloc((size_t)K.n_act + 1); K.t2.alloc((size_t)K.n_act + 1);
         cObjNrm1 += K.cNrm1; n2 += K.cNrm2Sq; cObjNrmInf = std::max(cObjNrmInf, K.cNrmInf);
         inputs[c] = ConeInput();   // the reader arrays are no longer needed
+    }
+    if (nLp > 0) {
+        build_lp();
+        // LORADSNrm1Obj / Nrm2Obj / NrmInfObj, lorads_solver.c:149-183, lorads_alg_common.c:300-316: the LP block
+        // contributes |c|_1 to the 1-norm, |c|_1^2 (sic, lp_cone_obj_nrm2Square) to the squared 2-norm and, in the
+        // -DUNDER_BLAS build, the entry after the first largest one (1-based idamax_ used 0-based) to the inf-norm
+        double l1 = 0.0, best = -1.0;
+        long long arg = 0;
+        for (long long j = 0; j < nLp; ++j) {
+            l1 += std::fabs(lp_c_h[(size_t)j]);
+            if (std::fabs(lp_c_h[(size_t)j]) > best) { best = std::fabs(lp_c_h[(size_t)j]); arg = j; }
+        }
+        cObjNrm1 += l1; n2 += l1 * l1;
+        cObjNrmInf = std::max(cObjNrmInf, std::fabs(lp_c_h[(size_t)std::min<long long>(arg + 1, nLp - 1)]));
     }
     cObjNrm2 = std::sqrt(n2);
     bNrm1 = 0; bNrmInf = 0; double b2 = 0;
@@ -178,7 +274,8 @@ void Solver::alloc_vars() {
         K.off = N;
         N += K.n * K.ld;
     }
-    for (DBuf<double> *v : {&R, &U, &V, &G, &M2, &Bls, &cg_r, &cg_p, &cg_Q, &Dtemp}) v->alloc((size_t)N);
+    Nt = N + nLp;
+    for (DBuf<double> *v : {&R, &U, &V, &G, &M2, &Bls, &cg_r, &cg_p, &cg_Q, &Dtemp}) v->alloc((size_t)Nt);
     {
         // split-K scratch of the dense symmetric product: up to 32 partial n x ldp blocks of the largest dense cone
         size_t need = 0;
@@ -191,7 +288,7 @@ void Solver::alloc_vars() {
     }
     lb_s.clear(); lb_y.clear();
     lb_s.resize(lbfgs_len); lb_y.resize(lbfgs_len);
-    for (int k = 0; k < lbfgs_len; ++k) { lb_s[k].alloc((size_t)N); lb_y[k].alloc((size_t)N); }
+    for (int k = 0; k < lbfgs_len; ++k) { lb_s[k].alloc((size_t)Nt); lb_y[k].alloc((size_t)Nt); }
     lb_head = 0;
 }
 
@@ -223,6 +320,14 @@ void Solver::init_vars(long long lbfgsLen, double initRho) {
         tmp.resize((size_t)(blkDims[c] * rank[c]));
         draw(tmp);
         upload_factor(R.p, cones[c], tmp.data());
+    }
+    if (nLp > 0) {
+        // rLp right after the cone factors (lorads_solver.c:458-466); uLp, vLp open LORADSInitADMMVars (:593-605)
+        tmp.resize((size_t)nLp);
+        for (double *dst : {R.p, U.p, V.p}) {
+            draw(tmp);
+            LB2_CUDA(cudaMemcpy(dst + N, tmp.data(), sizeof(double) * nLp, cudaMemcpyHostToDevice));
+        }
     }
     for (long long c = 0; c < nCones; ++c) {
         tmp.resize((size_t)(blkDims[c] * rank[c]));
@@ -298,7 +403,7 @@ void Solver::get_factor(char which, long long c, double *colMajor) const {
 void Solver::sync() { LB2_CUDA(cudaStreamSynchronize(ctx.stream)); }
 
 void Solver::read_slots() {
-    LB2_CUDA(cudaMemcpyAsync(S_host, S.p, sizeof(double) * (kNumSlots + 2 * nCones), cudaMemcpyDeviceToHost, ctx.stream));
+    LB2_CUDA(cudaMemcpyAsync(S_host, S.p, sizeof(double) * (kNumSlots + 2 * (nCones + 1)), cudaMemcpyDeviceToHost, ctx.stream));
     LB2_CUDA(cudaStreamSynchronize(ctx.stream));
 }
 
@@ -376,16 +481,20 @@ void Solver::cone_mul(ConeDev &K, const double *X, double a, double bcoef, const
 
 void Solver::init_constr_val_all(const double *Um, const double *Vm, bool same) {
     for (ConeDev &K : cones) cone_auv(K, false, Um, Vm, same, 1.0, K.cv.p);
+    // LORADSInitConstrValAllLP, lorads_alg_common.c:86-95: constrValLP[j] = a_j * (u_j v_j); only the product is kept
+    if (nLp > 0) launch_lp_prod(ctx, nLp, Um + N, Vm + N, lp_x.p);
 }
 
 void Solver::constr_val_sum() {
     if (single_identity) {
         LB2_CUDA(cudaMemcpyAsync(s.p, cones[0].cv.p, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx.stream));
-        return;
+    } else {
+        LB2_CUDA(cudaMemsetAsync(s.p, 0, sizeof(double) * m, ctx.stream));
+        for (ConeDev &K : cones)
+            launch_scatter_add(ctx, s.p, K.cv.p, K.identity_act ? nullptr : K.act_idx.p, K.n_act, 1.0, true, nullptr);
     }
-    LB2_CUDA(cudaMemsetAsync(s.p, 0, sizeof(double) * m, ctx.stream));
-    for (ConeDev &K : cones)
-        launch_scatter_add(ctx, s.p, K.cv.p, K.identity_act ? nullptr : K.act_idx.p, K.n_act, 1.0, true, nullptr);
+    // LORADSInitConstrValSumLP, lorads_alg_common.c:144-158
+    if (nLp > 0) launch_lp_rows(ctx, lp, lp_x.p, nullptr, 1.0, s.p, 0.0, nullptr);
 }
 
 void Solver::update_constr_val(long long c, const double *Um, const double *Vm) {
@@ -410,11 +519,14 @@ static void grad_from_M1(Solver &S_) {
         S_.cone_wsum(K, S_.M1.p, false, true);
         S_.cone_mul(K, S_.R.p, 2.0, 0.0, nullptr, nullptr, S_.G.p, S_.S.p + kNumSlots + 2 * c);
     }
+    // ALMSetGradLP, lorads_alm.c:56-78 (same multiplier vector M1 as the cones)
+    if (S_.nLp > 0)
+        launch_lp_grad(S_.ctx, S_.lp, S_.M1.p, S_.R.p + S_.N, S_.G.p + S_.N, S_.S.p + kNumSlots + 2 * S_.nCones);
 }
 
 static double sum_grad_sq(Solver &S_) {
     double t = 0.0;
-    for (long long c = 0; c < S_.nCones; ++c) t += S_.S_host[kNumSlots + 2 * c];
+    for (long long c = 0; c <= S_.nCones; ++c) t += S_.S_host[kNumSlots + 2 * c];    // slot nCones: LP block (0 without one)
     return t;
 }
 
@@ -423,7 +535,7 @@ double Solver::cal_grad(double rho) {
     push_scalars(0.0, rho);
     launch_alm_m_update(ctx, m, S.p + SL_TAU, nullptr, nullptr, s.p, lam.p, b.p, S.p + SL_RHO, M1.p);
     grad_from_M1(*this);
-    if (world > 1) allreduce(S.p + kNumSlots, 2 * nCones);
+    if (world > 1) allreduce(S.p + kNumSlots, 2 * (nCones + 1));
     vf_valid = false;          // the gradient changed without a new (s, y) pair
     read_slots();
     return sum_grad_sq(*this);
@@ -439,29 +551,29 @@ void Solver::lbfgs_direction(long long counter) {
         const int depth = (int)std::min<long long>(counter, 2);
         const int a = (lb_head + 1) % 2, bnode = lb_head;       // a = newest pair, bnode = the older one
         if (depth >= 1 && !vf_valid) {
-            launch_lbfgs_pair(ctx, N, false, lb_y[a].p, G.p, lb_s[a].p, lb_y[bnode].p, lb_s[bnode].p, S.p, SL_VF_D,
+            launch_lbfgs_pair(ctx, Nt, false, lb_y[a].p, G.p, lb_s[a].p, lb_y[bnode].p, lb_s[bnode].p, S.p, SL_VF_D,
                               SL_BETA0 + a, SL_VF_YY + a, world == 1);
             if (world > 1) { allreduce(S.p + SL_VF_D, 8); launch_lbfgs_pair_finalize(ctx, S.p, SL_VF_D, SL_BETA0 + a, SL_VF_YY + a); }
             vf_valid = true;
         }
-        launch_lbfgs_dir(ctx, N, depth, D, G.p, lb_y[a].p, lb_s[a].p, lb_y[bnode].p, lb_s[bnode].p, S.p, SL_VF_D,
-                         SL_BETA0 + a, SL_BETA0 + bnode, SL_VF_YY + bnode, S.p + kNumSlots, (int)nCones);
+        launch_lbfgs_dir(ctx, Nt, depth, D, G.p, lb_y[a].p, lb_s[a].p, lb_y[bnode].p, lb_s[bnode].p, S.p, SL_VF_D,
+                         SL_BETA0 + a, SL_BETA0 + bnode, SL_VF_YY + bnode, S.p + kNumSlots, (int)nCones + 1);
         return;
     }
     if (counter == 0) {
         // D = -G; the <D,G> >= 0 test of LBFGSDirectionUseGrad can only fire for G = 0, where it is a no-op
-        launch_axpby_dot(ctx, N, D, coef_const(-1.0), G.p, coef_const(0.0), nullptr, nullptr, S.p, SL_DG, false);
+        launch_axpby_dot(ctx, Nt, D, coef_const(-1.0), G.p, coef_const(0.0), nullptr, nullptr, S.p, SL_DG, false);
         return;
     }
     const int K = (int)((counter <= L - 1) ? counter : L);
     auto node = [&](int i) { return ((lb_head - i) % L + L) % L; };   // i = 1 newest ... K oldest used
-    launch_dot(ctx, N, lb_s[node(1)].p, G.p, S.p, SL_T0);
+    launch_dot(ctx, Nt, lb_s[node(1)].p, G.p, S.p, SL_T0);
     if (world > 1) allreduce(S.p + SL_T0, 1);
     for (int i = 1; i <= K; ++i) {
         const int nd = node(i);
         const double *zvec = (i < K) ? lb_s[node(i + 1)].p : lb_y[nd].p;
         // q = q - alpha*y, alpha = beta*<s,q>; -alpha is remembered for the second loop
-        launch_axpby_dot(ctx, N, q, coef_const(1.0), (i == 1) ? G.p : q,
+        launch_axpby_dot(ctx, Nt, q, coef_const(1.0), (i == 1) ? G.p : q,
                          coef_prod(SL_BETA0 + nd, SL_T0, -1.0, SL_NEGALPHA0 + nd), lb_y[nd].p, zvec, S.p, SL_T0, false);
         if (world > 1) allreduce(S.p + SL_T0, 1);
     }
@@ -470,16 +582,16 @@ void Solver::lbfgs_direction(long long counter) {
         if (i > 1) {
             // q = q + (alpha - beta*<y,q>) s
             Coef w{-1.0, SL_NEGALPHA0 + nd, -1.0, SL_BETA0 + nd, SL_T0, -1};
-            launch_axpby_dot(ctx, N, q, coef_const(1.0), q, w, lb_s[nd].p, lb_y[node(i - 1)].p, S.p, SL_T0, false);
+            launch_axpby_dot(ctx, Nt, q, coef_const(1.0), q, w, lb_s[nd].p, lb_y[node(i - 1)].p, S.p, SL_T0, false);
             if (world > 1) allreduce(S.p + SL_T0, 1);
         } else {
             // D = -(q + w s)
             Coef negw{1.0, SL_NEGALPHA0 + nd, 1.0, SL_BETA0 + nd, SL_T0, -1};
-            launch_axpby_dot(ctx, N, D, coef_const(-1.0), q, negw, lb_s[nd].p, G.p, S.p, SL_DG, false);
+            launch_axpby_dot(ctx, Nt, D, coef_const(-1.0), q, negw, lb_s[nd].p, G.p, S.p, SL_DG, false);
             if (world > 1) allreduce(S.p + SL_DG, 1);
         }
     }
-    launch_neg_if_nonneg(ctx, N, D, G.p, S.p, SL_DG);
+    launch_neg_if_nonneg(ctx, Nt, D, G.p, S.p, SL_DG);
 }
 
 void Solver::q12p12() {
@@ -490,6 +602,7 @@ void Solver::q12p12() {
         // Sharded: q1 and q2 are contiguous, one all-reduce completes both (P1 / P2 are reduced by the caller).
         cone_auv_dual(cones[0], R.p, U.p, q1.p, q2.p, S.p + SL_P1, S.p + SL_P2);
         if (world > 1) allreduce(q12.p, (long long)(q2.p - q1.p) + m + 1);
+        lp_q12p12();
         return;
     }
     LB2_CUDA(cudaMemsetAsync(q1.p, 0, sizeof(double) * m, ctx.stream));
@@ -500,6 +613,14 @@ void Solver::q12p12() {
         launch_scatter_add(ctx, q1.p, K.t1.p, map, K.n_act, 1.0, true, nullptr);
         launch_scatter_add(ctx, q2.p, K.t2.p, map, K.n_act, 1.0, true, nullptr);
     }
+    lp_q12p12();
+}
+
+void Solver::lp_q12p12() {
+    // ALMCalq12p12LP, lorads_alm.c:563-581: the LP block adds 2 A(r.d), A(d.d) and 2 c.(r.d), c.(d.d)
+    if (nLp == 0) return;
+    launch_lp_rows(ctx, lp, R.p + N, U.p + N, 2.0, q1.p, 1.0, q2.p);
+    launch_lp_obj(ctx, lp, R.p + N, U.p + N, 2.0, S.p + SL_P1, 1.0, S.p + SL_P2);
 }
 
 void Solver::primal_infeasibility(const double *Rm) {
@@ -514,6 +635,7 @@ double Solver::cal_obj(const double *Rm) {
     LB2_CUDA(cudaMemsetAsync(S.p + SL_OBJ, 0, sizeof(double), ctx.stream));
     for (ConeDev &K : cones) cone_auv(K, true, Rm, Rm, true, 1.0, K.t1.p, S.p + SL_OBJ);
     if (world > 1) allreduce(S.p + SL_OBJ, 1);
+    if (nLp > 0) launch_lp_obj(ctx, lp, Rm + N, Rm + N, 1.0, S.p + SL_OBJ, 0.0, nullptr);   // LORADSCalObjRR_ALM_LP
     read_slots();
     return S_host[SL_OBJ] / scaleObjHis;
 }
@@ -527,7 +649,7 @@ double Solver::cal_dual_obj() {
 
 void Solver::average_uv() {
     // averageUV, lorads_admm.c:310-315
-    launch_axpby_dot(ctx, N, R.p, coef_const(0.5), U.p, coef_const(0.5), V.p, nullptr, S.p, SL_T1, false);
+    launch_axpby_dot(ctx, Nt, R.p, coef_const(0.5), U.p, coef_const(0.5), V.p, nullptr, S.p, SL_T1, false);
 }
 
 void Solver::update_dual_var(double rho) { launch_dual_update(ctx, m, rho, b.p, s.p, lam.p); }
@@ -633,14 +755,14 @@ long long Solver::finish_front(double rho, double *tau, double *p12) {
 void Solver::enqueue_back(double rho, double tau) {
     (void)rho; (void)tau;     // both are read from the scalar slots S[SL_RHO], S[SL_TAU] (push_scalars)
     const int head = lb_head;
-    launch_alm_step(ctx, N, S.p + SL_TAU, G.p, U.p, R.p, lb_y[head].p, lb_s[head].p);
+    launch_alm_step(ctx, Nt, S.p + SL_TAU, G.p, U.p, R.p, lb_y[head].p, lb_s[head].p);
     launch_alm_m_update(ctx, m, S.p + SL_TAU, q1.p, q2.p, s.p, lam.p, b.p, S.p + SL_RHO, M1.p);
     grad_from_M1(*this);
-    if (world > 1) allreduce(S.p + kNumSlots, 2 * nCones);
+    if (world > 1) allreduce(S.p + kNumSlots, 2 * (nCones + 1));
     // setlbfgsHisTwo, lorads_alm.c:657-678: y += G_new, beta = 1/<y,s>, advance the ring
     if (vf_lbfgs && lbfgs_len == 2) {
         const int other = (head + 1) % 2;
-        launch_lbfgs_pair(ctx, N, true, lb_y[head].p, G.p, lb_s[head].p, lb_y[other].p, lb_s[other].p, S.p, SL_VF_D,
+        launch_lbfgs_pair(ctx, Nt, true, lb_y[head].p, G.p, lb_s[head].p, lb_y[other].p, lb_s[other].p, S.p, SL_VF_D,
                           SL_BETA0 + head, SL_VF_YY + head, world == 1);
         if (world > 1) {
             allreduce(S.p + SL_VF_D, 8);
@@ -648,7 +770,7 @@ void Solver::enqueue_back(double rho, double tau) {
         }
         vf_valid = true;
     } else {
-        launch_axpby_dot(ctx, N, lb_y[head].p, coef_const(1.0), lb_y[head].p, coef_const(1.0), G.p, lb_s[head].p, S.p,
+        launch_axpby_dot(ctx, Nt, lb_y[head].p, coef_const(1.0), lb_y[head].p, coef_const(1.0), G.p, lb_s[head].p, S.p,
                          SL_BETA0 + head, world == 1);
         if (world > 1) {
             allreduce(S.p + SL_BETA0 + head, 1);
@@ -668,7 +790,7 @@ void Solver::finish_back(double *lagNormSq, double *pinf1) {
 
 void Solver::iter_back_front(double rho, double tau, long long next_counter) {
     push_scalars(tau, rho);
-    const size_t slot_bytes = sizeof(double) * (kNumSlots + 2 * nCones);
+    const size_t slot_bytes = sizeof(double) * (kNumSlots + 2 * (nCones + 1));
     // NCCL all-reduces are captured into the graph too (validated at 2 ranks); LORADS_B200_NO_GRAPH_NCCL=1 opts out
     static const bool graph_nccl = getenv("LORADS_B200_NO_GRAPH_NCCL") == nullptr;
     if (!use_graphs || (world > 1 && !graph_nccl)) {
@@ -830,6 +952,22 @@ void Solver::update_sdp_var(double rho, double tol, long long maxit) {
             launch_scatter_add(ctx, s.p, K.cv.p, map, K.n_act, 1.0, true, nullptr);
         }
     }
+    // LORADSUpdateSDPLPVar, lorads_alg_common.c:225-249: the LP columns follow the cones in the same sweep
+    if (nLp > 0) launch_lp_sweep(ctx, lp, rho, b.p, lam.p, s.p, lp_x.p, U.p + N, V.p + N);
+}
+
+void Solver::get_lp_vec(char which, double *out) {
+    if (nLp == 0) return;
+    const double *src = (which == 'x') ? lp_x.p : (which == 'c') ? lp_c.p : factor_ptr(which) + N;
+    LB2_CUDA(cudaMemcpyAsync(out, src, sizeof(double) * nLp, cudaMemcpyDeviceToHost, ctx.stream));
+    LB2_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+void Solver::set_lp_vec(char which, const double *in) {
+    if (nLp == 0) return;
+    double *dst = (which == 'x') ? lp_x.p : factor_ptr(which) + N;
+    LB2_CUDA(cudaMemcpyAsync(dst, in, sizeof(double) * nLp, cudaMemcpyHostToDevice, ctx.stream));
+    LB2_CUDA(cudaStreamSynchronize(ctx.stream));
 }
 
 }  // namespace lb2

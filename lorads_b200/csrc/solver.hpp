@@ -25,7 +25,7 @@ enum Slot : int {
     SL_BETA0 = 48,        // 48..63  beta = 1/<y,s> per history node
     SL_VF_D = 64,         // 64..71 Gram dots of the vector-free L-BFGS (see launch_lbfgs_pair)
     SL_VF_YY = 72,        // 72..73 y.y of the two history nodes
-    kNumSlots = 80        // followed by 2 slots per cone: sum G.G and sum G.Z2 of that cone
+    kNumSlots = 80        // followed by 2 slots per cone (sum G.G, sum G.Z2 of that cone) and 2 for the LP block
 };
 constexpr int kMaxLbfgs = 16;
 
@@ -83,6 +83,18 @@ struct Solver {
     struct ConeInput { std::vector<int64_t> beg, idx; std::vector<double> elem; bool set = false; };
     std::vector<ConeInput> inputs;
     std::vector<ConeDev> cones;
+    // LP cone (diagonal block): nLp columns appended behind the cone factors in every N-vector, so that the
+    // L-BFGS / BLAS-1 kernels treat [cones | LP] as one vector exactly like the reference's Dtemp (lorads_alm.c:419-426)
+    long long nLp = 0;
+    ConeInput lp_input;                 // reader arrays (by constraint, column 0 = objective), kept until preprocess
+    std::vector<double> lp_c_h;
+    DBuf<double> lp_c, lp_rval, lp_cval, lp_nrm2sq, lp_x;
+    DBuf<int> lp_rbeg, lp_rcol, lp_cbeg, lp_crow, lp_lvl_ptr, lp_lvl_col;
+    LpDev lp;
+    void set_lp(long long nLpCols, const lb2_int *beg, const lb2_int *idx, const double *elem);
+    void build_lp();
+    void get_lp_vec(char which, double *out);
+    void set_lp_vec(char which, const double *in);
     bool preprocessed = false, vars_ready = false;
     bool single_identity = false;      // one cone whose active set is all constraints: no scatter passes
 
@@ -90,7 +102,8 @@ struct Solver {
     DBuf<double> b, lam, s, q12, M1, cvfull;   // q12 = [q1 (m+1) | q2 (m+1)] contiguous: one all-reduce covers both
     struct VecView { double *p = nullptr; } q1, q2;
     // N-vectors
-    long long N = 0;
+    long long N = 0;      // cone part: sum of n * ld
+    long long Nt = 0;     // N + nLp: length of the concatenated [cones | LP] vectors
     DBuf<double> R, U, V, G, M2, Bls, cg_r, cg_p, cg_Q, Dtemp;
     std::vector<DBuf<double>> lb_s, lb_y;
     int lbfgs_len = 2, lb_head = 0;
@@ -164,6 +177,7 @@ struct Solver {
     double cal_grad(double rho);                                                 // ALMCalGrad, returns sum ||G||^2
     void lbfgs_direction(long long counter);
     void q12p12();
+    void lp_q12p12();
     void primal_infeasibility(const double *Rm);                                 // fills S_host[SL_PINF] lazily
     double cal_obj(const double *Rm);                                            // <C, R R^T> / scaleObjHis
     double cal_dual_obj();

@@ -19,7 +19,7 @@ Everything here is host-side numpy; nothing touches the GPU.
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import List
+from typing import List, Optional
 
 import numpy as np
 
@@ -60,12 +60,25 @@ class Cone:
 
 
 @dataclass
+class LpBlock:
+    """The LP (diagonal) block in reader-output form (``LpMatBeg/Idx/Elem``, ``lorads_file_io.c:342-355``):
+    CSC with m + 1 columns, column 0 = objective (negated on read), column i = constraint i; the row index is the
+    LP column."""
+
+    n: int
+    beg: np.ndarray   # int64, length m + 2
+    idx: np.ndarray   # int64 LP column of the entry
+    elem: np.ndarray  # float64
+
+
+@dataclass
 class Instance:
     m: int
     b: np.ndarray
     cones: List[Cone]
     name: str = "instance"
     meta: dict = field(default_factory=dict)
+    lp: Optional[LpBlock] = None
 
     @property
     def blk_dims(self):
@@ -165,6 +178,41 @@ def matrix_completion(n1: int, n2: int, n_samples: int, rank: int, seed: int) ->
                     meta={"kind": "matrix_completion", "n1": n1, "n2": n2, "samples": int(n_samples), "seed": seed})
 
 
+def _lp_from_triplets(n_lp: int, m: int, con, col, val) -> LpBlock:
+    con = np.asarray(con, dtype=np.int64)
+    col = np.asarray(col, dtype=np.int64)
+    val = np.asarray(val, dtype=np.float64)
+    keep = np.abs(val) >= 1e-12
+    con, col, val = con[keep], col[keep], val[keep]
+    order = np.lexsort((col, con))
+    con, col, val = con[order], col[order], val[order]
+    beg = np.zeros(m + 2, dtype=np.int64)
+    np.add.at(beg, con + 1, 1)
+    return LpBlock(n=n_lp, beg=np.cumsum(beg), idx=col, elem=val)
+
+
+def add_lp_block(inst: Instance, n_lp: int, seed: int, max_rows_per_col: int = 3) -> Instance:
+    """Mixed SDP + LP instance: `n_lp` non-negative variables x are appended to an SDP instance.  Column j touches
+    1..max_rows_per_col random constraints with coefficients in [0.5, 1.5] and costs c_j in [0.1, 1]; the right-hand
+    side grows by A_lp x0 for a random x0 >= 0, so the mixed problem stays feasible and bounded:
+        min <C, X> + c^T x   s.t.  A(X) + A_lp x = b + A_lp x0,  X psd,  x >= 0."""
+    rng = np.random.default_rng(seed)
+    m = inst.m
+    cols, rows, vals = [], [], []
+    for j in range(n_lp):
+        k = int(rng.integers(1, max_rows_per_col + 1))
+        r = rng.choice(m, size=min(k, m), replace=False)
+        rows.append(np.sort(r)); cols.append(np.full(r.size, j)); vals.append(rng.uniform(0.5, 1.5, r.size))
+    rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+    cost = rng.uniform(0.1, 1.0, n_lp)
+    x0 = rng.uniform(0.0, 1.0, n_lp)
+    b = inst.b.copy()
+    np.add.at(b, rows, vals * x0[cols])
+    lp = _lp_from_triplets(n_lp, m, np.concatenate([np.zeros(n_lp, np.int64), rows + 1]),
+                           np.concatenate([np.arange(n_lp), cols]), np.concatenate([cost, vals]))
+    return Instance(m=m, b=b, cones=inst.cones, name=f"{inst.name}_lp{n_lp}_s{seed}", meta=dict(inst.meta, lp=n_lp), lp=lp)
+
+
 def multi_block(instances: List[Instance], name: str = "multiblock") -> Instance:
     """Stack single-block instances with the same m into one multi-cone instance (constraints are shared:
     A_i = blkdiag(A_i^1, A_i^2, ...), b = sum of the b's)."""
@@ -187,9 +235,17 @@ def write_dat_s(inst: Instance, path: str) -> None:
         blk = np.full(con.size, k + 1, dtype=np.int64)
         # SDPA entries are upper-triangular 1-based (i <= j)
         chunks.append((con, blk, col + 1, row + 1, val))
+    if inst.lp is not None:
+        # the LP block is the trailing diagonal block of (negative) dimension -nLpCols; entries are (j, j)
+        lp = inst.lp
+        con = np.repeat(np.arange(inst.m + 1, dtype=np.int64), np.diff(lp.beg))
+        val = np.where(con == 0, -lp.elem, lp.elem)
+        blk = np.full(con.size, len(inst.cones) + 1, dtype=np.int64)
+        chunks.append((con, blk, lp.idx + 1, lp.idx + 1, val))
     with open(path, "w") as f:
-        f.write(f"{inst.m}\n{len(inst.cones)}\n")
-        f.write(" ".join(str(c.n) for c in inst.cones) + "\n")
+        dims = [str(c.n) for c in inst.cones] + ([str(-inst.lp.n)] if inst.lp is not None else [])
+        f.write(f"{inst.m}\n{len(dims)}\n")
+        f.write(" ".join(dims) + "\n")
         f.write(" ".join(repr(float(x)) for x in inst.b) + "\n")
         for con, blk, i, j, val in chunks:
             lines = [f"{a} {b_} {c} {d} {e!r}" for a, b_, c, d, e in zip(con.tolist(), blk.tolist(), i.tolist(), j.tolist(), val.tolist())]
@@ -198,8 +254,8 @@ def write_dat_s(inst: Instance, path: str) -> None:
 
 
 def read_dat_s(path: str) -> Instance:
-    """Host-side reader with the output convention of ``LReadSDPA`` (PSD blocks only; an LP block, i.e.
-    a trailing negative dimension, is rejected -- SURVEY.md section 8f lists LP cones as 'next')."""
+    """Host-side reader with the output convention of ``LReadSDPA`` (a trailing negative dimension is the LP
+    block, ``lorads_file_io.c:139-155``)."""
     with open(path) as f:
         lines = f.read().split("\n")
     pos = 0
@@ -209,9 +265,12 @@ def read_dat_s(path: str) -> Instance:
     nblk = int(lines[pos].split()[0]); pos += 1
     dims = [int(t) for t in lines[pos].replace("{", " ").replace("}", " ").replace("(", " ").replace(")", " ").replace(",", " ").split()]
     pos += 1
-    if any(d <= 0 for d in dims):
-        raise ValueError("LP / diagonal blocks are out of scope for the device data layer")
     assert len(dims) == nblk
+    n_lp = 0
+    if dims and dims[-1] < 0:
+        n_lp = -dims.pop()
+    if any(d <= 0 for d in dims):
+        raise ValueError("only one diagonal (LP) block is supported and it must be the last one")
     b = np.array([float(t) for t in lines[pos].replace(",", " ").replace("{", " ").replace("}", " ").split()], dtype=np.float64)
     pos += 1
     assert b.size == m
@@ -229,4 +288,13 @@ def read_dat_s(path: str) -> Instance:
         hi = np.maximum(i[sel], j[sel])
         lo = np.minimum(i[sel], j[sel])
         cones.append(_csc_from_triplets(n, m, con[sel], hi, lo, val[sel]))
-    return Instance(m=m, b=b, cones=cones, name=path)
+    lp = None
+    if n_lp > 0:
+        sel = blk == len(dims)
+        keep = np.abs(val[sel]) >= 1e-12
+        c_, i_, v_ = con[sel][keep], i[sel][keep], val[sel][keep]
+        order = np.argsort(c_, kind="stable")          # the reader keeps file order inside a constraint
+        beg = np.zeros(m + 2, dtype=np.int64)
+        np.add.at(beg, c_ + 1, 1)
+        lp = LpBlock(n=n_lp, beg=np.cumsum(beg), idx=i_[order], elem=v_[order])
+    return Instance(m=m, b=b, cones=cones, name=path, lp=lp)

@@ -59,6 +59,10 @@ def _load(bits: int):
     lib.refh_time_alm_inner_iters.restype = C.c_double
     lib.refh_time_alm_inner_iters.argtypes = [C.c_void_p, C.c_double, C.c_int64, _dp]
     lib.refh_solve.argtypes = [C.c_void_p, C.c_double, C.c_int, _dp]
+    lib.refh_lp_ptr.restype = _dp
+    lib.refh_lp_ptr.argtypes = [C.c_void_p, C.c_char]
+    lib.refh_admm_init_constr.argtypes = [C.c_void_p]
+    lib.refh_admm_update_var.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int64]
     return lib
 
 
@@ -114,6 +118,23 @@ class RefSolver:
         """Live view of l(ambda) / s (constrValSum) / b / m (M1temp) / q (ARDSum) / Q (ADDSum) / v (constrVio)."""
         p = self.lib.refh_vec_ptr(self.ctx, which.encode())
         return np.ctypeslib.as_array(p, shape=(self.m,))
+
+    @property
+    def n_lp(self) -> int:
+        return self.info(9)
+
+    def lp(self, which: str) -> np.ndarray:
+        """Live view of the LP vectors rLp ('R') / uLp ('U') / vLp ('V') / gradLp ('G')."""
+        p = self.lib.refh_lp_ptr(self.ctx, which.encode())
+        return np.ctypeslib.as_array(p, shape=(self.n_lp,))
+
+    def admm_init_constr(self):
+        """constrVal / constrValSum from (U, V) and (uLp, vLp): head of LORADSADMMOptimize, lorads_admm.c:47-48."""
+        self.lib.refh_admm_init_constr(self.ctx)
+
+    def admm_update_var(self, rho: float, tol: float, maxit: int):
+        """One Gauss-Seidel sweep over every block: LORADSUpdateSDPVar / LORADSUpdateSDPLPVar."""
+        self.lib.refh_admm_update_var(self.ctx, rho, tol, maxit)
 
     def blinsys(self, cone=0) -> np.ndarray:
         n, r = self.dim(cone), self.rank(cone)

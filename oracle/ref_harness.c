@@ -49,6 +49,7 @@ typedef struct {
     lorads_alm_state alm;
     lorads_admm_state admm;
     SDPConst sdpConst;
+    lorads_func *f;            /* the reference's own function set: SDP only, or SDP + LP (lorads_solver.c:717-756) */
 } refh_ctx;
 
 static void default_params(lorads_params *p)
@@ -90,6 +91,7 @@ refh_ctx *refh_open(const char *fname, double timesLogRank)
     S->hisRecT = c->params.lbfgsListLength;
     LORADSInitADMMVars(S, S->var->rankElem, c->BlkDims, c->nBlks, c->nLpCols);
     initial_solver_state(&c->params, S, &c->alm, &c->admm, &c->sdpConst);
+    LORADSInitFuncSet(&c->f, c->nLpCols);
     return c;
 }
 
@@ -187,6 +189,33 @@ double *refh_vec_ptr(refh_ctx *c, char which)
 
 double *refh_blinsys_ptr(refh_ctx *c, int iCone) { return c->S->var->bLinSys[iCone]; }
 
+/* LP vectors of lorads_variable: 'R' rLp, 'U' uLp, 'V' vLp, 'G' gradLp (NULL without an LP block) */
+double *refh_lp_ptr(refh_ctx *c, char which)
+{
+    lorads_variable *v = c->S->var;
+    if (c->nLpCols <= 0) return NULL;
+    switch (which) {
+    case 'R': return v->rLp->matElem;
+    case 'U': return v->uLp->matElem;
+    case 'V': return v->vLp->matElem;
+    case 'G': return v->gradLp->matElem;
+    }
+    return NULL;
+}
+
+/* One ADMM sweep over all blocks, LP columns included: LORADSUpdateSDPVar / LORADSUpdateSDPLPVar
+ * (lorads_alg_common.c:187-249) after constrVal / constrValSum were initialised from (U, V). */
+void refh_admm_init_constr(refh_ctx *c)
+{
+    lorads_solver *S = c->S;
+    c->f->InitConstrValAll(S, S->var->uLp, S->var->vLp, S->var->U, S->var->V);
+    c->f->InitConstrValSum(S);
+}
+void refh_admm_update_var(refh_ctx *c, double rho, double tol, int64_t maxit)
+{
+    c->f->admmUpdateVar(c->S, rho, tol, (lorads_int)maxit);
+}
+
 /* out (length nRows) = A(sym(U V^T)) of one cone  -- LORADSInitConstrVal, lorads_alg_common.c:71 */
 void refh_auv(refh_ctx *c, int iCone, char u, char v, double *out)
 {
@@ -225,7 +254,7 @@ void refh_wsum_mulrk(refh_ctx *c, int iCone, double *w, int addC, char x, double
 double refh_alm_cal_grad(refh_ctx *c, double rho)
 {
     double lag = 0.0;
-    ALMCalGrad(c->S, c->S->var->rLp, c->S->var->gradLp, c->S->var->R, c->S->var->Grad, &lag, rho);
+    c->f->ALMCalGrad(c->S, c->S->var->rLp, c->S->var->gradLp, c->S->var->R, c->S->var->Grad, &lag, rho);
     return lag;
 }
 
@@ -253,10 +282,10 @@ int64_t refh_update_sdp_var_one(refh_ctx *c, int iCone, char upd, char noupd, do
 double refh_alm_prepare(refh_ctx *c, double rho)
 {
     lorads_solver *S = c->S;
-    LORADSInitConstrValAll(S, S->var->rLp, S->var->rLp, S->var->R, S->var->R);
-    LORADSInitConstrValSum(S);
+    c->f->InitConstrValAll(S, S->var->rLp, S->var->rLp, S->var->R, S->var->R);
+    c->f->InitConstrValSum(S);
     double lag = 0.0;
-    ALMCalGrad(S, S->var->rLp, S->var->gradLp, S->var->R, S->var->Grad, &lag, rho);
+    c->f->ALMCalGrad(S, S->var->rLp, S->var->gradLp, S->var->R, S->var->Grad, &lag, rho);
     return lag;
 }
 
@@ -268,24 +297,24 @@ int64_t refh_alm_inner_iter(refh_ctx *c, double rho, int64_t lbfgsCounter, doubl
     lorads_solver *S = c->S;
     lorads_int incx = 1;
     double minusOne = -1.0, tau = 0.0;
-    LBFGSDirection(&c->params, S, S->lbfgsHis, S->var->gradLp, S->var->uLp, S->var->Grad, S->var->U, (lorads_int)lbfgsCounter);
-    LBFGSDirectionUseGrad(S, S->var->uLp, S->var->gradLp, S->var->U, S->var->Grad);
+    c->f->LBFGSDirection(&c->params, S, S->lbfgsHis, S->var->gradLp, S->var->uLp, S->var->Grad, S->var->U, (lorads_int)lbfgsCounter);
+    c->f->LBFGSDirUseGrad(S, S->var->uLp, S->var->gradLp, S->var->U, S->var->Grad);
     double *q0 = S->var->M1temp;
     LORADS_MEMCPY(q0, S->rowRHS, double, S->nRows);
     axpy(&(S->nRows), &minusOne, S->var->constrValSum, &incx, q0, &incx);
     double p12[2];
-    ALMCalq12p12(S, S->var->rLp, S->var->uLp, S->var->R, S->var->U, S->var->ARDSum, S->var->ADDSum, p12);
+    c->f->ALMCalq12p12(S, S->var->rLp, S->var->uLp, S->var->R, S->var->U, S->var->ARDSum, S->var->ADDSum, p12);
     lorads_int rootNum = ALMLineSearch(rho, S->nRows, S->var->dualVar, p12[0], p12[1], q0, S->var->ARDSum, S->var->ADDSum, &tau);
     out[0] = tau; out[3] = p12[0]; out[4] = p12[1];
     if (rootNum == 0) return 0;
-    SetyAsNegGrad(S, S->var->gradLp, S->var->Grad);
-    ALMupdateVar(S, S->var->rLp, S->var->uLp, S->var->R, S->var->U, tau);
+    c->f->setAsNegGrad(S, S->var->gradLp, S->var->Grad);
+    c->f->ALMupdateVar(S, S->var->rLp, S->var->uLp, S->var->R, S->var->U, tau);
     double lag = 0.0, tauSquare = tau * tau;
     axpy(&(S->nRows), &tau, S->var->ARDSum, &incx, S->var->constrValSum, &incx);
     axpy(&(S->nRows), &tauSquare, S->var->ADDSum, &incx, S->var->constrValSum, &incx);
-    ALMCalGrad(S, S->var->rLp, S->var->gradLp, S->var->R, S->var->Grad, &lag, rho);
-    setlbfgsHisTwo(S, S->var->gradLp, S->var->uLp, S->var->Grad, S->var->U, tau);
-    LORADSUpdateDimacsErrorALM(S, S->var->R, S->var->R, S->var->rLp, S->var->rLp);
+    c->f->ALMCalGrad(S, S->var->rLp, S->var->gradLp, S->var->R, S->var->Grad, &lag, rho);
+    c->f->setlbfgsHisTwo(S, S->var->gradLp, S->var->uLp, S->var->Grad, S->var->U, tau);
+    c->f->updateDimacsALM(S, S->var->R, S->var->R, S->var->rLp, S->var->rLp);
     out[1] = lag;
     out[2] = S->dimacError[LORADS_DIMAC_ERROR_CONSTRVIO_L1];
     return rootNum;
@@ -343,8 +372,9 @@ void refh_solve(refh_ctx *c, double timeSecLimit, int reoptLevel, double *out)
             if (!P->highAccMode && c->admm.l_1_dual_infeasibility <= 5 * P->phase2Tol &&
                 c->admm.primal_dual_gap <= 5 * P->phase2Tol && c->admm.l_1_primal_infeasibility <= P->phase2Tol) break;
             reopt(P, S, &c->alm, &c->admm, &reopt_param, &reopt_alm_iter, &reopt_admm_iter, t0, &admm_bad_iter_flag, 2);
+            if (S->nLpCols > 0) averageUVLP(S->var->uLp, S->var->vLp, S->var->rLp);           /* main.c:438-447 */
             for (lorads_int i = 0; i < S->nCones; ++i) averageUV(S->var->U[i], S->var->V[i], S->var->R[i]);
-            copyRtoV(S->var->rLp, S->var->vLp, S->var->R, S->var->V, S->nCones);
+            c->f->copyRtoV(S->var->rLp, S->var->vLp, S->var->R, S->var->V, S->nCones);
             calculate_dual_infeasibility_solver(S);
             c->admm.l_1_dual_infeasibility = S->dimacError[LORADS_DIMAC_ERROR_DUALFEASIBLE_L1];
             c->admm.primal_dual_gap = S->dimacError[LORADS_DIMAC_ERROR_PDGAP];

@@ -11,6 +11,7 @@ if ROOT not in sys.path:
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ["maxcut_n120", "maxcut_n800", "mcomp_60x50", "theta_n60", "twoblock", "theta_n200"]
+LP_GOLDEN_CASES = ["lp_maxcut_n60", "lp_maxcut_n300", "lp_theta_n40", "lp_twoblock"]     # mixed SDP + LP blocks
 
 
 def pytest_configure(config):

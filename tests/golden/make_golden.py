@@ -30,7 +30,18 @@ CASES = {
 }
 
 
+# mixed SDP + LP instances: an LP block appended to a base instance (sdpa.add_lp_block)
+LP_CASES = {
+    "lp_maxcut_n60": ("with_lp", dict(base="maxcut", base_kw=dict(n=60, n_edges=200, seed=1), n_lp=25, seed=7)),
+    "lp_maxcut_n300": ("with_lp", dict(base="maxcut", base_kw=dict(n=300, n_edges=1500, seed=2), n_lp=400, seed=3)),
+    "lp_theta_n40": ("with_lp", dict(base="lovasz_theta", base_kw=dict(n=40, n_edges=150, seed=4), n_lp=30, seed=5)),
+    "lp_twoblock": ("with_lp", dict(base="two_block", base_kw=dict(n1=30, e1=90, n2=120, e2=500), n_lp=60, seed=9)),
+}
+
+
 def build_instance(kind, kw):
+    if kind == "with_lp":
+        return sdpa.add_lp_block(build_instance(kw["base"], kw["base_kw"]), kw["n_lp"], kw["seed"])
     if kind == "two_block":
         a = sdpa.maxcut(kw["n1"], kw["e1"], 11)
         b = sdpa.maxcut(kw["n2"], kw["e2"], 12)
@@ -113,5 +124,73 @@ def main():
         print(name, "ok", {k: sol[k] for k in ("pobj", "dobj", "pinf", "gap", "dinf", "alm_inner", "admm_iter", "cg_iter", "status")})
 
 
+def main_lp():
+    """LP fixtures: the reference's own LP function set (ALMCalGradLP, ALMCalq12p12LP, LORADSUpdateSDPLPVar, ...)
+    driven through oracle/ref_harness.c."""
+    only = sys.argv[1:]
+    for name, (kind, kw) in LP_CASES.items():
+        if only and name not in only:
+            continue
+        rng = np.random.default_rng(sum(map(ord, name)))
+        inst = build_instance(kind, kw)
+        d = tempfile.mkdtemp()
+        path = os.path.join(d, name + ".dat-s")
+        sdpa.write_dat_s(inst, path)
+        R = ref.RefSolver(path, 32)
+        assert R.n_lp == inst.lp.n
+        out = {"meta": json.dumps({"kind": kind, "kw": kw})}
+        nc = R.n_cones
+        rho = R.dinfo(6)
+        out["rho0"] = rho
+        out["norms"] = np.array([R.dinfo(k) for k in range(6)])
+        out["ranks"] = np.array([R.rank(c) for c in range(nc)])
+        for c in range(nc):
+            for f in "RUV":
+                out[f"{f}{c}"] = R.factor(f, c).copy()
+        for f in "RUV":
+            out[f"lp{f}"] = R.lp(f).copy()
+        lam = 0.1 * rng.standard_normal(R.m)
+        out["lam"] = lam
+        R.vec("l")[:] = lam
+        out["lag_sq"] = R.alm_prepare(rho)
+        out["lpG"] = R.lp("G").copy()
+        for c in range(nc):
+            out[f"grad{c}"] = R.factor("G", c).copy()
+        out["constr_sum"] = R.vec("s").copy()
+        # one full ADMM sweep (cones by CG, then the LP columns) from U = V = R, uLp = vLp = rLp
+        for c in range(nc):
+            R.factor("U", c)[:] = R.factor("R", c)
+            R.factor("V", c)[:] = R.factor("R", c)
+        R.lp("U")[:] = R.lp("R")
+        R.lp("V")[:] = R.lp("R")
+        R.admm_init_constr()
+        out["sweep_rho"] = 10.0 * rho
+        R.admm_update_var(10.0 * rho, 1e-10, 800)
+        out["sweep_lpU"], out["sweep_lpV"] = R.lp("U").copy(), R.lp("V").copy()
+        out["sweep_s"] = R.vec("s").copy()
+        for c in range(nc):
+            out[f"sweep_U{c}"], out[f"sweep_V{c}"] = R.factor("U", c).copy(), R.factor("V", c).copy()
+        # ALM inner iterations from lambda = 0 on a fresh context
+        R = ref.RefSolver(path, 32)
+        R.alm_prepare(rho)
+        taus, lags, pinfs, roots, p1s, p2s = [], [], [], [], [], []
+        for k in range(8):
+            root, o = R.alm_inner_iter(rho, k)
+            roots.append(root); taus.append(o["tau"]); lags.append(o["lag_norm_sq"]); pinfs.append(o["pinf"])
+            p1s.append(o["p1"]); p2s.append(o["p2"])
+        out["it_tau"], out["it_lag"], out["it_pinf"], out["it_root"], out["it_p1"], out["it_p2"] = map(
+            np.array, (taus, lags, pinfs, roots, p1s, p2s))
+        out["lpR_after_iters"] = R.lp("R").copy()
+        R2 = ref.RefSolver(path, 32)
+        sol = R2.solve()
+        out["solve"] = json.dumps(sol)
+        out["lp_x_solution"] = R2.lp("R").copy() ** 2
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "ok", {k: sol[k] for k in ("pobj", "dobj", "pinf", "gap", "dinf", "alm_inner", "admm_iter", "cg_iter", "status")})
+
+
 if __name__ == "__main__":
-    main()
+    if not any(a.startswith("lp_") for a in sys.argv[1:]):
+        main()
+    if not sys.argv[1:] or any(a.startswith("lp_") for a in sys.argv[1:]):
+        main_lp()

@@ -65,11 +65,31 @@ def test_dat_s_roundtrip(tmp_path, make):
         assert np.array_equal(a.beg, b.beg) and np.array_equal(a.idx, b.idx) and np.allclose(a.elem, b.elem)
 
 
-def test_reader_rejects_lp_block(tmp_path):
+def test_reader_takes_a_trailing_lp_block(tmp_path):
+    """A trailing negative dimension is the LP block (lorads_file_io.c:139-155): entries (j, j) of that block become
+    LpMatBeg/Idx/Elem, objective negated; a diagonal block anywhere else is rejected."""
     p = tmp_path / "lp.dat-s"
-    p.write_text("1\n2\n2 -3\n1.0\n0 1 1 1 1.0\n1 1 1 1 1.0\n")
+    p.write_text("2\n2\n2 -3\n1.0 2.0\n0 1 1 1 1.0\n0 2 2 2 -4.0\n1 1 1 1 1.0\n1 2 1 1 0.5\n2 2 3 3 2.5\n2 2 1 1 1.5\n")
+    inst = sdpa.read_dat_s(str(p))
+    assert inst.lp is not None and inst.lp.n == 3 and len(inst.cones) == 1
+    assert inst.lp.beg.tolist() == [0, 1, 2, 4]
+    assert inst.lp.idx.tolist() == [1, 0, 2, 0]          # file order inside a constraint, like the reference reader
+    assert inst.lp.elem.tolist() == [4.0, 0.5, 2.5, 1.5]
+    q = tmp_path / "bad.dat-s"
+    q.write_text("1\n2\n-3 2\n1.0\n0 2 1 1 1.0\n")
     with pytest.raises(ValueError):
-        sdpa.read_dat_s(str(p))
+        sdpa.read_dat_s(str(q))
+
+
+def test_lp_instance_roundtrip(tmp_path):
+    inst = sdpa.add_lp_block(sdpa.maxcut(30, 80, 1), 12, 3)
+    assert inst.lp.n == 12 and inst.lp.beg[1] == 12          # every LP column has a cost
+    path = str(tmp_path / "mix.dat-s")
+    sdpa.write_dat_s(inst, path)
+    back = sdpa.read_dat_s(path)
+    assert np.array_equal(back.lp.beg, inst.lp.beg) and np.array_equal(back.lp.idx, inst.lp.idx)
+    assert np.allclose(back.lp.elem, inst.lp.elem) and np.allclose(back.b, inst.b)
+    assert np.array_equal(back.cones[0].idx, inst.cones[0].idx)
 
 
 def test_tiny_entries_dropped():

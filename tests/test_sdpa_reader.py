@@ -47,11 +47,19 @@ def test_format_variants(tmp_path):
     assert c.idx.tolist() == [0, 2, 3, 5]          # PACK_IDX(3, row, col): (0,0)=0 (2,0)=2 (1,1)=3 (2,2)=5
 
 
-def test_lp_block_is_reported(tmp_path):
+def test_lp_block_is_returned(tmp_path):
     p = tmp_path / "lp.dat-s"
-    p.write_text("1\n2\n2 -3\n1.0\n0 1 1 1 1.0\n1 1 1 1 1.0\n1 2 2 2 1.0\n")
-    with pytest.raises(ValueError):
-        capi.read_sdpa(str(p))
+    p.write_text("1\n2\n2 -3\n1.0\n0 1 1 1 1.0\n0 2 3 3 2.0\n1 1 1 1 1.0\n1 2 2 2 1.0\n")
+    inst = capi.read_sdpa(str(p))
+    assert inst.lp.n == 3 and inst.lp.beg.tolist() == [0, 1, 2]
+    assert inst.lp.idx.tolist() == [2, 1] and inst.lp.elem.tolist() == [-2.0, 1.0]
+    # same arrays as the pure-python reader on a generated mixed instance
+    mix = sdpa.add_lp_block(sdpa.maxcut(40, 100, 2), 30, 4)
+    path = str(tmp_path / "mix.dat-s")
+    sdpa.write_dat_s(mix, path)
+    a, b = capi.read_sdpa(path), sdpa.read_dat_s(path)
+    assert np.array_equal(a.lp.beg, b.lp.beg) and np.array_equal(a.lp.idx, b.lp.idx) and np.array_equal(a.lp.elem, b.lp.elem)
+    assert np.array_equal(a.lp.beg, mix.lp.beg) and np.array_equal(a.lp.idx, mix.lp.idx)
 
 
 def test_errors(tmp_path):
