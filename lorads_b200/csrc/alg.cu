@@ -65,23 +65,19 @@ bool Solver::check_all_rank_max(double aug) const {
 }
 
 bool Solver::aug_rank(double aug) {
-    // Column sharding: ownership is by global column index (k % world), so old columns stay where they are and the
-    // host arrays below are full-size with only the owned columns filled / uploaded.
     // AUG_RANK, lorads_solver.c:806-906: append columns to U, V, R, Grad (M2temp keeps its old columns), the new
     // block of columns carries 1/sqrt(min(n, #new)) on its leading diagonal (lpRandomDiag :776-786); CG work
-    // vectors and the L-BFGS history are re-allocated (zeroed).
+    // vectors and the L-BFGS history are re-allocated (zeroed).  Everything stays on the device: the old buffers are
+    // set aside, new zero-filled ones are allocated for the larger leading dimensions and a copy kernel moves the
+    // old columns across.  Column sharding: ownership is by global column index (k % world), so the columns a rank
+    // already holds keep their local positions and only its share of the new columns is appended.
     if (check_all_rank_max(1.0)) return true;
-    std::vector<std::vector<double>> hR(nCones), hU(nCones), hV(nCones), hG(nCones), hM(nCones);
+    struct Old { long long off; int ld, r; };
+    std::vector<Old> old((size_t)nCones);
+    for (long long c = 0; c < nCones; ++c) old[(size_t)c] = Old{cones[c].off, cones[c].ld, cones[c].r};
+    const long long N_old = N;
     std::vector<long long> old_rank = rank;
-    for (long long c = 0; c < nCones; ++c) {
-        const size_t sz = (size_t)(blkDims[c] * rank[c]);
-        hR[c].resize(sz); hU[c].resize(sz); hV[c].resize(sz); hG[c].resize(sz); hM[c].resize(sz);
-        get_factor('R', c, hR[c].data()); get_factor('U', c, hU[c].data()); get_factor('V', c, hV[c].data());
-        get_factor('G', c, hG[c].data()); get_factor('M', c, hM[c].data());
-    }
-    // the LP vectors are separate arrays in the reference and survive AUG_RANK untouched
-    std::vector<double> lpR((size_t)nLp), lpU((size_t)nLp), lpV((size_t)nLp), lpG((size_t)nLp);
-    get_lp_vec('R', lpR.data()); get_lp_vec('U', lpU.data()); get_lp_vec('V', lpV.data()); get_lp_vec('G', lpG.data());
+    DBuf<double> oR = std::move(R), oU = std::move(U), oV = std::move(V), oG = std::move(G), oM = std::move(M2);
     for (long long c = 0; c < nCones; ++c) {
         const long long nr = (long long)std::min<double>(std::ceil((double)rank[c] * aug), (double)rank_max[c]);
         rank[c] = nr;
@@ -90,21 +86,39 @@ bool Solver::aug_rank(double aug) {
             if ((int)(k % world) == myrank) my_cols[c].push_back((int)k);
     }
     alloc_vars();
+    struct Pair { DBuf<double> *src, *dst; bool diag; };
+    const Pair pairs[5] = {{&oR, &R, true}, {&oU, &U, true}, {&oV, &V, true}, {&oG, &G, true}, {&oM, &M2, false}};
     for (long long c = 0; c < nCones; ++c) {
-        const long long n = blkDims[c], ro = old_rank[c], rn = rank[c], add = rn - ro;
-        auto grow = [&](std::vector<double> &h, bool diag) {
-            h.resize((size_t)(n * rn), 0.0);
-            std::fill(h.begin() + (size_t)(n * ro), h.end(), 0.0);
-            if (diag && add > 0) {
-                const long long rr = std::min(n, add);
-                for (long long i = 0; i < rr; ++i) h[(size_t)(n * ro + i * n + i)] = 1.0 / std::sqrt((double)rr);
-            }
-        };
-        grow(hU[c], true); grow(hV[c], true); grow(hR[c], true); grow(hG[c], true); grow(hM[c], false);
-        set_factor('U', c, hU[c].data()); set_factor('V', c, hV[c].data()); set_factor('R', c, hR[c].data());
-        set_factor('G', c, hG[c].data()); set_factor('M', c, hM[c].data());
+        ConeDev &K = cones[c];
+        const Old &o = old[(size_t)c];
+        const long long n = blkDims[c], ro = old_rank[c], add = rank[c] - ro;
+        // positions (inside this cone's slice) and value of the new diagonal entries held by this rank
+        std::vector<int> pos;
+        const long long rr = std::min(n, add);
+        for (int lc = o.r; lc < K.r; ++lc) {
+            const long long i = my_cols[c][(size_t)lc] - ro;          // row of the diagonal entry of global column ro + i
+            if (i >= 0 && i < rr) pos.push_back((int)(i * K.ld + lc));
+        }
+        DBuf<int> dpos;
+        DBuf<double> dval;
+        if (!pos.empty()) {
+            dpos.upload(pos);
+            dval.upload(std::vector<double>(pos.size(), 1.0 / std::sqrt((double)rr)));
+        }
+        for (const Pair &p : pairs) {
+            launch_relayout(ctx, n, o.r, o.ld, K.ld, p.src->p + o.off, p.dst->p + K.off);
+            if (p.diag && !pos.empty())
+                launch_scatter_add(ctx, p.dst->p + K.off, dval.p, dpos.p, (long long)pos.size(), 1.0, false, nullptr);
+        }
+        LB2_CUDA(cudaStreamSynchronize(ctx.stream));      // dpos / dval go out of scope
     }
-    set_lp_vec('R', lpR.data()); set_lp_vec('U', lpU.data()); set_lp_vec('V', lpV.data()); set_lp_vec('G', lpG.data());
+    if (nLp > 0) {
+        // the LP vectors are separate arrays in the reference and survive AUG_RANK untouched
+        for (const Pair &p : pairs)
+            if (p.diag)
+                LB2_CUDA(cudaMemcpyAsync(p.dst->p + N, p.src->p + N_old, sizeof(double) * nLp, cudaMemcpyDeviceToDevice, ctx.stream));
+    }
+    LB2_CUDA(cudaStreamSynchronize(ctx.stream));          // the old buffers are released on return
     return check_all_rank_max(aug);
 }
 
@@ -504,6 +518,8 @@ void Solver::dual_infeasibility() {
         const long long np2 = (n + 1) & ~1LL;            // even stride keeps every basis vector 16-byte aligned
         DBuf<double> Vb, w, x0;
         Vb.alloc((size_t)np2 * (kdim + 1)); w.alloc((size_t)np2); x0.alloc((size_t)np2);
+        DBuf<double> hbuf, hscratch;
+        hbuf.alloc(kLanczosMax); hscratch.alloc((size_t)512 * kLanczosMax);
         std::vector<double> v0((size_t)n);
         uint64_t st = 0x9E3779B97F4A7C15ull;
         double nr0 = 0.0;
@@ -530,17 +546,16 @@ void Solver::dual_infeasibility() {
             alpha.clear(); beta.clear();
             bool done = false;
             for (int j = 0; j < kdim; ++j) {
+                // w = S v_j, then two classical Gram-Schmidt passes against v_0..v_j, each one dots kernel + one
+                // update kernel (full re-orthogonalisation; the first pass also yields alpha_j = v_j . S v_j and
+                // removes the beta_{j-1} v_{j-1} term), |w|^2 from the last update, v_{j+1} = w/|w| issued before the
+                // single host synchronisation of the step
                 matvec(vec(j), w.p);
-                launch_dot(ctx, n, vec(j), w.p, S.p, SL_T0);                       // alpha_j
-                launch_axpby_dot(ctx, n, w.p, coef_const(1.0), w.p, coef_slot(SL_T0, -1.0), vec(j), nullptr, S.p, SL_T1, false);
-                if (j > 0)
-                    launch_axpby_dot(ctx, n, w.p, coef_const(1.0), w.p, coef_const(-beta[j - 1]), vec(j - 1), nullptr, S.p, SL_T1, false);
-                for (int pass = 0; pass < 2; ++pass)                               // full re-orthogonalisation
-                    for (int l = 0; l <= j; ++l) {
-                        launch_dot(ctx, n, vec(l), w.p, S.p, SL_T1);
-                        launch_axpby_dot(ctx, n, w.p, coef_const(1.0), w.p, coef_slot(SL_T1, -1.0), vec(l), nullptr, S.p, SL_DG, false);
-                    }
-                launch_dot(ctx, n, w.p, w.p, S.p, SL_T1);
+                launch_lanczos_dots(ctx, n, Vb.p, np2, j + 1, w.p, hbuf.p, hscratch.p, S.p, SL_T0);
+                launch_lanczos_update(ctx, n, Vb.p, np2, j + 1, hbuf.p, w.p, S.p, -1);
+                launch_lanczos_dots(ctx, n, Vb.p, np2, j + 1, w.p, hbuf.p, hscratch.p, S.p, -1);
+                launch_lanczos_update(ctx, n, Vb.p, np2, j + 1, hbuf.p, w.p, S.p, SL_T1);
+                if (j + 1 < kdim) launch_lanczos_next(ctx, n, w.p, vec(j + 1), S.p, SL_T1);
                 read_slots();
                 const double a = S_host[SL_T0], bb = std::sqrt(S_host[SL_T1]);
                 alpha.push_back(a); beta.push_back(bb);
@@ -559,16 +574,16 @@ void Solver::dual_infeasibility() {
                     const double est = std::fabs(bb * Q[(size_t)(mdim - 1) * mdim + best]);
                     const double scale = std::max(std::fabs(theta), 2.2e-16);
                     if (breakdown || est <= tol * scale || mdim >= n) { done = true; break; }
-                    // explicit restart from the Ritz vector
+                    // explicit restart from the Ritz vector x0 = sum_l Q[l][best] v_l, normalised on the device
+                    std::vector<double> hq((size_t)mdim);
+                    for (int l = 0; l < mdim; ++l) hq[(size_t)l] = -Q[(size_t)l * mdim + best];
+                    LB2_CUDA(cudaMemcpyAsync(hbuf.p, hq.data(), sizeof(double) * mdim, cudaMemcpyHostToDevice, ctx.stream));
+                    LB2_CUDA(cudaStreamSynchronize(ctx.stream));      // hq is pageable stack-lifetime memory
                     LB2_CUDA(cudaMemsetAsync(x0.p, 0, sizeof(double) * np2, ctx.stream));
-                    for (int l = 0; l < mdim; ++l)
-                        launch_axpby_dot(ctx, n, x0.p, coef_const(1.0), x0.p, coef_const(Q[(size_t)l * mdim + best]), vec(l), nullptr, S.p, SL_DG, false);
-                    launch_dot(ctx, n, x0.p, x0.p, S.p, SL_T1);
-                    read_slots();
-                    launch_axpby_dot(ctx, n, vec(0), coef_const(1.0 / std::sqrt(S_host[SL_T1])), x0.p, coef_const(0.0), nullptr, nullptr, S.p, SL_DG, false);
+                    launch_lanczos_update(ctx, n, Vb.p, np2, mdim, hbuf.p, x0.p, S.p, SL_T1);
+                    launch_lanczos_next(ctx, n, x0.p, vec(0), S.p, SL_T1);
                     break;
                 }
-                launch_axpby_dot(ctx, n, vec(j + 1), coef_const(1.0 / bb), w.p, coef_const(0.0), nullptr, nullptr, S.p, SL_DG, false);
             }
             if (done) break;
         }

@@ -1288,6 +1288,111 @@ void launch_scale(Ctx &c, double *x, long long n, double f) {
     LB2_LAUNCH_CHECK(c);
 }
 
+__global__ void __launch_bounds__(kBlock) relayout_kernel(long long n, int r_old, int ld_old, int ld_new,
+                                                          const double *__restrict__ src, double *__restrict__ dst) {
+    const long long total = n * r_old;
+    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < total; q += (long long)gridDim.x * kBlock) {
+        const long long i = q / r_old;
+        const int k = (int)(q % r_old);
+        dst[i * ld_new + k] = src[i * ld_old + k];
+    }
+}
+
+void launch_relayout(Ctx &c, long long n, int r_old, int ld_old, int ld_new, const double *src, double *dst) {
+    if (r_old <= 0) return;
+    relayout_kernel<<<grid_for(n * r_old, 2, c), kBlock, 0, c.stream>>>(n, r_old, ld_old, ld_new, src, dst);
+    LB2_LAUNCH_CHECK(c);
+}
+
+// =================================================================================================
+// Lanczos helpers (dual infeasibility): classical Gram-Schmidt against the whole basis in one pass
+// =================================================================================================
+__global__ void __launch_bounds__(kBlock) lanczos_dots_kernel(long long n, const double *__restrict__ Vb, long long stride, int nv,
+                                                              const double *__restrict__ w, double *h, double *scratch,
+                                                              unsigned int *ticket, double *S, int alpha_slot) {
+    __shared__ double sm[kBlock / 32][kLanczosMax];
+    __shared__ bool last;
+    double acc[kLanczosMax];
+#pragma unroll
+    for (int l = 0; l < kLanczosMax; ++l) acc[l] = 0.0;
+    for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+        const double wi = w[i];
+#pragma unroll
+        for (int l = 0; l < kLanczosMax; ++l)
+            if (l < nv) acc[l] = fma(Vb[l * stride + i], wi, acc[l]);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int l = 0; l < kLanczosMax; ++l) {
+        if (l < nv) {                               // warp-uniform
+            const double t = warp_sum(acc[l]);
+            if (lane == 0) sm[warp][l] = t;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < nv) {
+        double t = 0.0;
+        for (int q = 0; q < kBlock / 32; ++q) t += sm[q][threadIdx.x];
+        scratch[(size_t)blockIdx.x * kLanczosMax + threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < nv) {
+        double t = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) t += __ldcg(scratch + (size_t)b * kLanczosMax + threadIdx.x);
+        h[threadIdx.x] = t;
+        if (alpha_slot >= 0 && threadIdx.x == nv - 1) S[alpha_slot] = t;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+void launch_lanczos_dots(Ctx &c, long long n, const double *Vb, long long stride, int nv, const double *w, double *h,
+                         double *scratch, double *S, int alpha_slot) {
+    if (nv < 1 || nv > kLanczosMax) throw std::invalid_argument("Lanczos basis size out of range");
+    const int grid = std::min(grid_for(n, 2, c), 512);
+    lanczos_dots_kernel<<<grid, kBlock, 0, c.stream>>>(n, Vb, stride, nv, w, h, scratch, c.ticket, S, alpha_slot);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) lanczos_update_kernel(long long n, const double *__restrict__ Vb, long long stride, int nv,
+                                                                const double *__restrict__ h, double *__restrict__ w, double *S,
+                                                                int wsq_slot, ReduceScratch rs) {
+    __shared__ double hs[kLanczosMax];
+    if (threadIdx.x < nv) hs[threadIdx.x] = h[threadIdx.x];
+    __syncthreads();
+    double t[1] = {0.0};
+    for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+        double wi = w[i];
+        for (int l = 0; l < nv; ++l) wi = fma(-hs[l], Vb[l * stride + i], wi);
+        w[i] = wi;
+        t[0] = fma(wi, wi, t[0]);
+    }
+    if (wsq_slot >= 0) {
+        if (grid_reduce<1>(t, rs) && threadIdx.x == 0) S[wsq_slot] = t[0];
+    }
+}
+
+void launch_lanczos_update(Ctx &c, long long n, const double *Vb, long long stride, int nv, const double *h, double *w,
+                           double *S, int wsq_slot) {
+    lanczos_update_kernel<<<grid_for(n, 2, c), kBlock, 0, c.stream>>>(n, Vb, stride, nv, h, w, S, wsq_slot, c.rs);
+    LB2_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(kBlock) lanczos_next_kernel(long long n, const double *__restrict__ w, double *__restrict__ out,
+                                                              const double *S, int wsq_slot) {
+    const double f = 1.0 / sqrt(S[wsq_slot]);
+    for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) out[i] = f * w[i];
+}
+
+void launch_lanczos_next(Ctx &c, long long n, const double *w, double *out, const double *S, int wsq_slot) {
+    lanczos_next_kernel<<<grid_for(n, 2, c), kBlock, 0, c.stream>>>(n, w, out, S, wsq_slot);
+    LB2_LAUNCH_CHECK(c);
+}
+
 // =================================================================================================
 // LP cone
 // =================================================================================================

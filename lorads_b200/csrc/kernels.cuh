@@ -90,6 +90,17 @@ void launch_dense_symm(Ctx &c, long long n, int r, int ld, const double *Sp, con
 void launch_spmv_sym(Ctx &c, long long n, const int *adj_ptr, const int *adj_col, const int *adj_pos, const double *S,
                      const double *x, double *y, double c1 = 0.0, const double *sum_slot = nullptr);
 void launch_sum(Ctx &c, long long n, const double *x, double *S, int slot);   // S[slot] = sum x
+// Block Gram-Schmidt steps of the Lanczos process (basis vectors V[l] = Vb + l*stride, l < nv <= kLanczosMax):
+//   dots  : h[l] = V[l] . w for every l in ONE pass over w (deterministic two-level reduction; scratch holds
+//           gridDim * nv partials); h[nv-1] is also copied to S[alpha_slot] when alpha_slot >= 0
+//   update: w -= sum_l h[l] V[l] in one pass; S[wsq_slot] = sum w^2 afterwards when wsq_slot >= 0
+//   next  : out = w / sqrt(S[wsq_slot])
+constexpr int kLanczosMax = 40;
+void launch_lanczos_dots(Ctx &c, long long n, const double *Vb, long long stride, int nv, const double *w, double *h,
+                         double *scratch, double *S, int alpha_slot);
+void launch_lanczos_update(Ctx &c, long long n, const double *Vb, long long stride, int nv, const double *h, double *w,
+                           double *S, int wsq_slot);
+void launch_lanczos_next(Ctx &c, long long n, const double *w, double *out, const double *S, int wsq_slot);
 void launch_dense_symv(Ctx &c, long long n, const double *Sp, const double *x, double *y);
 
 // ------------------------------------------------------------------------------------------------
@@ -187,6 +198,10 @@ void launch_lp_sweep(Ctx &c, const LpDev &L, double rho, const double *b, const 
 // S[slot] = sum_j |min(c_j + a_j^T w, 0)|   (calculate_dual_infeasibility_solver, lorads_solver.c:1015-1023; w = -lambda)
 void launch_lp_dinf(Ctx &c, const LpDev &L, const double *w, double *S, int slot);
 
+// Rank augmentation (AUG_RANK, lorads_solver.c:806-906): dst (n x ld_new, zero-filled) receives the first r_old
+// columns of src (n x ld_old); rows i < n_diag of column (c_diag + i) get diag_val when diag_val != 0
+// (lpRandomDiag, lorads_solver.c:776-786).
+void launch_relayout(Ctx &c, long long n, int r_old, int ld_old, int ld_new, const double *src, double *dst);
 void launch_recip(Ctx &c, double *S, int slot);   // S[slot] = 1/S[slot]
 void launch_scale(Ctx &c, double *x, long long n, double f);   // x *= f
 
