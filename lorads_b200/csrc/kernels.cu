@@ -264,9 +264,11 @@ static void launch_auv_mode(Ctx &c, const ItemListDev &L, const double *U, const
                             double s2, double *o1, double *o2, double *b1, double *b2, double *c1, double *c2) {
     if (MODE == AUV_FROMZ) { launch_auv_tile<MODE, 4, 1>(c, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); return; }
     if (ld > 256) throw std::runtime_error("rank above 256 is not supported by the A(UV^T) kernel yet");
-    const int G = ld <= 32 ? 4 : (ld <= 64 ? 8 : (ld <= 128 ? 16 : 32));
+    // ld <= 4 (column-sharded factors): two lanes cover a row, so a warp works on 16 items at a time
+    const int G = ld <= 4 ? 2 : (ld <= 32 ? 4 : (ld <= 64 ? 8 : (ld <= 128 ? 16 : 32)));
     const int np = (ld + 2 * G - 1) / (2 * G);
     switch (G) {
+    case 2: launch_auv_np<MODE, 2>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
     case 4: launch_auv_np<MODE, 4>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
     case 8: launch_auv_np<MODE, 8>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
     case 16: launch_auv_np<MODE, 16>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
@@ -426,9 +428,10 @@ void launch_spmm(Ctx &c, long long n, int ld, const int *adj_ptr, const int *adj
                  const double *S, const double *X, double a, double b, const double *Z, const double *Z2, double *Y,
                  double *red, const double *cs, double c1) {
     if (ld > 256) throw std::runtime_error("rank above 256 is not supported by the SpMM kernel yet");
-    int G = ld <= 32 ? 4 : (ld <= 64 ? 8 : (ld <= 128 ? 16 : 32));
+    int G = ld <= 4 ? 2 : (ld <= 32 ? 4 : (ld <= 64 ? 8 : (ld <= 128 ? 16 : 32)));
     int np = (ld + 2 * G - 1) / (2 * G);
     switch (G) {
+    case 2: launch_spmm_g<2>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red, cs, c1); break;
     case 4: launch_spmm_g<4>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red, cs, c1); break;
     case 8: launch_spmm_g<8>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red, cs, c1); break;
     case 16: launch_spmm_g<16>(c, np, n, ld, adj_ptr, adj_col, adj_pos, S, X, a, b, Z, Z2, Y, red, cs, c1); break;
@@ -1301,6 +1304,111 @@ __global__ void __launch_bounds__(kBlock) relayout_kernel(long long n, int r_old
 void launch_relayout(Ctx &c, long long n, int r_old, int ld_old, int ld_new, const double *src, double *dst) {
     if (r_old <= 0) return;
     relayout_kernel<<<grid_for(n * r_old, 2, c), kBlock, 0, c.stream>>>(n, r_old, ld_old, ld_new, src, dst);
+    LB2_LAUNCH_CHECK(c);
+}
+
+// =================================================================================================
+// all-reduce over NVLink peer memory
+// =================================================================================================
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kBlock) p2p_push_kernel(P2PDev P, const double *__restrict__ data, long long count) {
+    __shared__ bool last;
+    const unsigned long long e = *P.epoch + 1;
+    const size_t base = ((size_t)(e & 1) * P.world + P.rank) * P.cap;
+    // peer-major striping: consecutive blocks serve different peers so that all NVLink ports are busy at once
+    const int nb = gridDim.x / P.world;                       // blocks per peer (grid is a multiple of world)
+    const int peer = blockIdx.x % P.world, bid = blockIdx.x / P.world;
+    double *dst = P.peer_x[peer] + base;
+    if ((reinterpret_cast<unsigned long long>(data) & 15ull) == 0) {
+        const long long n2 = count >> 1;
+        for (long long q = (long long)bid * kBlock + threadIdx.x; q < n2; q += (long long)nb * kBlock)
+            st2(dst + 2 * q, ld2(data + 2 * q));
+        if ((count & 1) && bid == 0 && threadIdx.x == 0) dst[count - 1] = data[count - 1];
+    } else {
+        for (long long q = (long long)bid * kBlock + threadIdx.x; q < count; q += (long long)nb * kBlock) dst[q] = data[q];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence_system();
+    if (threadIdx.x < P.world) st_release_sys(P.peer_f[threadIdx.x] + (size_t)(e & 1) * P.world + P.rank, e);
+    if (threadIdx.x == 0) *P.ticket = 0u;
+}
+
+__global__ void __launch_bounds__(kBlock) p2p_reduce_kernel(P2PDev P, double *__restrict__ data, long long count) {
+    __shared__ bool last;
+    const unsigned long long e = *P.epoch + 1;
+    const unsigned long long *fl = P.f + (size_t)(e & 1) * P.world;
+    if (threadIdx.x < P.world) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(fl + threadIdx.x) < e) {
+            if (clock64() - t0 > 20000000000LL) __trap();      // ~10 s: a peer is gone; fail loudly instead of hanging
+        }
+    }
+    __syncthreads();
+    const double *src = P.x + (size_t)(e & 1) * P.world * P.cap;
+    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < count; q += (long long)gridDim.x * kBlock) {
+        double t = 0.0;
+        for (int r = 0; r < P.world; ++r) t += __ldcg(src + (size_t)r * P.cap + q);
+        data[q] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(P.ticket + 1, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last && threadIdx.x == 0) { P.ticket[1] = 0u; *P.epoch = e; }
+}
+
+// Small messages (scalars, dot tables): push, arrival wait and the rank-ordered sum in ONE single-CTA kernel, so the
+// whole all-reduce costs one launch plus one NVLink round trip.
+constexpr int kP2PSmall = 1024;
+__global__ void __launch_bounds__(kBlock) p2p_small_kernel(P2PDev P, double *__restrict__ data, int count) {
+    const unsigned long long e = *P.epoch + 1;
+    const size_t set = (size_t)(e & 1) * P.world;
+    for (int q = threadIdx.x; q < count; q += kBlock) {
+        const double v = data[q];
+        for (int r = 0; r < P.world; ++r) P.peer_x[r][(set + P.rank) * P.cap + q] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < P.world) {
+        st_release_sys(P.peer_f[threadIdx.x] + set + P.rank, e);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(P.f + set + threadIdx.x) < e) {
+            if (clock64() - t0 > 20000000000LL) __trap();
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < count; q += kBlock) {
+        double t = 0.0;
+        for (int r = 0; r < P.world; ++r) t += __ldcg(P.x + (set + r) * P.cap + q);
+        data[q] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *P.epoch = e;
+}
+
+void launch_p2p_allreduce(Ctx &c, const P2PDev &P, double *data, long long count) {
+    if ((size_t)count > P.cap) throw std::invalid_argument("p2p all-reduce: message larger than the exchange slot");
+    if (count <= kP2PSmall) {
+        p2p_small_kernel<<<1, kBlock, 0, c.stream>>>(P, data, (int)count);
+        LB2_LAUNCH_CHECK(c);
+        return;
+    }
+    int per_peer = (int)std::min<long long>(16, std::max<long long>(1, count / (2 * kBlock * 4)));
+    p2p_push_kernel<<<per_peer * P.world, kBlock, 0, c.stream>>>(P, data, count);
+    LB2_LAUNCH_CHECK(c);
+    const int rgrid = (int)std::min<long long>(2LL * c.num_sms, std::max<long long>(1, (count + kBlock - 1) / kBlock));
+    p2p_reduce_kernel<<<rgrid, kBlock, 0, c.stream>>>(P, data, count);
     LB2_LAUNCH_CHECK(c);
 }
 

@@ -202,6 +202,28 @@ void launch_lp_dinf(Ctx &c, const LpDev &L, const double *w, double *S, int slot
 // columns of src (n x ld_old); rows i < n_diag of column (c_diag + i) get diag_val when diag_val != 0
 // (lpRandomDiag, lorads_solver.c:776-786).
 void launch_relayout(Ctx &c, long long n, int r_old, int ld_old, int ld_new, const double *src, double *dst);
+// ------------------------------------------------------------------------------------------------
+// One-shot all-reduce over NVLink peer memory (column-sharded runs).  Every rank owns an exchange buffer of
+// 2 sets x world slots x cap doubles and 2 x world arrival flags, mapped into every peer through CUDA IPC.
+//   push  : the rank stores its `count` partial values into slot[myrank] of EVERY peer's buffer (its own included)
+//           and, once all of its stores are fenced, raises flag[myrank] = epoch on every peer;
+//   reduce: waits until the `world` local flags carry the epoch, then adds the slots in rank order (the same order
+//           on every rank, so all ranks hold bit-identical sums) and writes the result back over the input.
+// Two buffer sets alternate with the epoch parity: a peer can be at most one all-reduce ahead, so a slot is never
+// overwritten while its owner still reads it.  The epoch counter lives on the device, which keeps the pair of
+// launches replayable inside a CUDA graph.
+// ------------------------------------------------------------------------------------------------
+struct P2PDev {
+    int world = 1, rank = 0;
+    size_t cap = 0;                               // doubles per slot
+    double *const *peer_x = nullptr;              // [world] exchange buffers (device array of peer pointers)
+    unsigned long long *const *peer_f = nullptr;  // [world] flag arrays
+    double *x = nullptr;                          // this rank's exchange buffer
+    unsigned long long *f = nullptr;              // this rank's flags
+    unsigned long long *epoch = nullptr;          // completed all-reduces (device counter)
+    unsigned int *ticket = nullptr;               // block tickets of the two kernels (2 counters)
+};
+void launch_p2p_allreduce(Ctx &c, const P2PDev &P, double *data, long long count);
 void launch_recip(Ctx &c, double *S, int slot);   // S[slot] = 1/S[slot]
 void launch_scale(Ctx &c, double *x, long long n, double f);   // x *= f
 

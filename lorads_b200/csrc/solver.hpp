@@ -129,6 +129,15 @@ struct Solver {
     // communicator (column sharding)
     int world = 1, myrank = 0;
     void *nccl = nullptr;
+    // one-shot all-reduce over NVLink peer memory (kernels.cuh P2PDev); messages above p2p.cap go through NCCL
+    P2PDev p2p;
+    bool p2p_on = false;
+    DBuf<double> p2p_x;
+    DBuf<unsigned long long> p2p_f, p2p_epoch;
+    DBuf<unsigned int> p2p_ticket;
+    DBuf<double *> p2p_peer_x;
+    DBuf<unsigned long long *> p2p_peer_f;
+    std::vector<void *> p2p_opened;      // peer mappings to close
     std::vector<std::vector<int>> my_cols;   // per cone: global column ids held here
 
     // problem constants / convergence state (lorads_solver fields, def_lorads_solver.h:76-105)
