@@ -594,6 +594,12 @@ void Solver::lbfgs_direction(long long counter) {
     launch_neg_if_nonneg(ctx, Nt, D, G.p, S.p, SL_DG);
 }
 
+bool Solver::p12_from_rows() const {
+    // single cone covering every constraint, sparse scratch, no rank-one objective part: row m of q1 / q2 is the
+    // complete objective term, so the all-reduce of [q1 | q2] already delivers p1 and p2
+    return single_identity && !cones[0].dense_path && cones[0].c_rank1 == 0.0 && nLp == 0;
+}
+
 void Solver::q12p12() {
     // ALMCalq12p12, lorads_alm.c:540-560: q1 = 2 A(sym(R D^T)), p1 = 2 <C, sym(R D^T)>, q2 = A(D D^T), p2 = <C, D D^T>
     LB2_CUDA(cudaMemsetAsync(S.p + SL_P1, 0, 2 * sizeof(double), ctx.stream));
@@ -601,7 +607,14 @@ void Solver::q12p12() {
         // row m of the outputs is the objective row; its value is also accumulated into the P1 / P2 slots.
         // Sharded: q1 and q2 are contiguous, one all-reduce completes both (P1 / P2 are reduced by the caller).
         cone_auv_dual(cones[0], R.p, U.p, q1.p, q2.p, S.p + SL_P1, S.p + SL_P2);
-        if (world > 1) allreduce(q12.p, (long long)(q2.p - q1.p) + m + 1);
+        if (world > 1) {
+            allreduce(q12.p, (long long)(q2.p - q1.p) + m + 1);
+            if (p12_from_rows()) {
+                // the reduced objective rows ARE p1 and p2: no separate scalar all-reduce
+                LB2_CUDA(cudaMemcpyAsync(S.p + SL_P1, q1.p + m, sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+                LB2_CUDA(cudaMemcpyAsync(S.p + SL_P2, q2.p + m, sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+            }
+        }
         lp_q12p12();
         return;
     }
@@ -743,7 +756,7 @@ void Solver::enqueue_front(double rho, long long counter) {
     (void)rho;     // read by the kernels from S[SL_RHO] (push_scalars)
     lbfgs_direction(counter);
     q12p12();
-    if (world > 1) allreduce(S.p + SL_P1, 2);
+    if (world > 1 && !p12_from_rows()) allreduce(S.p + SL_P1, 2);
     launch_linesearch_dots(ctx, m, b.p, s.p, lam.p, S.p + SL_RHO, q1.p, q2.p, S.p, SL_LS);
 }
 
@@ -758,18 +771,19 @@ void Solver::enqueue_back(double rho, double tau) {
     launch_alm_step(ctx, Nt, S.p + SL_TAU, G.p, U.p, R.p, lb_y[head].p, lb_s[head].p);
     launch_alm_m_update(ctx, m, S.p + SL_TAU, q1.p, q2.p, s.p, lam.p, b.p, S.p + SL_RHO, M1.p);
     grad_from_M1(*this);
-    if (world > 1) allreduce(S.p + kNumSlots, 2 * (nCones + 1));
     // setlbfgsHisTwo, lorads_alm.c:657-678: y += G_new, beta = 1/<y,s>, advance the ring
     if (vf_lbfgs && lbfgs_len == 2) {
         const int other = (head + 1) % 2;
         launch_lbfgs_pair(ctx, Nt, true, lb_y[head].p, G.p, lb_s[head].p, lb_y[other].p, lb_s[other].p, S.p, SL_VF_D,
                           SL_BETA0 + head, SL_VF_YY + head, world == 1);
         if (world > 1) {
-            allreduce(S.p + SL_VF_D, 8);
+            // one all-reduce for the 8 dots (slots 64..71) and the per-cone gradient sums (slots 80..): 72..79 are unused
+            allreduce(S.p + SL_VF_D, (kNumSlots - SL_VF_D) + 2 * (nCones + 1));
             launch_lbfgs_pair_finalize(ctx, S.p, SL_VF_D, SL_BETA0 + head, SL_VF_YY + head);
         }
         vf_valid = true;
     } else {
+        if (world > 1) allreduce(S.p + kNumSlots, 2 * (nCones + 1));
         launch_axpby_dot(ctx, Nt, lb_y[head].p, coef_const(1.0), lb_y[head].p, coef_const(1.0), G.p, lb_s[head].p, S.p,
                          SL_BETA0 + head, world == 1);
         if (world > 1) {

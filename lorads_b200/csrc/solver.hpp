@@ -24,7 +24,8 @@ enum Slot : int {
     SL_NEGALPHA0 = 32,    // 32..47  -alpha of the L-BFGS two-loop, per history node
     SL_BETA0 = 48,        // 48..63  beta = 1/<y,s> per history node
     SL_VF_D = 64,         // 64..71 Gram dots of the vector-free L-BFGS (see launch_lbfgs_pair)
-    SL_VF_YY = 72,        // 72..73 y.y of the two history nodes
+    SL_VF_YY = 29,        // 29..30 y.y of the two history nodes (kept away from 64..79 so that one all-reduce can
+                          // cover the dot table and the per-cone gradient sums that follow kNumSlots)
     kNumSlots = 80        // followed by 2 slots per cone (sum G.G, sum G.Z2 of that cone) and 2 for the LP block
 };
 constexpr int kMaxLbfgs = 16;
@@ -187,6 +188,7 @@ struct Solver {
     void lbfgs_direction(long long counter);
     void q12p12();
     void lp_q12p12();
+    bool p12_from_rows() const;
     void primal_infeasibility(const double *Rm);                                 // fills S_host[SL_PINF] lazily
     double cal_obj(const double *Rm);                                            // <C, R R^T> / scaleObjHis
     double cal_dual_obj();
