@@ -74,7 +74,11 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def mark(self):
+        """Start of the timed region: nvidia-smi is already running (it needs ~0.2 s to deliver its first line)."""
+        self.t0 = time.time()
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -84,9 +88,14 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t1 = time.time()
+        t0 = getattr(self, "t0", 0.0)
+        inside = [ln for (ts, ln) in self.lines if t0 <= ts <= t1 + 0.05]
+        if not inside and self.lines:
+            inside = [self.lines[-1][1]]      # region shorter than the sampling period: closest sample (still under load)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -246,12 +255,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing ----------------
+    sampler = ClockSampler(local)
+    sampler.start()        # started before the warm-up so that samples are flowing when the timed region begins
     S.alm_prepare(rho)
     S.time_alm_inner_iters(rho, max(3, args.warmup))
     S.alm_prepare(rho)     # same start for every arm: ALG_START state of the random point advanced by the warm-up
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark()
     l0 = S.launches
     sec, done = S.time_alm_inner_iters(rho, args.steps)
     launches = S.launches - l0
@@ -312,6 +322,33 @@ def run_ours(args):
                 "peak_source": peak_src, "alg_bytes_per_launch": kb[dom][1],
                 "launch_ms": kt[dom], "kernels": kernels}
 
+    # ---------------- the other BASELINE.json metrics on the same workload (N=1, informational) ----------------
+    secondary = None
+    if world == 1:
+        try:
+            secondary = {}
+            # CG iterations/s of the ADMM block solve (LORADSUpdateSDPVarOne): tolerance 0 forces exactly 60 iterations
+            S.admm_init_constr()
+            S.update_sdp_var_one("U", "V", rho, 0.0, 5)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            its = S.update_sdp_var_one("U", "V", rho, 0.0, 60)
+            torch.cuda.synchronize()
+            secondary["cg_iterations_per_second"] = its / (time.perf_counter() - t0)
+            # wall time of a whole solve to DIMACS 1e-5 (default parameters, fresh solver, data already on the host)
+            if WORKLOAD is WORKLOADS["cfg2"]:
+                from lorads_b200.capi import default_params
+                S2 = Solver(inst, device=local)
+                with c_stdout_to_stderr():
+                    res = S2.solve(default_params())
+                S2.close()
+                secondary["whole_solve"] = {"seconds_to_dimacs_1e-5": res["solveSeconds"], "alm_inner_iterations": res["almInnerIter"],
+                                            "admm_iterations": res["admmIter"], "status": res["status"],
+                                            "pInfeasL1": res["pInfeasL1"], "dInfeasL1": res["dInfeasL1"], "pdGap": res["pdGap"],
+                                            "final_rank": res["finalRank0"]}
+        except Exception as e:
+            log("secondary metrics failed:", e)
+
     # ---------------- CPU baseline (bounded sample) ----------------
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -327,6 +364,7 @@ def run_ours(args):
         cpu = {"value": None, "unit": "iterations/s", "cores": 1, "kind": "reference", "sample": "not run"}
 
     line = {
+        "secondary": secondary,
         "metric": "alm_inner_iterations_per_second", "value": value, "unit": "iterations/s", "n_gpus": world,
         "steps": done, "warmup": max(3, args.warmup), "ms_per_step": 1e3 * sec / done, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
