@@ -115,7 +115,9 @@ EDGE_CASES = {
     # rank above 32 / 64: wider lane groups of the gather kernels (ld = 40, 72)
     "maxcut_rank40": (lambda: sdpa.maxcut(400, 3000, 43), dict(times_log_rank=6.5)),
     "maxcut_rank72": (lambda: sdpa.maxcut(400, 3000, 44), dict(times_log_rank=12.0)),
+    # ld = 4: the two-lane groups of the gather kernels (also what an 8-way column shard of a rank-24 factor sees)
     "rank_one": (lambda: sdpa.maxcut(300, 900, 45), dict(times_log_rank=0.1)),
+    "maxcut_rank4": (lambda: sdpa.maxcut(600, 4000, 53), dict(times_log_rank=0.6)),
     # isolated vertices: zero diagonal entries of C are dropped by the reader, pattern still has the diagonal
     "maxcut_isolated": (lambda: sdpa.maxcut(200, 60, 46), {}),
     # m > n, single-entry off-diagonal constraints, diagonal C
