@@ -50,10 +50,13 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
                                                            const double *__restrict__ V, int ld, double scale1,
                                                            double scale2, double *__restrict__ out1,
                                                            double *__restrict__ out2, double *obj1, double *obj2,
-                                                           double *carry1, double *carry2, unsigned int *ticket) {
-    constexpr bool DUAL = (MODE == AUV_DUAL);
+                                                           double *carry1, double *carry2, unsigned int *ticket,
+                                                           double *__restrict__ out3, double *carry3) {
+    constexpr bool TRI = (MODE == AUV_TRI);                 // DUAL + third output A(U U^T) (scale 1)
+    constexpr bool DUAL = (MODE == AUV_DUAL) || TRI;
     __shared__ double sp1[TILE];
     __shared__ double sp2[DUAL ? TILE : 1];
+    __shared__ double sp3[TRI ? TILE : 1];
     __shared__ double sred[8];
     __shared__ bool s_last;
 
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
         for (int s_ = 0; s_ < IPG; ++s_) {
             const int k = t0 + g * IPG + s_;
             const bool live = k < t1;
-            double a1 = 0.0, a2 = 0.0, a3 = 0.0, cf = 0.0;
+            double a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, cf = 0.0;
             bool diag = true;
             if (live) {
                 const int i = L.irow[k], j = L.icol[k];
@@ -127,6 +130,7 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
                         a1 = fma(x[q].x, y[q].x, a1); a1 = fma(x[q].y, y[q].y, a1);          // U_i . V_j
                         a2 = fma(p[q].x, qv[q].x, a2); a2 = fma(p[q].y, qv[q].y, a2);        // U_j . V_i
                         if constexpr (DUAL) { a3 = fma(qv[q].x, y[q].x, a3); a3 = fma(qv[q].y, y[q].y, a3); }  // V_i . V_j
+                        if constexpr (TRI) { a4 = fma(x[q].x, p[q].x, a4); a4 = fma(x[q].y, p[q].y, a4); }      // U_i . U_j
                     }
                 }
                 pi = i; pj = j;
@@ -134,12 +138,14 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
             a1 = group_sum<G>(a1);
             if constexpr (MODE != AUV_SAME) a2 = group_sum<G>(a2);
             if constexpr (DUAL) a3 = group_sum<G>(a3);
+            if constexpr (TRI) a4 = group_sum<G>(a4);
             if (live && gl == 0) {
                 if constexpr (MODE == AUV_SAME) {
                     sp1[k - t0] = scale1 * cf * a1;
                 } else {
                     sp1[k - t0] = scale1 * cf * (diag ? a1 : (0.5 * a1 + 0.5 * a2));
                     if constexpr (DUAL) sp2[k - t0] = scale2 * cf * a3;
+                    if constexpr (TRI) sp3[k - t0] = cf * a4;
                 }
             }
         }
@@ -149,10 +155,11 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
     const int row_lo = L.tile_row_lo[tile], row_hi = L.tile_row_hi[tile];
     const int nrows = row_hi - row_lo + 1;
     const int nit = t1 - t0;
-    auto emit = [&](int r, bool complete, double v1, double v2) {
+    auto emit = [&](int r, bool complete, double v1, double v2, double v3) {
         if (complete) {
             out1[r] = v1;
             if constexpr (DUAL) out2[r] = v2;
+            if constexpr (TRI) out3[r] = v3;
             if (r == L.obj_row) {
                 if (obj1) *obj1 += v1;
                 if constexpr (DUAL) { if (obj2) *obj2 += v2; }
@@ -161,30 +168,34 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
             const int slot = (r == row_lo) ? 2 * tile : 2 * tile + 1;
             carry1[slot] = v1;
             if constexpr (DUAL) carry2[slot] = v2;
+            if constexpr (TRI) carry3[slot] = v3;
         }
     };
 
     if (nrows == 1) {
         // the whole tile belongs to one row: block reduction in a fixed order
-        double v1 = 0.0, v2 = 0.0;
+        double v1 = 0.0, v2 = 0.0, v3 = 0.0;
         for (int k = tid; k < nit; k += kBlock) {
             v1 += sp1[k];
             if constexpr (DUAL) v2 += sp2[k];
+            if constexpr (TRI) v3 += sp3[k];
         }
         v1 = block_sum(v1, sred);
         if constexpr (DUAL) v2 = block_sum(v2, sred);
-        if (tid == 0) emit(row_lo, (L.ptr[row_lo] >= t0) && (L.ptr[row_lo + 1] <= t1), v1, v2);
+        if constexpr (TRI) v3 = block_sum(v3, sred);
+        if (tid == 0) emit(row_lo, (L.ptr[row_lo] >= t0) && (L.ptr[row_lo + 1] <= t1), v1, v2, v3);
     } else if (nrows * 8 >= nit) {
         // short rows: one thread per row, sequential (deterministic) sum
         for (int r = row_lo + tid; r <= row_hi; r += kBlock) {
             const int pa = L.ptr[r], pb = L.ptr[r + 1];
             const int a = max(pa, t0) - t0, b = min(pb, t1) - t0;
-            double v1 = 0.0, v2 = 0.0;
+            double v1 = 0.0, v2 = 0.0, v3 = 0.0;
             for (int k = a; k < b; ++k) {
                 v1 += sp1[k];
                 if constexpr (DUAL) v2 += sp2[k];
+                if constexpr (TRI) v3 += sp3[k];
             }
-            emit(r, pa >= t0 && pb <= t1, v1, v2);
+            emit(r, pa >= t0 && pb <= t1, v1, v2, v3);
         }
     } else {
         // longer rows: one warp per row
@@ -192,14 +203,16 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
         for (int r = row_lo + w; r <= row_hi; r += kBlock / 32) {
             const int pa = L.ptr[r], pb = L.ptr[r + 1];
             const int a = max(pa, t0) - t0, b = min(pb, t1) - t0;
-            double v1 = 0.0, v2 = 0.0;
+            double v1 = 0.0, v2 = 0.0, v3 = 0.0;
             for (int k = a + lane; k < b; k += 32) {
                 v1 += sp1[k];
                 if constexpr (DUAL) v2 += sp2[k];
+                if constexpr (TRI) v3 += sp3[k];
             }
             v1 = warp_sum(v1);
             if constexpr (DUAL) v2 = warp_sum(v2);
-            if (lane == 0) emit(r, pa >= t0 && pb <= t1, v1, v2);
+            if constexpr (TRI) v3 = warp_sum(v3);
+            if (lane == 0) emit(r, pa >= t0 && pb <= t1, v1, v2, v3);
         }
     }
 
@@ -216,17 +229,20 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
         for (int sidx = w; sidx < (int)L.n_split; sidx += kBlock / 32) {
             const int row = L.split_row[sidx], fs = L.split_first_slot[sidx], ta = L.split_tile_a[sidx];
             const int ne = L.split_tile_b[sidx] - ta + 1;
-            double v1 = 0.0, v2 = 0.0;
+            double v1 = 0.0, v2 = 0.0, v3 = 0.0;
             for (int e = lane; e < ne; e += 32) {
                 const int slot = (e == 0) ? fs : 2 * (ta + e);
                 v1 += __ldcg(carry1 + slot);
                 if constexpr (DUAL) v2 += __ldcg(carry2 + slot);
+                if constexpr (TRI) v3 += __ldcg(carry3 + slot);
             }
             v1 = warp_sum(v1);
             if constexpr (DUAL) v2 = warp_sum(v2);
+            if constexpr (TRI) v3 = warp_sum(v3);
             if (lane == 0) {
                 out1[row] = v1;
                 if constexpr (DUAL) out2[row] = v2;
+                if constexpr (TRI) out3[row] = v3;
                 if (row == L.obj_row) {
                     if (obj1) *obj1 += v1;
                     if constexpr (DUAL) { if (obj2) *obj2 += v2; }
@@ -239,54 +255,60 @@ __global__ void __launch_bounds__(kBlock) auv_items_kernel(ItemListDev L, const 
 
 template <int MODE, int G, int NP>
 static void launch_auv_tile(Ctx &c, const ItemListDev &L, const double *U, const double *V, int ld, double s1, double s2,
-                            double *o1, double *o2, double *b1, double *b2, double *c1, double *c2) {
+                            double *o1, double *o2, double *b1, double *b2, double *c1, double *c2, double *o3 = nullptr,
+                            double *c3 = nullptr) {
     const int grid = (int)L.n_tiles;
     if (L.tile == kAuvTileSmall)
-        auv_items_kernel<MODE, G, NP, kAuvTileSmall><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2, c.ticket);
+        auv_items_kernel<MODE, G, NP, kAuvTileSmall><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2, c.ticket, o3, c3);
     else
-        auv_items_kernel<MODE, G, NP, kAuvTileLarge><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2, c.ticket);
+        auv_items_kernel<MODE, G, NP, kAuvTileLarge><<<grid, kBlock, 0, c.stream>>>(L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2, c.ticket, o3, c3);
     LB2_LAUNCH_CHECK(c);
 }
 
 template <int MODE, int G>
 static void launch_auv_np(Ctx &c, int np, const ItemListDev &L, const double *U, const double *V, int ld, double s1,
-                          double s2, double *o1, double *o2, double *b1, double *b2, double *c1, double *c2) {
+                          double s2, double *o1, double *o2, double *b1, double *b2, double *c1, double *c2, double *o3,
+                          double *c3) {
     switch (np) {
-    case 1: launch_auv_tile<MODE, G, 1>(c, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
-    case 2: launch_auv_tile<MODE, G, 2>(c, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
-    case 3: launch_auv_tile<MODE, G, 3>(c, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
-    default: launch_auv_tile<MODE, G, 4>(c, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
+    case 1: launch_auv_tile<MODE, G, 1>(c, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2, o3, c3); break;
+    case 2: launch_auv_tile<MODE, G, 2>(c, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2, o3, c3); break;
+    case 3: launch_auv_tile<MODE, G, 3>(c, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2, o3, c3); break;
+    default: launch_auv_tile<MODE, G, 4>(c, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2, o3, c3); break;
     }
 }
 
 template <int MODE>
 static void launch_auv_mode(Ctx &c, const ItemListDev &L, const double *U, const double *V, int ld, double s1,
-                            double s2, double *o1, double *o2, double *b1, double *b2, double *c1, double *c2) {
+                            double s2, double *o1, double *o2, double *b1, double *b2, double *c1, double *c2,
+                            double *o3 = nullptr, double *c3 = nullptr) {
     if (MODE == AUV_FROMZ) { launch_auv_tile<MODE, 4, 1>(c, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); return; }
     if (ld > 256) throw std::runtime_error("rank above 256 is not supported by the A(UV^T) kernel yet");
     // ld <= 4 (column-sharded factors): two lanes cover a row, so a warp works on 16 items at a time
     const int G = ld <= 4 ? 2 : (ld <= 32 ? 4 : (ld <= 64 ? 8 : (ld <= 128 ? 16 : 32)));
     const int np = (ld + 2 * G - 1) / (2 * G);
     switch (G) {
-    case 2: launch_auv_np<MODE, 2>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
-    case 4: launch_auv_np<MODE, 4>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
-    case 8: launch_auv_np<MODE, 8>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
-    case 16: launch_auv_np<MODE, 16>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
-    default: launch_auv_np<MODE, 32>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2); break;
+    case 2: launch_auv_np<MODE, 2>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2, o3, c3); break;
+    case 4: launch_auv_np<MODE, 4>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2, o3, c3); break;
+    case 8: launch_auv_np<MODE, 8>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2, o3, c3); break;
+    case 16: launch_auv_np<MODE, 16>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2, o3, c3); break;
+    default: launch_auv_np<MODE, 32>(c, np, L, U, V, ld, s1, s2, o1, o2, b1, b2, c1, c2, o3, c3); break;
     }
 }
 
 void launch_auv(Ctx &c, AuvMode mode, const ItemListDev &L, const double *U, const double *V, int ld, double scale1,
-                double scale2, double *out1, double *out2, double *carry1, double *carry2, double *obj1, double *obj2) {
+                double scale2, double *out1, double *out2, double *carry1, double *carry2, double *obj1, double *obj2,
+                double *out3, double *carry3) {
     if (L.has_empty_rows) {
         LB2_CUDA(cudaMemsetAsync(out1, 0, sizeof(double) * L.n_rows, c.stream));
-        if (mode == AUV_DUAL) LB2_CUDA(cudaMemsetAsync(out2, 0, sizeof(double) * L.n_rows, c.stream));
+        if (mode == AUV_DUAL || mode == AUV_TRI) LB2_CUDA(cudaMemsetAsync(out2, 0, sizeof(double) * L.n_rows, c.stream));
+        if (mode == AUV_TRI) LB2_CUDA(cudaMemsetAsync(out3, 0, sizeof(double) * L.n_rows, c.stream));
     }
     if (L.n_items == 0) return;
     switch (mode) {
     case AUV_SAME: launch_auv_mode<AUV_SAME>(c, L, U, V, ld, scale1, scale2, out1, out2, obj1, obj2, carry1, carry2); break;
     case AUV_PAIR: launch_auv_mode<AUV_PAIR>(c, L, U, V, ld, scale1, scale2, out1, out2, obj1, obj2, carry1, carry2); break;
     case AUV_DUAL: launch_auv_mode<AUV_DUAL>(c, L, U, V, ld, scale1, scale2, out1, out2, obj1, obj2, carry1, carry2); break;
+    case AUV_TRI: launch_auv_mode<AUV_TRI>(c, L, U, V, ld, scale1, scale2, out1, out2, obj1, obj2, carry1, carry2, out3, carry3); break;
     case AUV_FROMZ: launch_auv_mode<AUV_FROMZ>(c, L, U, V, ld, scale1, scale2, out1, out2, obj1, obj2, carry1, carry2); break;
     }
 }

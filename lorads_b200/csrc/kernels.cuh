@@ -33,14 +33,15 @@ enum AuvMode {
     AUV_SAME = 0,   // U == V            : z = U_i . U_j
     AUV_PAIR = 1,   // U != V            : z = (U_i.V_j + U_j.V_i)/2
     AUV_DUAL = 2,   // (R,D) and (D,D)   : z1 = (R_i.D_j + R_j.D_i)/2 , z2 = D_i.D_j  (one gather pass)
-    AUV_FROMZ = 3   // dense path        : z is materialised (packed), item.irow is the packed position
+    AUV_FROMZ = 3,  // dense path        : z is materialised (packed), item.irow is the packed position
+    AUV_TRI = 4     // AUV_DUAL + out3 = A(R R^T) from the rows the dual pass already holds (z3 = R_i.R_j, scale 1)
 };
 
 // out1/out2: n_rows values each; carry: 2*n_tiles doubles per output.  U,V row-major n x ld (ld % 4 == 0).
 // obj1/obj2 (may be null): the value of the objective row is ADDED to *obj1 / *obj2 as well.
 void launch_auv(Ctx &c, AuvMode mode, const ItemListDev &L, const double *U, const double *V, int ld,
                 double scale1, double scale2, double *out1, double *out2, double *carry1, double *carry2,
-                double *obj1 = nullptr, double *obj2 = nullptr);
+                double *obj1 = nullptr, double *obj2 = nullptr, double *out3 = nullptr, double *carry3 = nullptr);
 
 // dst[idx ? idx[a] : a] (+)= alpha * src[a]  for a < n ; when obj_dst != nullptr: *obj_dst += alpha*src[n]
 void launch_scatter_add(Ctx &c, double *dst, const double *src, const int *idx, long long n, double alpha,

@@ -199,7 +199,7 @@ void Solver::preprocess() {
         K.listAC.upload(L.listAC);
         K.obj_item_begin = L.listAC.ptr[L.n_act];
         const size_t ntile = (size_t)std::max<long long>(1, K.listAC.dev.n_tiles);
-        K.carry1.alloc(2 * ntile); K.carry2.alloc(2 * ntile);
+        K.carry1.alloc(2 * ntile); K.carry2.alloc(2 * ntile); K.carry3.alloc(2 * ntile);
         K.C_onP.upload(L.C_onP);
         K.S.alloc((size_t)K.np);
         K.T_ptr.upload(L.T_ptr); K.T_con.upload(L.T_con); K.T_val.upload(L.T_val);
@@ -247,7 +247,7 @@ void Solver::preprocess() {
     single_identity = (nCones == 1 && cones[0].identity_act);
     b.alloc((size_t)m + 1); lam.alloc((size_t)m + 1); s.alloc((size_t)m + 1);
     const size_t mpad = ((size_t)m + 2) & ~(size_t)1;     // even stride keeps q2 16-byte aligned
-    q12.alloc(2 * mpad); q1.p = q12.p; q2.p = q12.p + mpad;
+    q12.alloc(3 * mpad); q1.p = q12.p; q2.p = q12.p + mpad; q3.p = q12.p + 2 * mpad;
     M1.alloc((size_t)m + 1); cvfull.alloc((size_t)m + 1);
     LB2_CUDA(cudaMemcpy(b.p, b_h.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
     preprocessed = true;
@@ -600,20 +600,40 @@ bool Solver::p12_from_rows() const {
     return single_identity && !cones[0].dense_path && cones[0].c_rank1 == 0.0 && nLp == 0;
 }
 
+bool Solver::tri_ok() const { return single_identity && !cones[0].dense_path && nLp == 0; }
+
 void Solver::q12p12() {
     // ALMCalq12p12, lorads_alm.c:540-560: q1 = 2 A(sym(R D^T)), p1 = 2 <C, sym(R D^T)>, q2 = A(D D^T), p2 = <C, D D^T>
     LB2_CUDA(cudaMemsetAsync(S.p + SL_P1, 0, 2 * sizeof(double), ctx.stream));
     if (single_identity) {
         // row m of the outputs is the objective row; its value is also accumulated into the P1 / P2 slots.
         // Sharded: q1 and q2 are contiguous, one all-reduce completes both (P1 / P2 are reduced by the caller).
-        cone_auv_dual(cones[0], R.p, U.p, q1.p, q2.p, S.p + SL_P1, S.p + SL_P2);
+        const bool tri = tri_ok();
+        if (tri) {
+            // third output of the same gather pass: A(RR^T) of the CURRENT point, i.e. the exact constrValSum and the
+            // primal infeasibility that updateDimacsALM recomputes every iteration (lorads_alg_common.c:250-258)
+            ConeDev &K = cones[0];
+            launch_auv(ctx, AUV_TRI, K.listAC.dev, R.p + K.off, U.p + K.off, K.ld, 2.0, 1.0, q1.p, q2.p, K.carry1.p, K.carry2.p,
+                       S.p + SL_P1, S.p + SL_P2, q3.p, K.carry3.p);
+            if (K.c_rank1 != 0.0) {
+                launch_colsum(ctx, K.n, K.ld, R.p + K.off, K.csA.p, K.cs_scratch.p);
+                launch_colsum(ctx, K.n, K.ld, U.p + K.off, K.csB.p, K.cs_scratch.p);
+                launch_rank1_obj(ctx, K.ld, K.csA.p, K.csB.p, 2.0 * K.c_rank1, S.p + SL_P1, K.c_rank1, S.p + SL_P2);
+            }
+        } else {
+            cone_auv_dual(cones[0], R.p, U.p, q1.p, q2.p, S.p + SL_P1, S.p + SL_P2);
+        }
         if (world > 1) {
-            allreduce(q12.p, (long long)(q2.p - q1.p) + m + 1);
+            allreduce(q12.p, (long long)((tri ? q3.p : q2.p) - q1.p) + m + 1);
             if (p12_from_rows()) {
                 // the reduced objective rows ARE p1 and p2: no separate scalar all-reduce
                 LB2_CUDA(cudaMemcpyAsync(S.p + SL_P1, q1.p + m, sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
                 LB2_CUDA(cudaMemcpyAsync(S.p + SL_P2, q2.p + m, sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
             }
+        }
+        if (tri) {
+            LB2_CUDA(cudaMemcpyAsync(s.p, q3.p, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx.stream));
+            launch_resid_sq(ctx, m, b.p, s.p, S.p, SL_PINF);
         }
         lp_q12p12();
         return;
@@ -765,7 +785,7 @@ long long Solver::finish_front(double rho, double *tau, double *p12) {
     return line_search(rho, S_host + SL_LS, p12[0], p12[1], tau);
 }
 
-void Solver::enqueue_back(double rho, double tau) {
+void Solver::enqueue_back(double rho, double tau, bool front_follows) {
     (void)rho; (void)tau;     // both are read from the scalar slots S[SL_RHO], S[SL_TAU] (push_scalars)
     const int head = lb_head;
     launch_alm_step(ctx, Nt, S.p + SL_TAU, G.p, U.p, R.p, lb_y[head].p, lb_s[head].p);
@@ -792,7 +812,8 @@ void Solver::enqueue_back(double rho, double tau) {
         }
     }
     lb_head = (head + 1) % lbfgs_len;
-    primal_infeasibility(R.p);
+    // the front half that follows in the same submission recomputes A(RR^T) inside its dual gather pass
+    if (!(front_follows && tri_ok())) primal_infeasibility(R.p);
 }
 
 void Solver::finish_back(double *lagNormSq, double *pinf1) {
@@ -808,7 +829,7 @@ void Solver::iter_back_front(double rho, double tau, long long next_counter) {
     // NCCL all-reduces are captured into the graph too (validated at 2 ranks); LORADS_B200_NO_GRAPH_NCCL=1 opts out
     static const bool graph_nccl = getenv("LORADS_B200_NO_GRAPH_NCCL") == nullptr;
     if (!use_graphs || (world > 1 && !graph_nccl)) {
-        enqueue_back(rho, tau);
+        enqueue_back(rho, tau, next_counter >= 0);
         if (next_counter >= 0) enqueue_front(rho, next_counter);
         read_slots();
         return;
@@ -824,7 +845,7 @@ void Solver::iter_back_front(double rho, double tau, long long next_counter) {
         cudaGraph_t graph = nullptr;
         LB2_CUDA(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal));
         try {
-            enqueue_back(rho, tau);
+            enqueue_back(rho, tau, next_counter >= 0);
             if (next_counter >= 0) enqueue_front(rho, next_counter);
             LB2_CUDA(cudaMemcpyAsync(S_host, S.p, slot_bytes, cudaMemcpyDeviceToHost, ctx.stream));
         } catch (...) {

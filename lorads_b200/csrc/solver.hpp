@@ -53,7 +53,7 @@ struct ConeDev {
     std::vector<int32_t> P_row_h, P_col_h;          // kept for lb2_get_pattern / dual infeasibility
     DBuf<int> act_idx;
     ItemListBufs listA, listAC;
-    DBuf<double> carry1, carry2;
+    DBuf<double> carry1, carry2, carry3;
     DBuf<double> C_onP, S, T_val;
     DBuf<int> T_ptr, T_con, adj_ptr, adj_col, adj_pos;
     DBuf<long long> D_pos;
@@ -101,7 +101,7 @@ struct Solver {
 
     // m-vectors (capacity m + 1: slot m receives the objective value of fused evaluations)
     DBuf<double> b, lam, s, q12, M1, cvfull;   // q12 = [q1 (m+1) | q2 (m+1)] contiguous: one all-reduce covers both
-    struct VecView { double *p = nullptr; } q1, q2;
+    struct VecView { double *p = nullptr; } q1, q2, q3;    // q3: A(RR^T) as third output of the fused pass
     // N-vectors
     long long N = 0;      // cone part: sum of n * ld
     long long Nt = 0;     // N + nLp: length of the concatenated [cones | LP] vectors
@@ -189,6 +189,7 @@ struct Solver {
     void q12p12();
     void lp_q12p12();
     bool p12_from_rows() const;
+    bool tri_ok() const;      // the dual gather pass can also deliver A(RR^T) (single cone over all constraints, sparse scratch)
     void primal_infeasibility(const double *Rm);                                 // fills S_host[SL_PINF] lazily
     double cal_obj(const double *Rm);                                            // <C, R R^T> / scaleObjHis
     double cal_dual_obj();
@@ -200,7 +201,7 @@ struct Solver {
     // phases
     void enqueue_front(double rho, long long counter);
     long long finish_front(double rho, double *tau, double *p12);
-    void enqueue_back(double rho, double tau);
+    void enqueue_back(double rho, double tau, bool front_follows = false);
     void finish_back(double *lagNormSq, double *pinf1);
     long long run_inner_iters(double rho, long long iters, double *out);
     int alm_inner_front(double rho, long long counter, double *tau, double *p12, long long *rootNum);

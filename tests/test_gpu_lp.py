@@ -172,6 +172,22 @@ def test_lp_dropin_matches_reference_binary(tmp_path):
     assert a["pinf"] <= 1e-5 and a["gap"] <= 5e-5
 
 
+def test_lp_file_through_the_standalone_cli(tmp_path):
+    """Library reader (LP block included) + solve, no reference tree involved; same result block as the golden solve."""
+    from test_gpu_dropin import parse
+    cli = os.path.join(ROOT, "lorads_b200", "lorads_b200_cli")
+    assert os.path.exists(cli), "build with python -m lorads_b200.build"
+    g, inst = load_golden("lp_twoblock")
+    path = str(tmp_path / "mix.dat-s")
+    sdpa.write_dat_s(inst, path)
+    out = subprocess.run([cli, path, "--quiet"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "lp Cols = 60" in out.stdout
+    got, ref = parse(out.stdout), json.loads(str(g["solve"]))
+    assert abs(got["pobj"] - ref["pobj"]) <= 1e-6 * (1 + abs(ref["pobj"]))
+    assert abs(got["dobj"] - ref["dobj"]) <= 1e-6 * (1 + abs(ref["dobj"]))
+
+
 def test_lp_rejected_with_sharding_and_bad_input():
     from lorads_b200.capi import Lb2Error
     inst = sdpa.add_lp_block(sdpa.maxcut(20, 40, 1), 5, 2)
