@@ -18,6 +18,10 @@
 #include <cstdint>
 #include <numeric>
 #include <stdexcept>
+#include <thread>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace lb2 {
@@ -112,10 +116,23 @@ inline void finish_item_list(ItemList &L) {
     }
 }
 
+// phase timer of the pre-solve (LORADS_B200_PRESOLVE_TIMING=1 prints the split to stderr)
+struct PhaseTimer {
+    bool on = getenv("LORADS_B200_PRESOLVE_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        if (!on) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "  presolve %-28s %8.3f s\n", what, std::chrono::duration<double>(now - t).count());
+        t = now;
+    }
+};
+
 // Build the layout of one cone from the reader's arrays (column 0 = C, column i = A_i).
 inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in, const int64_t *idx, const double *elem,
                                     bool allow_rank_one = true) {
     ConeLayout L;
+    PhaseTimer pt;
     L.n = n; L.m = m;
     const double packedSize = (double)(n * (n + 1) / 2);
     if (beg_in[m + 1] > (int64_t)2000000000) throw std::runtime_error("cone has more than 2^31 non-zeros");
@@ -135,6 +152,7 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
         }
     }
 
+    pt.lap("copy + per-column order");
     // objective norms on the ORIGINAL C (dataMatSparseNrm1/Nrm2Square/NrmInf lorads_sdp_data.c:148-183; the dense
     // variants :227-272 are the same sums over the packed array)
     for (int64_t k = beg_in[0]; k < beg_in[1]; ++k) {
@@ -207,18 +225,26 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
         }
     }
 
+    pt.lap("norms, classes, rows/cols");
     // --- scratch type decision (AConePresolveData, lorads_sdp_conic.c:884-989)
     std::vector<int64_t> keys;     // (col, row) keys of the union pattern
     bool dense = (n < 20) || L.any_dense_coeff;
     if (!dense) {
+        // The entries of one coefficient are already in (col,row) order, so the objective is one sorted run and the
+        // constraints are one more whenever their keys happen to ascend (MaxCut, theta, matrix completion files do):
+        // sort only what is not sorted, then merge the two runs.
         keys.resize(nnz_all);
         for (int64_t k = 0; k < nnz_all; ++k) keys[k] = (int64_t)ecol[k] * n + erow[k];
-        std::sort(keys.begin(), keys.end());
+        auto mid = keys.begin() + beg[1];
+        if (!std::is_sorted(keys.begin(), mid)) std::sort(keys.begin(), mid);
+        if (!std::is_sorted(mid, keys.end())) std::sort(mid, keys.end());
+        std::inplace_merge(keys.begin(), mid, keys.end());
         keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
         double spRatio = (double)keys.size() / packedSize;
         if (spRatio >= 0.1) dense = true;
     }
     L.dense_path = dense;
+    pt.lap("union pattern (sort)");
 
     auto fill_items = [&](ItemList &IL, bool with_obj) {
         IL.has_obj = with_obj;
@@ -286,13 +312,30 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
         if (L.P_col[p] == L.P_row[p]) L.n_diag++;
     }
     // pattern position of every entry (replaces the hash dictionary)
+    // (merge-join: while the keys of consecutive entries ascend, the search continues from the previous hit with a
+    //  galloping step; a binary search over the whole pattern is the fallback for a descending step)
     std::vector<int32_t> epos(nnz_all);
-    for (int64_t k = 0; k < nnz_all; ++k) {
-        int64_t key = (int64_t)ecol[k] * n + erow[k];
-        epos[k] = (int32_t)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin());
+    {
+        int64_t prev_key = -1, prev_pos = 0;
+        for (int64_t k = 0; k < nnz_all; ++k) {
+            const int64_t key = (int64_t)ecol[k] * n + erow[k];
+            int64_t lo, hi;
+            if (key >= prev_key) {
+                lo = prev_pos;
+                int64_t step = 1;
+                hi = lo;
+                while (hi < np && keys[hi] < key) { lo = hi + 1; hi += step; step <<= 1; }
+                if (hi > np) hi = np;
+            } else { lo = 0; hi = prev_pos; }
+            prev_pos = std::lower_bound(keys.begin() + lo, keys.begin() + hi, key) - keys.begin();
+            prev_key = key;
+            epos[k] = (int32_t)prev_pos;
+        }
     }
+    pt.lap("pattern positions");
     fill_items(L.listA, false);
     fill_items(L.listAC, true);
+    pt.lap("item lists");
 
     L.C_onP.assign(np, 0.0);
     for (int64_t k = beg[0]; k < beg[1]; ++k) L.C_onP[epos[k]] += sval[k];
@@ -316,6 +359,7 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
         }
     }
 
+    pt.lap("C on P, T");
     // symmetric adjacency CSR: row i lists (j, p) for every pattern entry (i,j) or (j,i)
     L.adj_ptr.assign(n + 1, 0);
     for (int64_t p = 0; p < np; ++p) {
@@ -329,16 +373,28 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
         // emit in an order that leaves every row sorted by neighbour index: P is sorted by (col,row); the
         // entries (i, j<i) of row i come from pattern columns j ascending, then (i,i), then (j>i, i) from
         // pattern column i with rows ascending.  Two passes keep that order.
+        // The first pass scatters by ROW over the whole array (cache hostile at n = 1e6): it is split over threads by
+        // row range, every thread scans P once and fills only the rows it owns, in the same order as a single scan.
         std::vector<int32_t> cur(L.adj_ptr.begin(), L.adj_ptr.end() - 1);
-        for (int64_t p = 0; p < np; ++p) {           // lower part seen from the row: (row, col<row)
-            int32_t r = L.P_row[p], c = L.P_col[p];
-            if (r != c) { int32_t q = cur[r]++; L.adj_col[q] = c; L.adj_pos[q] = (int32_t)p; }
+        const int nth = (np > 2000000) ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+        auto lower_pass = [&](int64_t r0, int64_t r1) {
+            for (int64_t p = 0; p < np; ++p) {       // lower part seen from the row: (row, col<row)
+                const int32_t r = L.P_row[p], c = L.P_col[p];
+                if (r != c && r >= r0 && r < r1) { int32_t q = cur[r]++; L.adj_col[q] = c; L.adj_pos[q] = (int32_t)p; }
+            }
+        };
+        if (nth == 1) lower_pass(0, n);
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nth; ++t) th.emplace_back(lower_pass, n * t / nth, n * (t + 1) / nth);
+            for (std::thread &x : th) x.join();
         }
         for (int64_t p = 0; p < np; ++p) {           // diagonal and upper part: row c gets (r >= c)
             int32_t r = L.P_row[p], c = L.P_col[p];
             int32_t q = cur[c]++; L.adj_col[q] = r; L.adj_pos[q] = (int32_t)p;
         }
     }
+    pt.lap("adjacency");
     return L;
 }
 

@@ -308,13 +308,20 @@ void Solver::init_vars(long long lbfgsLen, double initRho) {
     alloc_vars();
     // the reference's libc draw order: srand(925); R of every cone (lorads_solver.c:415-446), later U then V of
     // every cone (lorads_solver.c:631-658); each element is rand()/RAND_MAX - rand()/RAND_MAX (:361-370)
-    auto draw = [](std::vector<double> &x) {
+    // glibc's rand() is random() on a 128-byte TYPE_3 state behind a lock; random_r on a private state of the same
+    // size yields the identical stream without the lock (1.7e8 draws at n = 1e6, r = 28)
+    struct random_data rd;
+    char rstate[128];
+    std::memset(&rd, 0, sizeof(rd));
+    initstate_r(925, rstate, sizeof(rstate), &rd);
+    auto draw = [&rd](std::vector<double> &x) {
+        int32_t a, b;
         for (double &v : x) {
-            v = (double)rand() / RAND_MAX;
-            v -= (double)rand() / RAND_MAX;
+            random_r(&rd, &a); random_r(&rd, &b);
+            v = (double)a / RAND_MAX;
+            v -= (double)b / RAND_MAX;
         }
     };
-    srand(925);
     std::vector<double> tmp;
     for (long long c = 0; c < nCones; ++c) {
         tmp.resize((size_t)(blkDims[c] * rank[c]));

@@ -128,3 +128,33 @@ def test_golden_solves_reached_tolerance():
         sol = json.loads(str(g["solve"]))
         assert sol["status"] in (1.0, 2.0)
         assert sol["pinf"] <= 1e-5 and sol["gap"] <= 5e-5
+
+
+def test_host_presolve_is_order_independent():
+    """The union pattern must not depend on the order of the constraints in the file: the pre-solve merges sorted
+    runs when the keys ascend and falls back to a sort / binary search when they do not."""
+    from lorads_b200 import sdpa
+    inst = sdpa.lovasz_theta(120, 900, 3)
+    cone = inst.cones[0]
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(inst.m)
+    counts = np.diff(cone.beg)
+    cols = [np.arange(cone.beg[c], cone.beg[c + 1]) for c in range(inst.m + 1)]
+    order = [cols[0]] + [cols[1 + p] for p in perm]
+    take = np.concatenate(order)
+    beg = np.concatenate([[0], np.cumsum([counts[0]] + [counts[1 + p] for p in perm])]).astype(np.int64)
+    shuffled = sdpa.Cone(n=cone.n, beg=beg, idx=cone.idx[take], elem=cone.elem[take])
+    a, ra, ca = capi.host_presolve(cone, inst.m)
+    b, rb, cb = capi.host_presolve(shuffled, inst.m)
+    assert a == b
+    assert np.array_equal(ra, rb) and np.array_equal(ca, cb)
+    # a sparse objective too (no rank-one shortcut): MaxCut with shuffled constraints
+    mc = sdpa.maxcut(300, 1500, 5).cones[0]
+    counts = np.diff(mc.beg)
+    perm = rng.permutation(300)
+    take = np.concatenate([np.arange(mc.beg[0], mc.beg[1])] + [np.arange(mc.beg[1 + p], mc.beg[2 + p]) for p in perm])
+    beg = np.concatenate([[0], np.cumsum([counts[0]] + [counts[1 + p] for p in perm])]).astype(np.int64)
+    sh = sdpa.Cone(n=mc.n, beg=beg, idx=mc.idx[take], elem=mc.elem[take])
+    a, ra, ca = capi.host_presolve(mc, 300)
+    b, rb, cb = capi.host_presolve(sh, 300)
+    assert a == b and np.array_equal(ra, rb) and np.array_equal(ca, cb)
