@@ -99,18 +99,21 @@ bool Solver::aug_rank(double aug) {
             const long long i = my_cols[c][(size_t)lc] - ro;          // row of the diagonal entry of global column ro + i
             if (i >= 0 && i < rr) pos.push_back((int)(i * K.ld + lc));
         }
-        DBuf<int> dpos;
-        DBuf<double> dval;
+        if (pos.size() > 1024) throw std::runtime_error("rank augmentation: more than 1024 new columns");
+        if (!aug_pos.p) { aug_pos.alloc(1024); aug_val.alloc(1024); }          // allocated once, never freed mid-solve
+        DBuf<int> &dpos = aug_pos;
+        DBuf<double> &dval = aug_val;
         if (!pos.empty()) {
-            dpos.upload(pos);
-            dval.upload(std::vector<double>(pos.size(), 1.0 / std::sqrt((double)rr)));
+            const std::vector<double> vals(pos.size(), 1.0 / std::sqrt((double)rr));
+            LB2_CUDA(cudaMemcpy(dpos.p, pos.data(), sizeof(int) * pos.size(), cudaMemcpyHostToDevice));
+            LB2_CUDA(cudaMemcpy(dval.p, vals.data(), sizeof(double) * pos.size(), cudaMemcpyHostToDevice));
         }
         for (const Pair &p : pairs) {
             launch_relayout(ctx, n, o.r, o.ld, K.ld, p.src->p + o.off, p.dst->p + K.off);
             if (p.diag && !pos.empty())
                 launch_scatter_add(ctx, p.dst->p + K.off, dval.p, dpos.p, (long long)pos.size(), 1.0, false, nullptr);
         }
-        LB2_CUDA(cudaStreamSynchronize(ctx.stream));      // dpos / dval go out of scope
+        LB2_CUDA(cudaStreamSynchronize(ctx.stream));      // dpos / dval are rewritten for the next cone
     }
     if (nLp > 0) {
         // the LP vectors are separate arrays in the reference and survive AUG_RANK untouched
@@ -118,7 +121,8 @@ bool Solver::aug_rank(double aug) {
             if (p.diag)
                 LB2_CUDA(cudaMemcpyAsync(p.dst->p + N, p.src->p + N_old, sizeof(double) * nLp, cudaMemcpyDeviceToDevice, ctx.stream));
     }
-    LB2_CUDA(cudaStreamSynchronize(ctx.stream));          // the old buffers are released on return
+    LB2_CUDA(cudaStreamSynchronize(ctx.stream));
+    for (DBuf<double> *o : {&oR, &oU, &oV, &oG, &oM}) retire(*o);     // parked, not freed (see Solver::retired)
     return check_all_rank_max(aug);
 }
 
@@ -501,6 +505,9 @@ void Solver::dual_infeasibility() {
     // calculate_dual_infeasibility_solver, lorads_solver.c:1007-1037.  The Lanczos basis, the mat-vec
     // (S = C - A^*(lambda) on the pattern) and the re-orthogonalisation all stay on the device; per Lanczos step
     // the host reads two scalars (alpha, |w|^2) and solves the small tridiagonal eigenproblem per restart cycle.
+    static const bool timing = getenv("LORADS_B200_TIMING") != nullptr;
+    const double t_begin = wall_time();
+    int n_cycles = 0;
     launch_axpby_dot(ctx, m, M1.p, coef_const(-1.0), lam.p, coef_const(0.0), nullptr, nullptr, S.p, SL_T1, false);
     double total = 0.0;
     if (nLp > 0) {
@@ -516,10 +523,10 @@ void Solver::dual_infeasibility() {
         int kdim = (40 > n) ? 2 : 40;       // dual_infeasible: ncv = 40, or 2 when ncv > n (lorads_sdp_conic.c:1288-1294)
         if (kdim > n) kdim = (int)n;
         const long long np2 = (n + 1) & ~1LL;            // even stride keeps every basis vector 16-byte aligned
-        DBuf<double> Vb, w, x0;
-        Vb.alloc((size_t)np2 * (kdim + 1)); w.alloc((size_t)np2); x0.alloc((size_t)np2);
-        DBuf<double> hbuf, hscratch;
-        hbuf.alloc(kLanczosMax); hscratch.alloc((size_t)512 * kLanczosMax);
+        auto want = [&](DBuf<double> &buf, size_t count) { if (buf.n < count) { retire(buf); buf.alloc(count); } };
+        want(lz_basis, (size_t)np2 * (kdim + 1)); want(lz_w, (size_t)np2); want(lz_x0, (size_t)np2);
+        want(lz_h, kLanczosMax); want(lz_scratch, (size_t)512 * kLanczosMax); want(lz_tab, 2 * (size_t)kLanczosMax);
+        DBuf<double> &Vb = lz_basis, &w = lz_w, &x0 = lz_x0, &hbuf = lz_h, &hscratch = lz_scratch, &lz = lz_tab;
         std::vector<double> v0((size_t)n);
         uint64_t st = 0x9E3779B97F4A7C15ull;
         double nr0 = 0.0;
@@ -542,54 +549,61 @@ void Solver::dual_infeasibility() {
         double theta = 0.0;
         const double tol = 1e-2;
         std::vector<double> alpha, beta;
+        // One restart cycle = kdim Lanczos steps issued back to back: alpha_j and |w_j|^2 land in a small device table
+        // and are read ONCE per cycle.  A breakdown (beta ~ 0) inside the cycle only produces garbage in the later
+        // steps, which the host discards by truncating the tridiagonal matrix at the first tiny beta.
+        std::vector<double> lz_host(2 * (size_t)kLanczosMax);
+        const double t_alloc = wall_time();
         for (int cycle = 0; cycle < 600; ++cycle) {
+            ++n_cycles;
             alpha.clear(); beta.clear();
-            bool done = false;
             for (int j = 0; j < kdim; ++j) {
                 // w = S v_j, then two classical Gram-Schmidt passes against v_0..v_j, each one dots kernel + one
                 // update kernel (full re-orthogonalisation; the first pass also yields alpha_j = v_j . S v_j and
-                // removes the beta_{j-1} v_{j-1} term), |w|^2 from the last update, v_{j+1} = w/|w| issued before the
-                // single host synchronisation of the step
+                // removes the beta_{j-1} v_{j-1} term), |w|^2 from the last update, v_{j+1} = w/|w|
                 matvec(vec(j), w.p);
-                launch_lanczos_dots(ctx, n, Vb.p, np2, j + 1, w.p, hbuf.p, hscratch.p, S.p, SL_T0);
-                launch_lanczos_update(ctx, n, Vb.p, np2, j + 1, hbuf.p, w.p, S.p, -1);
-                launch_lanczos_dots(ctx, n, Vb.p, np2, j + 1, w.p, hbuf.p, hscratch.p, S.p, -1);
-                launch_lanczos_update(ctx, n, Vb.p, np2, j + 1, hbuf.p, w.p, S.p, SL_T1);
-                if (j + 1 < kdim) launch_lanczos_next(ctx, n, w.p, vec(j + 1), S.p, SL_T1);
-                read_slots();
-                const double a = S_host[SL_T0], bb = std::sqrt(S_host[SL_T1]);
-                alpha.push_back(a); beta.push_back(bb);
-                const int mdim = j + 1;
-                const bool breakdown = bb < 1e-14 * (std::fabs(a) + 1.0);
-                if (mdim == kdim || breakdown) {
-                    std::vector<double> T((size_t)mdim * mdim, 0.0), Q;
-                    for (int i = 0; i < mdim; ++i) {
-                        T[(size_t)i * mdim + i] = alpha[i];
-                        if (i + 1 < mdim) { T[(size_t)i * mdim + i + 1] = beta[i]; T[(size_t)(i + 1) * mdim + i] = beta[i]; }
-                    }
-                    jacobi_eig(mdim, T, Q);
-                    int best = 0;
-                    for (int i = 1; i < mdim; ++i) if (T[(size_t)i * mdim + i] < T[(size_t)best * mdim + best]) best = i;
-                    theta = T[(size_t)best * mdim + best];
-                    const double est = std::fabs(bb * Q[(size_t)(mdim - 1) * mdim + best]);
-                    const double scale = std::max(std::fabs(theta), 2.2e-16);
-                    if (breakdown || est <= tol * scale || mdim >= n) { done = true; break; }
-                    // explicit restart from the Ritz vector x0 = sum_l Q[l][best] v_l, normalised on the device
-                    std::vector<double> hq((size_t)mdim);
-                    for (int l = 0; l < mdim; ++l) hq[(size_t)l] = -Q[(size_t)l * mdim + best];
-                    LB2_CUDA(cudaMemcpyAsync(hbuf.p, hq.data(), sizeof(double) * mdim, cudaMemcpyHostToDevice, ctx.stream));
-                    LB2_CUDA(cudaStreamSynchronize(ctx.stream));      // hq is pageable stack-lifetime memory
-                    LB2_CUDA(cudaMemsetAsync(x0.p, 0, sizeof(double) * np2, ctx.stream));
-                    launch_lanczos_update(ctx, n, Vb.p, np2, mdim, hbuf.p, x0.p, S.p, SL_T1);
-                    launch_lanczos_next(ctx, n, x0.p, vec(0), S.p, SL_T1);
-                    break;
-                }
+                launch_lanczos_dots(ctx, n, Vb.p, np2, j + 1, w.p, hbuf.p, hscratch.p, lz.p, j);
+                launch_lanczos_update(ctx, n, Vb.p, np2, j + 1, hbuf.p, w.p, lz.p, -1);
+                launch_lanczos_dots(ctx, n, Vb.p, np2, j + 1, w.p, hbuf.p, hscratch.p, lz.p, -1);
+                launch_lanczos_update(ctx, n, Vb.p, np2, j + 1, hbuf.p, w.p, lz.p, kLanczosMax + j);
+                if (j + 1 < kdim) launch_lanczos_next(ctx, n, w.p, vec(j + 1), lz.p, kLanczosMax + j);
             }
-            if (done) break;
+            LB2_CUDA(cudaMemcpyAsync(lz_host.data(), lz.p, sizeof(double) * lz_host.size(), cudaMemcpyDeviceToHost, ctx.stream));
+            LB2_CUDA(cudaStreamSynchronize(ctx.stream));
+            int mdim = kdim;
+            bool breakdown = false;
+            for (int j = 0; j < kdim; ++j) {
+                const double a = lz_host[(size_t)j], bb = std::sqrt(lz_host[(size_t)kLanczosMax + j]);
+                alpha.push_back(a); beta.push_back(bb);
+                if (!(bb >= 1e-14 * (std::fabs(a) + 1.0))) { mdim = j + 1; breakdown = true; break; }   // also catches NaN
+            }
+            const double bb = beta[(size_t)mdim - 1];
+            std::vector<double> T((size_t)mdim * mdim, 0.0), Q;
+            for (int i = 0; i < mdim; ++i) {
+                T[(size_t)i * mdim + i] = alpha[i];
+                if (i + 1 < mdim) { T[(size_t)i * mdim + i + 1] = beta[i]; T[(size_t)(i + 1) * mdim + i] = beta[i]; }
+            }
+            jacobi_eig(mdim, T, Q);
+            int best = 0;
+            for (int i = 1; i < mdim; ++i) if (T[(size_t)i * mdim + i] < T[(size_t)best * mdim + best]) best = i;
+            theta = T[(size_t)best * mdim + best];
+            const double est = std::fabs(bb * Q[(size_t)(mdim - 1) * mdim + best]);
+            const double scale = std::max(std::fabs(theta), 2.2e-16);
+            if (breakdown || est <= tol * scale || mdim >= n) break;
+            // explicit restart from the Ritz vector x0 = sum_l Q[l][best] v_l, normalised on the device
+            std::vector<double> hq((size_t)mdim);
+            for (int l = 0; l < mdim; ++l) hq[(size_t)l] = -Q[(size_t)l * mdim + best];
+            LB2_CUDA(cudaMemcpyAsync(hbuf.p, hq.data(), sizeof(double) * mdim, cudaMemcpyHostToDevice, ctx.stream));
+            LB2_CUDA(cudaStreamSynchronize(ctx.stream));      // hq is pageable stack-lifetime memory
+            LB2_CUDA(cudaMemsetAsync(x0.p, 0, sizeof(double) * np2, ctx.stream));
+            launch_lanczos_update(ctx, n, Vb.p, np2, mdim, hbuf.p, x0.p, S.p, SL_T1);
+            launch_lanczos_next(ctx, n, x0.p, vec(0), S.p, SL_T1);
         }
+        if (timing) fprintf(stderr, "  dual infeasibility cone %lld: setup %.3f s, %d cycles %.3f s\n", c, t_alloc - t_begin, n_cycles, wall_time() - t_alloc);
         total += std::fabs(std::min(theta, 0.0));
     }
     dimac_dinf = total / scaleObjHis / (cObjNrm1 + 1);
+    if (timing) { sync(); fprintf(stderr, "  dual infeasibility total %.3f s\n", wall_time() - t_begin); }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -1471,11 +1471,15 @@ __global__ void __launch_bounds__(kBlock) lanczos_dots_kernel(long long n, const
     __syncthreads();
     if (!last) return;
     __threadfence();
-    if (threadIdx.x < nv) {
+    // one warp per basis vector: lanes stride the per-block partials (independent loads in flight), fixed shuffle tree
+    for (int l = warp; l < nv; l += kBlock / 32) {
         double t = 0.0;
-        for (unsigned int b = 0; b < gridDim.x; ++b) t += __ldcg(scratch + (size_t)b * kLanczosMax + threadIdx.x);
-        h[threadIdx.x] = t;
-        if (alpha_slot >= 0 && threadIdx.x == nv - 1) S[alpha_slot] = t;
+        for (unsigned int b = lane; b < gridDim.x; b += 32) t += __ldcg(scratch + (size_t)b * kLanczosMax + l);
+        t = warp_sum(t);
+        if (lane == 0) {
+            h[l] = t;
+            if (alpha_slot >= 0 && l == nv - 1) S[alpha_slot] = t;
+        }
     }
     if (threadIdx.x == 0) *ticket = 0u;
 }

@@ -275,17 +275,19 @@ void Solver::alloc_vars() {
         N += K.n * K.ld;
     }
     Nt = N + nLp;
-    for (DBuf<double> *v : {&R, &U, &V, &G, &M2, &Bls, &cg_r, &cg_p, &cg_Q, &Dtemp}) v->alloc((size_t)Nt);
+    for (DBuf<double> *v : {&R, &U, &V, &G, &M2, &Bls, &cg_r, &cg_p, &cg_Q, &Dtemp}) { retire(*v); v->alloc((size_t)Nt); }
     {
         // split-K scratch of the dense symmetric product: up to 32 partial n x ldp blocks of the largest dense cone
         size_t need = 0;
         for (const ConeDev &K : cones)
             if (K.dense_path) need = std::max(need, (size_t)32 * (size_t)K.n * (size_t)(((K.ld + 7) / 8) * 8));
         need = std::min(need, (size_t)1 << 28);     // cap at 2 GiB of doubles; the launcher lowers the split count
-        dense_part.alloc(need, false);
+        if (need > dense_part.n) { retire(dense_part); dense_part.alloc(need, false); }
         ctx.dense_part = dense_part.p;
         ctx.dense_part_cap = need;
     }
+    for (DBuf<double> &v : lb_s) retire(v);
+    for (DBuf<double> &v : lb_y) retire(v);
     lb_s.clear(); lb_y.clear();
     lb_s.resize(lbfgs_len); lb_y.resize(lbfgs_len);
     for (int k = 0; k < lbfgs_len; ++k) { lb_s[k].alloc((size_t)Nt); lb_y[k].alloc((size_t)Nt); }

@@ -107,6 +107,14 @@ struct Solver {
     long long Nt = 0;     // N + nLp: length of the concatenated [cones | LP] vectors
     DBuf<double> R, U, V, G, M2, Bls, cg_r, cg_p, cg_Q, Dtemp;
     std::vector<DBuf<double>> lb_s, lb_y;
+    // cudaFree synchronises the device and was measured to stall for up to 1.5 s on this platform, so nothing is
+    // freed while a solve is running: buffers replaced by rank augmentation are parked here until the solver dies
+    std::vector<DBuf<double>> retired;
+    void retire(DBuf<double> &b) { if (b.p) retired.emplace_back(std::move(b)); }
+    // Lanczos workspace of the dual infeasibility (allocated once, grown on demand)
+    DBuf<double> lz_basis, lz_w, lz_x0, lz_h, lz_scratch, lz_tab;
+    DBuf<int> aug_pos;            // scatter list of the diagonal entries of freshly appended factor columns
+    DBuf<double> aug_val;
     int lbfgs_len = 2, lb_head = 0;
     bool vf_lbfgs = false;     // vector-free (Gram) L-BFGS for history length 2
     bool vf_valid = false;     // the G-dots in the Gram table belong to the current gradient
