@@ -83,12 +83,15 @@ class ClockSampler:
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.time()
+        deadline = t1 + 1.5
+        while not self.lines and time.time() < deadline:      # very short timed region: wait for the first sample
+            time.sleep(0.02)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        t1 = time.time()
         t0 = getattr(self, "t0", 0.0)
         inside = [ln for (ts, ln) in self.lines if t0 <= ts <= t1 + 0.05]
         if not inside and self.lines:
@@ -127,7 +130,7 @@ def ncu_traffic(kernel_label: str):
         table = json.load(open(p))["dram_bytes_per_launch"]
     except Exception:
         return None
-    key = {"auv_items_kernel<DUAL>": "auv_items_kernel<2,", "auv_items_kernel<SAME>": "auv_items_kernel<0,",
+    key = {"auv_items_kernel<TRI>": "auv_items_kernel<4,", "auv_items_kernel<DUAL>": "auv_items_kernel<2,", "auv_items_kernel<SAME>": "auv_items_kernel<0,",
            "spmm_sym_kernel": "spmm_sym_kernel", "axpby_dot2_kernel": "axpby_dot2_kernel", "wsum_kernel": "wsum_kernel"}
     for prefix, ncu_prefix in key.items():
         if kernel_label.startswith(prefix):
@@ -143,8 +146,12 @@ def kernel_bytes(S) -> dict:
     itAC, itA, nact = S.info(15), S.info(16), S.info(8)
     npat, nadj, nnzA = S.info(4), S.info(14), S.info(12)
     N = S.info(18)
+    tri = S.info(20) == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1
+    dual = (("auv_items_kernel<TRI> A(sym(RD^T)),A(DD^T),A(RR^T)+obj", 2 * 8 * n * ld + 16 * itAC + 4 * (nact + 2) + 3 * 8 * (nact + 1))
+            if tri else
+            ("auv_items_kernel<DUAL> A(sym(RD^T)),A(DD^T)+obj", 2 * 8 * n * ld + 16 * itAC + 4 * (nact + 2) + 2 * 8 * (nact + 1)))
     return {
-        0: ("auv_items_kernel<DUAL> A(sym(RD^T)),A(DD^T)+obj", 2 * 8 * n * ld + 16 * itAC + 4 * (nact + 2) + 2 * 8 * (nact + 1)),
+        0: dual,
         1: ("auv_items_kernel<SAME> A(RR^T)", 8 * n * ld + 16 * itA + 4 * (nact + 1) + 8 * nact),
         2: ("wsum_kernel S=C+A^*(w)", npat * (8 + 8 + 4) + nnzA * (4 + 8 + 8)),
         3: ("spmm_sym_kernel G=2SR", nadj * 8 + npat * 8 + 4 * (n + 1) + 2 * 8 * n * ld),
@@ -308,7 +315,8 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
     # per-iteration share: 1 dual pass, 1 A-only pass, 1 wsum, 1 spmm, ~6 BLAS-1 passes
-    mult = {0: 1, 1: 1, 2: 1, 3: 1, 4: 6}
+    # (with the three-output gather pass the separate A(RR^T) launch is no longer part of the pipelined step)
+    mult = {0: 1, 1: 0 if S.info(20) == 1 else 1, 2: 1, 3: 1, 4: 6}
     share = {w: kt[w] * mult[w] for w in kt}
     dom = max(share, key=share.get)
     kernels = {kb[w][0]: {"ms": kt[w], "alg_bytes": kb[w][1], "gbs": kb[w][1] / (kt[w] * 1e-3) / 1e9,

@@ -274,6 +274,7 @@ lb2_int lb2_info(const lb2_solver *s, int what, lb2_int c) {
     case 17: return K.ld;
     case 18: return S.N;
     case 19: return S.nLp;
+    case 20: return S.tri_ok() ? 1 : 0;
     }
     return -1;
 }
@@ -473,7 +474,13 @@ int lb2_bench_kernel(lb2_solver *s, int which, lb2_int reps, double *ms) {
     LB2_CUDA(cudaEventCreate(&e0)); LB2_CUDA(cudaEventCreate(&e1));
     auto once = [&]() {
         switch (which) {
-        case 0: S.cone_auv_dual(K, S.R.p, S.U.p, K.t1.p, K.t2.p); break;
+        case 0:
+            // what the pipelined ALM step launches: the three-output pass when it applies, else the dual pass
+            if (S.tri_ok())
+                launch_auv(S.ctx, AUV_TRI, K.listAC.dev, S.R.p + K.off, S.U.p + K.off, K.ld, 2.0, 1.0, K.t1.p, K.t2.p, K.carry1.p,
+                           K.carry2.p, nullptr, nullptr, S.q3.p, K.carry3.p);
+            else S.cone_auv_dual(K, S.R.p, S.U.p, K.t1.p, K.t2.p);
+            break;
         case 1: S.cone_auv(K, false, S.R.p, S.R.p, true, 1.0, K.cv.p); break;
         case 2: S.cone_wsum(K, S.M1.p, false, true); break;
         case 3: S.cone_mul(K, S.R.p, 2.0, 0.0, nullptr, nullptr, S.G.p, S.S.p + kNumSlots); break;
