@@ -110,16 +110,23 @@ static void setup_p2p(Solver &S) {
         S.p2p.world = W; S.p2p.rank = S.myrank; S.p2p.cap = cap;
         S.p2p.peer_x = S.p2p_peer_x.p; S.p2p.peer_f = S.p2p_peer_f.p;
         S.p2p.x = S.p2p_x.p; S.p2p.f = S.p2p_f.p; S.p2p.epoch = S.p2p_epoch.p; S.p2p.ticket = S.p2p_ticket.p;
-        // nobody may push before every rank has mapped and zeroed its flags: a 1-element NCCL all-reduce is the barrier
-        S.p2p_on = false;
-        S.allreduce(S.S.p + SL_T1, 1);
-        LB2_CUDA(cudaStreamSynchronize(S.ctx.stream));
         S.p2p_on = true;
     } catch (const std::exception &e) {
         cudaGetLastError();
         S.p2p_on = false;
-        fprintf(stderr, "lorads_b200: peer-memory all-reduce unavailable (%s); using NCCL\n", e.what());
+        fprintf(stderr, "lorads_b200: peer-memory all-reduce unavailable on rank %d (%s); using NCCL\n", S.myrank, e.what());
     }
+    // Agreement + barrier in one NCCL all-reduce: the exchange is used only if EVERY rank mapped its peers, and nobody
+    // pushes before every rank has zeroed its flags.
+    const bool mine_ok = S.p2p_on;
+    S.p2p_on = false;
+    const double flag = mine_ok ? 1.0 : 0.0;
+    LB2_CUDA(cudaMemcpy(S.S.p + SL_T1, &flag, sizeof(double), cudaMemcpyHostToDevice));
+    S.allreduce(S.S.p + SL_T1, 1);
+    double sum = 0.0;
+    LB2_CUDA(cudaStreamSynchronize(S.ctx.stream));
+    LB2_CUDA(cudaMemcpy(&sum, S.S.p + SL_T1, sizeof(double), cudaMemcpyDeviceToHost));
+    S.p2p_on = (sum == (double)S.world);
 }
 
 extern "C" {

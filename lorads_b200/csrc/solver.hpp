@@ -110,7 +110,13 @@ struct Solver {
     // cudaFree synchronises the device and was measured to stall for up to 1.5 s on this platform, so nothing is
     // freed while a solve is running: buffers replaced by rank augmentation are parked here until the solver dies
     std::vector<DBuf<double>> retired;
-    void retire(DBuf<double> &b) { if (b.p) retired.emplace_back(std::move(b)); }
+    size_t retired_bytes = 0;
+    void retire(DBuf<double> &b) {
+        if (!b.p) return;
+        retired_bytes += b.n * sizeof(double);
+        retired.emplace_back(std::move(b));
+        if (retired_bytes > ((size_t)32 << 30)) { retired.clear(); retired_bytes = 0; }   // cap the parked memory at 32 GiB
+    }
     // Lanczos workspace of the dual infeasibility (allocated once, grown on demand)
     DBuf<double> lz_basis, lz_w, lz_x0, lz_h, lz_scratch, lz_tab;
     DBuf<int> aug_pos;            // scatter list of the diagonal entries of freshly appended factor columns
