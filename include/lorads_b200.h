@@ -138,6 +138,9 @@ int lb2_comm_init(lb2_solver *s, const void *id128, int rank, int world);
  * The arrays can be passed straight to lb2_set_cone_data. */
 typedef struct lb2_sdpa lb2_sdpa;
 int lb2_read_sdpa(const char *path, lb2_sdpa **out);
+/* Binary instance cache: writes the reader's output arrays as they are; lb2_read_sdpa recognises such a file by its
+ * magic and loads it without parsing (SURVEY 8f-3 "binary instance format"). */
+int lb2_sdpa_save(const lb2_sdpa *s, const char *path);
 /* what: 0 nConstrs, 1 number of PSD blocks, 2 dimension of block k, 3 non-zeros of block k, 4 nLpCols, 5 nElems */
 lb2_int lb2_sdpa_info(const lb2_sdpa *s, int what, lb2_int k);
 /* copies block k (beg: m+2, idx/elem: nnz) and/or the right-hand side (m); pass k = -1 for the rhs only */

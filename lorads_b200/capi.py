@@ -54,7 +54,7 @@ EXPORTS = [
     "lb2_time_alm_inner_iters", "lb2_alm_run_host", "lb2_bench_kernel", "lb2_alm_optimize", "lb2_alm_to_admm", "lb2_admm_optimize", "lb2_dual_infeasibility",
     "lb2_solve", "lb2_get_solution", "lb2_reopt", "lb2_average_uv", "lb2_copy_r_to_v", "lb2_get_state", "lb2_set_state", "lb2_host_presolve", "lb2_host_line_search", "lb2_host_rank_rule",
     "lb2_set_lp_data", "lb2_get_lp_vec", "lb2_set_lp_vec", "lb2_admm_init_constr", "lb2_admm_update_var",
-    "lb2_read_sdpa", "lb2_sdpa_info", "lb2_sdpa_get", "lb2_sdpa_free", "lb2_sdpa_last_error",
+    "lb2_read_sdpa", "lb2_sdpa_save", "lb2_sdpa_info", "lb2_sdpa_get", "lb2_sdpa_free", "lb2_sdpa_last_error",
 ]
 
 _lib = None
@@ -122,6 +122,7 @@ def load_library():
     lib.lb2_sdpa_info.argtypes = [C.c_void_p, C.c_int, C.c_int64]
     lib.lb2_sdpa_get.argtypes = [C.c_void_p, C.c_int64, _ip, _ip, _dp, _dp]
     lib.lb2_sdpa_free.argtypes = [C.c_void_p]
+    lib.lb2_sdpa_save.argtypes = [C.c_void_p, C.c_char_p]
     lib.lb2_sdpa_free.restype = None
     lib.lb2_sdpa_last_error.restype = C.c_char_p
     _lib = lib
@@ -166,14 +167,17 @@ def host_presolve(cone, m: int):
     return dict(zip(keys, info.tolist())), rows, cols
 
 
-def read_sdpa(path: str) -> Instance:
-    """Fast .dat-s ingest through the library (same arrays as the reference's LReadSDPA)."""
+def read_sdpa(path: str, save_binary: str | None = None) -> Instance:
+    """Fast .dat-s ingest through the library (same arrays as the reference's LReadSDPA); `path` may also be a binary
+    instance cache written by an earlier call with `save_binary`."""
     from .sdpa import Cone
     lib = load_library()
     h = C.c_void_p()
     if lib.lb2_read_sdpa(path.encode(), C.byref(h)) != 0:
         raise Lb2Error(lib.lb2_sdpa_last_error().decode())
     try:
+        if save_binary is not None and lib.lb2_sdpa_save(h, save_binary.encode()) != 0:
+            raise Lb2Error(lib.lb2_sdpa_last_error().decode())
         m = int(lib.lb2_sdpa_info(h, 0, 0))
         nblk = int(lib.lb2_sdpa_info(h, 1, 0))
         b = np.zeros(m)

@@ -24,7 +24,8 @@ static struct option long_options[] = {
     {"endALMSubTol", required_argument, 0, 1016}, {"l2Rescaling", required_argument, 0, 1017},
     {"reoptLevel", required_argument, 0, 1018},   {"dyrankLevel", required_argument, 0, 1019},
     {"highAccMode", required_argument, 0, 1020},  {"device", required_argument, 0, 2000},
-    {"quiet", no_argument, 0, 2001},              {0, 0, 0, 0}};
+    {"quiet", no_argument, 0, 2001},              {"saveBinary", required_argument, 0, 2002},
+    {0, 0, 0, 0}};
 
 static void fail(const char *what) {
     std::fprintf(stderr, "lorads_b200_cli: %s: %s\n", what, lb2_last_error());
@@ -33,13 +34,14 @@ static void fail(const char *what) {
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        std::fprintf(stderr, "usage: %s file.dat-s [--timesLogRank x] [--phase2Tol x] [--timeSecLimit x] ... [--device k] [--quiet]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s file.dat-s [--timesLogRank x] [--phase2Tol x] [--timeSecLimit x] ... [--device k] [--quiet] [--saveBinary file]\n", argv[0]);
         return 1;
     }
     lb2_params P;
     lb2_default_params(&P);
     P.verbose = 1;
     int device = 0, opt, idx = 0;
+    const char *save_binary = nullptr;      // write the parsed instance as a binary cache (readable in place of the .dat-s)
     const char *fname = argv[1];
     while ((opt = getopt_long(argc, argv, "", long_options, &idx)) != -1) {
         switch (opt) {
@@ -55,12 +57,14 @@ int main(int argc, char **argv) {
         case 1018: P.reoptLevel = atoll(optarg); break;   case 1019: P.dyrankLevel = atoll(optarg); break;
         case 1020: P.highAccMode = atoi(optarg); break;   case 2000: device = atoi(optarg); break;
         case 2001: P.verbose = 0; break;
+        case 2002: save_binary = optarg; break;
         default: break;
         }
     }
     P.rhoCellingADMM = P.rhoMax * 200;      // main.c:236
     lb2_sdpa *F = nullptr;
     if (lb2_read_sdpa(fname, &F) != LB2_OK) { std::fprintf(stderr, "cannot read %s: %s\n", fname, lb2_sdpa_last_error()); return 2; }
+    if (save_binary && lb2_sdpa_save(F, save_binary) != LB2_OK) { std::fprintf(stderr, "cannot write %s: %s\n", save_binary, lb2_sdpa_last_error()); return 2; }
     const lb2_int m = lb2_sdpa_info(F, 0, 0), nblk = lb2_sdpa_info(F, 1, 0);
     const lb2_int nlp = lb2_sdpa_info(F, 4, 0);
     std::printf("nConstrs = %lld, sdp nBlks = %lld, lp Cols = %lld\n", (long long)m, (long long)nblk, (long long)nlp);

@@ -12,7 +12,9 @@
 #include <cstring>
 #include <memory>
 #include <stdexcept>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/lorads_b200.h"
@@ -59,11 +61,79 @@ inline bool parse_double(const char *&p, const char *end, double &v) {
 }
 inline bool is_punct(char c) { return c == '{' || c == '}' || c == '(' || c == ')' || c == ',' || c == '\''; }
 
+// Binary instance cache (lb2_sdpa_save / auto-detected by lb2_read_sdpa): the reader's output arrays as they are, native
+// little-endian: magic, m, #PSD blocks, nLpCols, nElems, dims[], rhs[], then per block (PSD blocks, then the LP block
+// when nLpCols > 0): nnz, beg[m+2], idx[nnz], elem[nnz].
+const char kBinMagic[9] = "LB2SDPA1";
+
+int load_binary(const char *p, const char *end, lb2_sdpa **out) {
+    try {
+        auto take = [&](void *dst, size_t bytes) {
+            if ((size_t)(end - p) < bytes) throw std::runtime_error("binary instance file is truncated");
+            std::memcpy(dst, p, bytes);
+            p += bytes;
+        };
+        p += 8;
+        std::unique_ptr<lb2_sdpa> S(new lb2_sdpa());
+        lb2_int hdr[4];
+        take(hdr, sizeof(hdr));
+        S->m = hdr[0]; S->nLpCols = hdr[2]; S->nElems = hdr[3];
+        const lb2_int nblk = hdr[1];
+        if (S->m <= 0 || nblk < 0 || nblk > (1 << 24) || S->nLpCols < 0) throw std::runtime_error("bad binary instance header");
+        S->dims.resize((size_t)nblk);
+        take(S->dims.data(), sizeof(lb2_int) * (size_t)nblk);
+        S->rhs.resize((size_t)S->m);
+        take(S->rhs.data(), sizeof(double) * (size_t)S->m);
+        S->blocks.resize((size_t)nblk);
+        auto block = [&](lb2_sdpa::Block &B) {
+            lb2_int nnz = 0;
+            take(&nnz, sizeof(nnz));
+            if (nnz < 0) throw std::runtime_error("bad binary instance block");
+            B.beg.resize((size_t)S->m + 2); B.idx.resize((size_t)nnz); B.elem.resize((size_t)nnz);
+            take(B.beg.data(), sizeof(lb2_int) * B.beg.size());
+            take(B.idx.data(), sizeof(lb2_int) * (size_t)nnz);
+            take(B.elem.data(), sizeof(double) * (size_t)nnz);
+            if (B.beg.back() != nnz) throw std::runtime_error("bad binary instance block");
+        };
+        for (lb2_int k = 0; k < nblk; ++k) block(S->blocks[(size_t)k]);
+        if (S->nLpCols > 0) block(S->lp);
+        *out = S.release();
+    } catch (const std::exception &e) {
+        g_reader_err = e.what();
+        return LB2_ERR_ARG;
+    }
+    return LB2_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
 const char *lb2_sdpa_last_error(void) { return g_reader_err.c_str(); }
+
+int lb2_sdpa_save(const lb2_sdpa *s, const char *path) {
+    if (!s || !path) return LB2_ERR_ARG;
+    FILE *f = std::fopen(path, "wb");
+    if (!f) { g_reader_err = std::string("cannot create ") + path; return LB2_ERR_ARG; }
+    bool ok = true;
+    auto put = [&](const void *src, size_t bytes) { ok = ok && (bytes == 0 || std::fwrite(src, 1, bytes, f) == bytes); };
+    const lb2_int hdr[4] = {s->m, (lb2_int)s->dims.size(), s->nLpCols, s->nElems};
+    put(kBinMagic, 8); put(hdr, sizeof(hdr));
+    put(s->dims.data(), sizeof(lb2_int) * s->dims.size());
+    put(s->rhs.data(), sizeof(double) * s->rhs.size());
+    auto block = [&](const lb2_sdpa::Block &B) {
+        const lb2_int nnz = (lb2_int)B.idx.size();
+        put(&nnz, sizeof(nnz));
+        put(B.beg.data(), sizeof(lb2_int) * B.beg.size());
+        put(B.idx.data(), sizeof(lb2_int) * B.idx.size());
+        put(B.elem.data(), sizeof(double) * B.elem.size());
+    };
+    for (const lb2_sdpa::Block &B : s->blocks) block(B);
+    if (s->nLpCols > 0) block(s->lp);
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) { g_reader_err = "write failed"; return LB2_ERR_ARG; }
+    return LB2_OK;
+}
 
 int lb2_read_sdpa(const char *path, lb2_sdpa **out) {
     if (!path || !out) return LB2_ERR_ARG;
@@ -78,6 +148,7 @@ int lb2_read_sdpa(const char *path, lb2_sdpa **out) {
     std::fclose(f);
     buf[(size_t)sz] = '\0';
     const char *p = buf.data(), *end = buf.data() + sz;
+    if (sz >= 8 && std::memcmp(p, kBinMagic, 8) == 0) return load_binary(p, end, out);
     try {
         lb2_sdpa *S = new lb2_sdpa();
         std::unique_ptr<lb2_sdpa> guard(S);
@@ -114,35 +185,77 @@ int lb2_read_sdpa(const char *path, lb2_sdpa **out) {
             if (!parse_double(p, end, S->rhs[(size_t)i])) throw std::runtime_error("bad right-hand side");
         }
         skip_line(p, end);
-        // entries: first pass collects triplets per block
+        // entries: the rest of the file is cut at line boundaries into one chunk per thread; every thread collects
+        // the triplets of its chunk per block, and the chunks are concatenated in file order afterwards (the reader's
+        // output keeps file order inside a constraint column)
         struct Trip { lb2_int con, pos; double val; };
+        struct Part {
+            std::vector<std::vector<Trip>> trips;
+            std::vector<Trip> lp;
+            lb2_int nElems = 0;
+            bool stop = false;          // BEGIN.COMMENT seen: everything after this chunk position is ignored
+            std::string err;
+        };
+        const size_t body = (size_t)(end - p);
+        unsigned nth = 1;
+        if (body > (size_t)(8u << 20)) nth = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        std::vector<const char *> cut(nth + 1);
+        cut[0] = p; cut[nth] = end;
+        for (unsigned t = 1; t < nth; ++t) {
+            const char *q = p + body * t / nth;
+            while (q < end && *q != '\n') ++q;
+            cut[t] = (q < end) ? q + 1 : end;
+        }
+        std::vector<Part> parts(nth);
+        const lb2_int mrows = S->m, nlp = S->nLpCols;
+        const std::vector<lb2_int> &bdims = S->dims;
+        auto work = [&](unsigned t) {
+            Part &P = parts[t];
+            P.trips.resize((size_t)nsdp);
+            const char *q = cut[t], *qe = cut[t + 1];
+            while (q < qe) {
+                skip_ws(q, qe);
+                if (q >= qe) break;
+                if (*q == '\n') { ++q; continue; }
+                long long con, blk, i, j;
+                double val;
+                const char *line = q;
+                if (!parse_int(q, qe, con) || !parse_int(q, qe, blk) || !parse_int(q, qe, i) || !parse_int(q, qe, j) || !parse_double(q, qe, val)) {
+                    if (std::strncmp(line, "BEGIN.COMMENT", 13) == 0) { P.stop = true; return; }
+                    P.err = "malformed entry line";
+                    return;
+                }
+                skip_line(q, qe);
+                if (con < 0 || con > mrows || blk < 1 || blk > nblk) { P.err = "entry index out of range"; return; }
+                if (std::fabs(val) < 1e-12) continue;
+                if (con == 0) val = -val;
+                blk -= 1; i -= 1; j -= 1;
+                if (nlp > 0 && blk == nsdp) {
+                    P.lp.push_back({(lb2_int)con, (lb2_int)i, val});
+                } else {
+                    const long long n = bdims[(size_t)blk];
+                    const long long hi = i > j ? i : j, lo = i > j ? j : i;
+                    if (lo < 0 || hi >= n) { P.err = "matrix index out of range"; return; }
+                    P.trips[(size_t)blk].push_back({(lb2_int)con, (lb2_int)((2 * n - lo - 1) * lo / 2 + hi), val});
+                }
+                P.nElems += 1;
+            }
+        };
+        if (nth == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nth; ++t) th.emplace_back(work, t);
+            for (std::thread &x : th) x.join();
+        }
         std::vector<std::vector<Trip>> trips((size_t)nsdp);
         std::vector<Trip> lptrips;
-        while (p < end) {
-            skip_ws(p, end);
-            if (p >= end) break;
-            if (*p == '\n') { ++p; continue; }
-            long long con, blk, i, j;
-            double val;
-            const char *line = p;
-            if (!parse_int(p, end, con) || !parse_int(p, end, blk) || !parse_int(p, end, i) || !parse_int(p, end, j) || !parse_double(p, end, val)) {
-                if (std::strncmp(line, "BEGIN.COMMENT", 13) == 0) break;
-                throw std::runtime_error("malformed entry line");
-            }
-            skip_line(p, end);
-            if (con < 0 || con > S->m || blk < 1 || blk > nblk) throw std::runtime_error("entry index out of range");
-            if (std::fabs(val) < 1e-12) continue;
-            if (con == 0) val = -val;
-            blk -= 1; i -= 1; j -= 1;
-            if (S->nLpCols > 0 && blk == nsdp) {
-                lptrips.push_back({(lb2_int)con, (lb2_int)i, val});
-            } else {
-                const long long n = S->dims[(size_t)blk];
-                const long long hi = i > j ? i : j, lo = i > j ? j : i;
-                if (lo < 0 || hi >= n) throw std::runtime_error("matrix index out of range");
-                trips[(size_t)blk].push_back({(lb2_int)con, (lb2_int)((2 * n - lo - 1) * lo / 2 + hi), val});
-            }
-            S->nElems += 1;
+        for (unsigned t = 0; t < nth; ++t) {
+            if (!parts[t].err.empty()) throw std::runtime_error(parts[t].err);
+            for (long long k = 0; k < nsdp; ++k)
+                trips[(size_t)k].insert(trips[(size_t)k].end(), parts[t].trips[(size_t)k].begin(), parts[t].trips[(size_t)k].end());
+            lptrips.insert(lptrips.end(), parts[t].lp.begin(), parts[t].lp.end());
+            S->nElems += parts[t].nElems;
+            if (parts[t].stop) break;
         }
         auto compress = [&](const std::vector<Trip> &t, lb2_sdpa::Block &B) {
             B.beg.assign((size_t)S->m + 2, 0);

@@ -85,3 +85,34 @@ def test_against_reference_reader_and_speed(tmp_path):
     beg, idx, elem = R.reader_csc()
     same_csc(got.cones[0], sdpa.Cone(n=3000, beg=beg, idx=idx, elem=elem), inst.m)
     assert t_lib < 1.0
+
+
+def test_binary_cache_roundtrip(tmp_path):
+    """lb2_sdpa_save writes the reader's arrays; lb2_read_sdpa recognises the file by its magic."""
+    mix = sdpa.add_lp_block(sdpa.maxcut(50, 160, 3), 20, 6)
+    txt, binp = str(tmp_path / "mix.dat-s"), str(tmp_path / "mix.lb2")
+    sdpa.write_dat_s(mix, txt)
+    a = capi.read_sdpa(txt, save_binary=binp)
+    b = capi.read_sdpa(binp)
+    assert b.m == a.m and np.array_equal(a.b, b.b) and len(a.cones) == len(b.cones)
+    for x, y in zip(a.cones, b.cones):
+        assert x.n == y.n and np.array_equal(x.beg, y.beg) and np.array_equal(x.idx, y.idx) and np.array_equal(x.elem, y.elem)
+    assert b.lp.n == a.lp.n and np.array_equal(a.lp.beg, b.lp.beg) and np.array_equal(a.lp.idx, b.lp.idx) and np.array_equal(a.lp.elem, b.lp.elem)
+    # truncated cache files are rejected
+    data = open(binp, "rb").read()
+    bad = tmp_path / "bad.lb2"
+    bad.write_bytes(data[: len(data) // 2])
+    with pytest.raises(capi.Lb2Error):
+        capi.read_sdpa(str(bad))
+
+
+def test_threaded_parse_keeps_file_order(tmp_path):
+    """Files above 8 MB are parsed by several threads; the arrays must equal the single-thread result (checked against
+    the pure-python reader, which keeps file order inside a constraint)."""
+    inst = sdpa.maxcut(120000, 500000, 9)
+    path = str(tmp_path / "big.dat-s")
+    sdpa.write_dat_s(inst, path)
+    assert os.path.getsize(path) > (8 << 20)
+    a = capi.read_sdpa(path)
+    c0 = inst.cones[0]
+    assert np.array_equal(a.cones[0].beg, c0.beg) and np.array_equal(a.cones[0].idx, c0.idx) and np.allclose(a.cones[0].elem, c0.elem)
