@@ -914,7 +914,14 @@ __global__ void scalar_prologue_kernel(Coef ca, Coef cb, double *S) {
 __global__ void __launch_bounds__(kBlock) axpby_dot2_kernel(long long n, double *out, Coef ca, const double *x, Coef cb,
                                                             const double *y, const double *z, double *S, int dot_slot,
                                                             bool recip, ReduceScratch rs) {
+    // Every block evaluates the coefficients from the scalar slots itself.  S[dot_slot] is rewritten only by the LAST
+    // block to finish, i.e. after every block has read its coefficients, and a remembered coefficient goes to a slot
+    // nobody reads in this kernel, so no separate one-thread prologue launch is needed.
     const double a = eval_coef(ca, S), b = eval_coef(cb, S);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (ca.store >= 0) S[ca.store] = a;
+        if (cb.store >= 0) S[cb.store] = b;
+    }
     double acc = 0.0;
     const long long n2 = n >> 1;
     for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n2; q += (long long)gridDim.x * kBlock) {
@@ -944,9 +951,12 @@ __global__ void __launch_bounds__(kBlock) axpby_dot2_kernel(long long n, double 
 
 void launch_axpby_dot(Ctx &c, long long n, double *out, Coef a, const double *x, Coef b, const double *y,
                       const double *z, double *S, int dot_slot, bool recip) {
-    if (a.store >= 0 || b.store >= 0) {
-        // remembered coefficients are written by a one-thread kernel that runs before (same stream), and the
-        // main kernel then reads them back from their slots -> no intra-kernel race on S
+    if ((a.store >= 0 && (a.store == dot_slot || a.store == a.i0 || a.store == a.i1 || a.store == a.i2 || a.store == b.i0 ||
+                          a.store == b.i1 || a.store == b.i2)) ||
+        (b.store >= 0 && (b.store == dot_slot || b.store == a.i0 || b.store == a.i1 || b.store == a.i2 || b.store == b.i0 ||
+                          b.store == b.i1 || b.store == b.i2))) {
+        // a remembered coefficient that aliases a slot read or written by the same launch would race: evaluate it in
+        // a one-thread launch first (not used by the current call sites)
         scalar_prologue_kernel<<<1, 32, 0, c.stream>>>(a, b, S);
         LB2_LAUNCH_CHECK(c);
         if (a.store >= 0) a = coef_slot(a.store);
@@ -1219,6 +1229,41 @@ __global__ void __launch_bounds__(kBlock) linesearch_dots_kernel(long long m, co
     }
     if (grid_reduce<5>(v, rs) && threadIdx.x == 0)
         for (int k = 0; k < 5; ++k) S[slot + k] = v[k];
+}
+
+// The same sums when the exact constraint values arrive in `src` (third output of the gather pass): s := src, the
+// primal residual |b - s|^2 goes to S[pinf_slot], all in one pass.
+__global__ void __launch_bounds__(kBlock) linesearch_resid_kernel(long long m, const double *__restrict__ b,
+                                                                  const double *__restrict__ src, double *__restrict__ s,
+                                                                  const double *__restrict__ lam, const double *rho_p,
+                                                                  const double *__restrict__ q1,
+                                                                  const double *__restrict__ q2, double *S, int slot,
+                                                                  int pinf_slot, ReduceScratch rs) {
+    const double rhoInv = 1.0 / (*rho_p);
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < m; i += (long long)gridDim.x * kBlock) {
+        const double sv = src[i];
+        s[i] = sv;
+        const double d = b[i] - sv;
+        const double q0 = fma(rhoInv, lam[i], d);
+        const double a = q1[i], c2 = q2[i];
+        v[0] = fma(c2, c2, v[0]);
+        v[1] = fma(a, c2, v[1]);
+        v[2] = fma(q0, c2, v[2]);
+        v[3] = fma(a, a, v[3]);
+        v[4] = fma(q0, a, v[4]);
+        v[5] = fma(d, d, v[5]);
+    }
+    if (grid_reduce<6>(v, rs) && threadIdx.x == 0) {
+        for (int k = 0; k < 5; ++k) S[slot + k] = v[k];
+        S[pinf_slot] = v[5];
+    }
+}
+
+void launch_linesearch_resid(Ctx &c, long long m, const double *b, const double *src, double *s, const double *lam,
+                             const double *rho_p, const double *q1, const double *q2, double *S, int slot, int pinf_slot) {
+    linesearch_resid_kernel<<<grid_for(m, 4, c), kBlock, 0, c.stream>>>(m, b, src, s, lam, rho_p, q1, q2, S, slot, pinf_slot, c.rs);
+    LB2_LAUNCH_CHECK(c);
 }
 
 void launch_linesearch_dots(Ctx &c, long long m, const double *b, const double *s, const double *lam, const double *rho_p,

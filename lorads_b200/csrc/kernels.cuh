@@ -155,6 +155,9 @@ void launch_lbfgs_dir(Ctx &c, long long n, int depth, double *D, const double *G
 // S[slot+0]=|q2|^2  S[slot+1]=q1.q2  S[slot+2]=q0.q2  S[slot+3]=|q1|^2  S[slot+4]=q0.q1
 void launch_linesearch_dots(Ctx &c, long long m, const double *b, const double *s, const double *lam, const double *rho_p,
                             const double *q1, const double *q2, double *S, int slot);
+// the same five sums with s := src first and S[pinf_slot] = sum (b - s)^2 (primalInfeasibility) from the same pass
+void launch_linesearch_resid(Ctx &c, long long m, const double *b, const double *src, double *s, const double *lam,
+                             const double *rho_p, const double *q1, const double *q2, double *S, int slot, int pinf_slot);
 // s += tau*q1 + tau^2*q2 (when q1 != nullptr) ; M1 = -lambda - rho*b + rho*s   (lorads_alm.c:1123-1124, 15-27)
 void launch_alm_m_update(Ctx &c, long long m, const double *tau_p, const double *q1, const double *q2, double *s,
                          const double *lam, const double *b, const double *rho_p, double *M1);

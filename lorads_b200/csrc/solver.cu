@@ -640,10 +640,7 @@ void Solver::q12p12() {
                 LB2_CUDA(cudaMemcpyAsync(S.p + SL_P2, q2.p + m, sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
             }
         }
-        if (tri) {
-            LB2_CUDA(cudaMemcpyAsync(s.p, q3.p, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx.stream));
-            launch_resid_sq(ctx, m, b.p, s.p, S.p, SL_PINF);
-        }
+        tri_pending = tri;        // enqueue_front folds s := q3 and the residual into its line-search pass
         lp_q12p12();
         return;
     }
@@ -784,9 +781,12 @@ long long line_search(double rho, const double *sums, double p1, double p2, doub
 void Solver::enqueue_front(double rho, long long counter) {
     (void)rho;     // read by the kernels from S[SL_RHO] (push_scalars)
     lbfgs_direction(counter);
+    tri_pending = false;
     q12p12();
     if (world > 1 && !p12_from_rows()) allreduce(S.p + SL_P1, 2);
-    launch_linesearch_dots(ctx, m, b.p, s.p, lam.p, S.p + SL_RHO, q1.p, q2.p, S.p, SL_LS);
+    if (tri_pending) launch_linesearch_resid(ctx, m, b.p, q3.p, s.p, lam.p, S.p + SL_RHO, q1.p, q2.p, S.p, SL_LS, SL_PINF);
+    else launch_linesearch_dots(ctx, m, b.p, s.p, lam.p, S.p + SL_RHO, q1.p, q2.p, S.p, SL_LS);
+    tri_pending = false;
 }
 
 long long Solver::finish_front(double rho, double *tau, double *p12) {

@@ -203,6 +203,7 @@ struct Solver {
     void q12p12();
     void lp_q12p12();
     bool p12_from_rows() const;
+    bool tri_pending = false; // q3 holds A(RR^T) that the line-search pass still has to move into constrValSum
     bool tri_ok() const;      // the dual gather pass can also deliver A(RR^T) (single cone over all constraints, sparse scratch)
     void primal_infeasibility(const double *Rm);                                 // fills S_host[SL_PINF] lazily
     double cal_obj(const double *Rm);                                            // <C, R R^T> / scaleObjHis
