@@ -347,10 +347,20 @@ int Solver::admm_optimize(lb2_params *P, long long iter_celling, double timeSolv
     init_constr_val_all(U.p, V.p, false);
     constr_val_sum();
     auto refresh_obj = [&]() {
+        // LORADSCalObjUV_ADMM (lorads_admm.c:325-337), LORADSCalDualObj and LORADSUpdateDimacsErrorADMM: R = (U+V)/2,
+        // <C,RR^T>, b.lambda, |b - A(RR^T)|; everything is enqueued first and the scalars come back in ONE read
         average_uv();
-        pObj = cal_obj(R.p);          // LORADSCalObjUV_ADMM, lorads_admm.c:325-337
-        dObj = cal_dual_obj();
-        update_dimacs_admm();
+        LB2_CUDA(cudaMemsetAsync(S.p + SL_OBJ, 0, sizeof(double), ctx.stream));
+        for (ConeDev &K : cones) cone_auv(K, true, R.p, R.p, true, 1.0, K.t1.p, S.p + SL_OBJ);
+        if (world > 1) allreduce(S.p + SL_OBJ, 1);
+        if (nLp > 0) launch_lp_obj(ctx, lp, R.p + N, R.p + N, 1.0, S.p + SL_OBJ, 0.0, nullptr);
+        launch_dot(ctx, m, b.p, lam.p, S.p, SL_DOBJ);
+        primal_infeasibility(R.p);    // also leaves constrVal / constrValSum = A(RR^T), as updateDimacsADMM does
+        read_slots();
+        pObj = S_host[SL_OBJ] / scaleObjHis;
+        dObj = S_host[SL_DOBJ] / scaleObjHis;
+        dimac_pinf = std::sqrt(S_host[SL_PINF]) / (1 + bNrm1);
+        dimac_gap = std::fabs(pObj - dObj) / (1 + std::fabs(pObj) + std::fabs(dObj));
     };
     refresh_obj();
     admm.pobj = pObj; admm.dobj = dObj; admm.gap = dimac_gap; admm.pinf_1 = dimac_pinf;
