@@ -564,9 +564,7 @@ void Solver::dual_infeasibility() {
         // steps, which the host discards by truncating the tridiagonal matrix at the first tiny beta.
         std::vector<double> lz_host(2 * (size_t)kLanczosMax);
         const double t_alloc = wall_time();
-        for (int cycle = 0; cycle < 600; ++cycle) {
-            ++n_cycles;
-            alpha.clear(); beta.clear();
+        auto enqueue_cycle = [&]() {
             for (int j = 0; j < kdim; ++j) {
                 // w = S v_j, then two classical Gram-Schmidt passes against v_0..v_j, each one dots kernel + one
                 // update kernel (full re-orthogonalisation; the first pass also yields alpha_j = v_j . S v_j and
@@ -577,6 +575,33 @@ void Solver::dual_infeasibility() {
                 launch_lanczos_dots(ctx, n, Vb.p, np2, j + 1, w.p, hbuf.p, hscratch.p, lz.p, -1);
                 launch_lanczos_update(ctx, n, Vb.p, np2, j + 1, hbuf.p, w.p, lz.p, kLanczosMax + j);
                 if (j + 1 < kdim) launch_lanczos_next(ctx, n, w.p, vec(j + 1), lz.p, kLanczosMax + j);
+            }
+        };
+        // the ~6*kdim launches of a cycle never change between restarts: record them once, replay as one graph
+        cudaGraphExec_t cycle_exec = nullptr;
+        long long cycle_launches = 0;
+        for (int cycle = 0; cycle < 600; ++cycle) {
+            ++n_cycles;
+            alpha.clear(); beta.clear();
+            if (!use_graphs) enqueue_cycle();
+            else {
+                if (!cycle_exec) {
+                    const long long l0 = ctx.launches;
+                    cudaGraph_t graph = nullptr;
+                    LB2_CUDA(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal));
+                    try { enqueue_cycle(); } catch (...) {
+                        cudaStreamEndCapture(ctx.stream, &graph);
+                        if (graph) cudaGraphDestroy(graph);
+                        throw;
+                    }
+                    LB2_CUDA(cudaStreamEndCapture(ctx.stream, &graph));
+                    LB2_CUDA(cudaGraphInstantiate(&cycle_exec, graph, 0));
+                    LB2_CUDA(cudaGraphDestroy(graph));
+                    cycle_launches = ctx.launches - l0;
+                    ctx.launches = l0;
+                }
+                LB2_CUDA(cudaGraphLaunch(cycle_exec, ctx.stream));
+                ctx.launches += cycle_launches;
             }
             LB2_CUDA(cudaMemcpyAsync(lz_host.data(), lz.p, sizeof(double) * lz_host.size(), cudaMemcpyDeviceToHost, ctx.stream));
             LB2_CUDA(cudaStreamSynchronize(ctx.stream));
@@ -609,6 +634,7 @@ void Solver::dual_infeasibility() {
             launch_lanczos_update(ctx, n, Vb.p, np2, mdim, hbuf.p, x0.p, S.p, SL_T1);
             launch_lanczos_next(ctx, n, x0.p, vec(0), S.p, SL_T1);
         }
+        if (cycle_exec) { LB2_CUDA(cudaStreamSynchronize(ctx.stream)); cudaGraphExecDestroy(cycle_exec); }
         if (timing) fprintf(stderr, "  dual infeasibility cone %lld: setup %.3f s, %d cycles %.3f s\n", c, t_alloc - t_begin, n_cycles, wall_time() - t_alloc);
         total += std::fabs(std::min(theta, 0.0));
     }
