@@ -168,7 +168,9 @@ lb2_int lb2_host_rank_rule(lb2_int n, lb2_int nNonzeroCoeff, lb2_int nCones, dou
  *       6 1 if the cone uses the dense scratch path, 7 nnz of the cone, 8 active constraints of the cone,
  *       9 rank_max, 10 local rank (column shard) , 11 kernel launches so far, 12 nnzA, 13 nnzC,
  *       14 adjacency entries (2|P| - #diag), 15 items of [A;C], 16 items of A, 17 padded row length ld,
- *       18 length N of the concatenated factor vectors */
+ *       18 length N of the concatenated factor vectors (PSD cones only), 19 nLpCols,
+ *       20 1 if the pipelined ALM step uses the three-output gather pass (single cone over all constraints,
+ *          sparse scratch, no LP block) */
 lb2_int lb2_info(const lb2_solver *s, int what, lb2_int iCone);
 /* what: 0 cObjNrm1, 1 cObjNrm2, 2 cObjNrmInf, 3 bNrm1, 4 bNrm2, 5 bNrmInf, 6 rho0, 7 pObj, 8 dObj,
  *       9 pinf(1), 10 gap, 11 dinf(1), 12 scaleObjHis */
