@@ -71,3 +71,58 @@ def test_column_assignment_covers_every_column_once():
             flat = sorted(c for o in owned for c in o)
             assert flat == list(range(r))
             assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+
+
+def _two_loop(g, sa, ya, sb, yb):
+    """L-BFGS two-loop recursion with two history pairs (a = newest) and H0 = I, as LBFGSDirection does it
+    (reference lorads_alm.c:230-391): D = -H g."""
+    ba, bb = 1.0 / float(ya @ sa), 1.0 / float(yb @ sb)
+    q = g.copy()
+    aa = ba * float(sa @ q); q -= aa * ya
+    ab = bb * float(sb @ q); q -= ab * yb
+    wb = ab - bb * float(yb @ q); q += wb * sb
+    wa = aa - ba * float(ya @ q); q += wa * sa
+    return -q
+
+
+def _gram_worker(rank, world, port, q):
+    """Sharded Gram-table L-BFGS (what column-sharded runs use): every rank reduces its slice to the 8 dots of
+    launch_lbfgs_pair (+ y_b.y_b kept from the previous step), ONE all-reduce completes them, and the direction is a
+    linear combination with coefficients computed from the table alone."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)
+    n, r = 200, 10
+    g, sa, ya, sb, yb = (rng.standard_normal((n, r)) for _ in range(5))
+    ya += 2.0 * sa      # keep y.s away from zero
+    yb += 2.0 * sb
+    ref = _two_loop(*(x.ravel() for x in (g, sa, ya, sb, yb))).reshape(n, r)
+    cols = [k for k in range(r) if k % world == rank]
+    G, SA, YA, SB, YB = (x[:, cols].ravel() for x in (g, sa, ya, sb, yb))
+    table = torch.tensor([YA @ SA, YA @ YA, YA @ YB, YA @ SB, SA @ G, SB @ G, YA @ G, YB @ G, YB @ YB, YB @ SB], dtype=torch.float64)
+    dist.all_reduce(table, op=dist.ReduceOp.SUM)
+    d = table.numpy()
+    ba, bb = 1.0 / d[0], 1.0 / d[9]
+    aa = ba * d[4]
+    ab = bb * (d[5] - aa * d[3])
+    wb = ab - bb * (d[7] - aa * d[2] - ab * d[8])
+    wa = aa - ba * (d[6] - aa * d[1] - ab * d[2] + wb * d[3])
+    mine = -(G - aa * YA - ab * YB + wb * SB + wa * SA)
+    err = float(np.abs(mine - ref[:, cols].ravel()).max() / np.abs(ref).max())
+    q.put((rank, err))
+    dist.destroy_process_group()
+
+
+def test_sharded_gram_lbfgs_direction_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gram_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(err < 1e-11 for _, err in res), res
