@@ -158,6 +158,20 @@ int lb2_host_presolve(lb2_int n, lb2_int m, const lb2_int *coneMatBeg, const lb2
                       const double *coneMatElem, lb2_int *info, lb2_int *rows, lb2_int *cols);
 /* ALMLineSearch (lorads_alm.c:161-228) from its five m-vector sums {|q2|^2, q1.q2, q0.q2, |q1|^2, q0.q1};
  * returns rootNum, *tau is in/out exactly as in the reference. */
+/* Host-only view of the device layouts the pre-solve builds for one cone (no CUDA involved): lets a test validate item
+ * lists, the transposed constraint table and the adjacency against the reference WITHOUT a GPU.
+ * lb2_layout_info what: 0 n, 1 pattern size, 2 dense scratch path, 3 active constraints, 4 nnzA, 5 items of A,
+ *   6 items of [A;C], 7 adjacency entries, 8 tile size of A, 9 tile size of [A;C], 10 T entries, 11 split rows of [A;C]
+ * lb2_layout_get which (dst sized by the caller from lb2_layout_info):
+ *   int32: 0 act_idx, 1 P_row, 2 P_col, 3 A.ptr, 4 A.irow, 5 A.icol, 6 AC.ptr, 7 AC.irow, 8 AC.icol, 9 T_ptr, 10 T_con,
+ *          11 adj_ptr, 12 adj_col, 13 adj_pos;  double: 20 A.coef, 21 AC.coef, 22 T_val, 23 C_onP, 24 {c_rank1} */
+typedef struct lb2_layout lb2_layout;
+int lb2_layout_build(lb2_int n, lb2_int m, const lb2_int *coneMatBeg, const lb2_int *coneMatIdx, const double *coneMatElem,
+                     lb2_layout **out);
+lb2_int lb2_layout_info(const lb2_layout *l, int what);
+int lb2_layout_get(const lb2_layout *l, int which, void *dst);
+void lb2_layout_free(lb2_layout *l);
+
 lb2_int lb2_host_line_search(double rho, const double *sums, double p1, double p2, double *tau);
 /* LORADSDetermineRank rule for one cone (lorads_solver.c:290-319); returns the rank, *rankMax the cap. */
 lb2_int lb2_host_rank_rule(lb2_int n, lb2_int nNonzeroCoeff, lb2_int nCones, double timesLogRank, lb2_int *rankMax);

@@ -54,6 +54,7 @@ EXPORTS = [
     "lb2_time_alm_inner_iters", "lb2_alm_run_host", "lb2_bench_kernel", "lb2_alm_optimize", "lb2_alm_to_admm", "lb2_admm_optimize", "lb2_dual_infeasibility",
     "lb2_solve", "lb2_get_solution", "lb2_reopt", "lb2_average_uv", "lb2_copy_r_to_v", "lb2_get_state", "lb2_set_state", "lb2_host_presolve", "lb2_host_line_search", "lb2_host_rank_rule",
     "lb2_set_lp_data", "lb2_get_lp_vec", "lb2_set_lp_vec", "lb2_admm_init_constr", "lb2_admm_update_var",
+    "lb2_layout_build", "lb2_layout_info", "lb2_layout_get", "lb2_layout_free",
     "lb2_read_sdpa", "lb2_sdpa_save", "lb2_sdpa_info", "lb2_sdpa_get", "lb2_sdpa_free", "lb2_sdpa_last_error",
 ]
 
@@ -165,6 +166,47 @@ def host_presolve(cone, m: int):
         lib.lb2_host_presolve(cone.n, m, _i(beg), _i(idx), _d(elem), _i(info), _i(rows), _i(cols))
     keys = ["psize", "dense_path", "dense_cone", "n_act", "nnzA", "nnzC", "n_nonzero_coeff", "n_split_rows", "rank_one_objective"]
     return dict(zip(keys, info.tolist())), rows, cols
+
+
+def host_layout(cone, m: int) -> dict:
+    """The device layouts of one cone as numpy arrays, built on the host only (item lists of A and [A;C], the
+    constraint table transposed by pattern position, C on the pattern, the symmetric adjacency)."""
+    lib = load_library()
+    lib.lb2_layout_build.argtypes = [C.c_int64, C.c_int64, _ip, _ip, _dp, C.POINTER(C.c_void_p)]
+    lib.lb2_layout_info.argtypes = [C.c_void_p, C.c_int]
+    lib.lb2_layout_info.restype = C.c_int64
+    lib.lb2_layout_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.lb2_layout_free.argtypes = [C.c_void_p]
+    h = C.c_void_p()
+    beg = np.ascontiguousarray(cone.beg, dtype=np.int64)
+    idx = np.ascontiguousarray(cone.idx, dtype=np.int64)
+    elem = np.ascontiguousarray(cone.elem, dtype=np.float64)
+    if lib.lb2_layout_build(cone.n, m, _i(beg), _i(idx), _d(elem), C.byref(h)) != 0:
+        raise Lb2Error(lib.lb2_last_error().decode())
+    try:
+        info = [int(lib.lb2_layout_info(h, k)) for k in range(12)]
+        n, psize, dense, n_act, nnzA, itA, itAC, nadj, tileA, tileAC, nT, nsplit = info
+        out = dict(n=n, psize=psize, dense_path=bool(dense), n_act=n_act, nnzA=nnzA, tile_A=tileA, tile_AC=tileAC, n_split_AC=nsplit)
+
+        def geti(which, count):
+            a = np.zeros(max(count, 1), np.int32)
+            lib.lb2_layout_get(h, which, a.ctypes.data_as(C.c_void_p))
+            return a[:count]
+
+        def getd(which, count):
+            a = np.zeros(max(count, 1), np.float64)
+            lib.lb2_layout_get(h, which, a.ctypes.data_as(C.c_void_p))
+            return a[:count]
+        npat = 0 if dense else psize
+        out.update(act_idx=geti(0, n_act), P_row=geti(1, npat), P_col=geti(2, npat),
+                   A_ptr=geti(3, n_act + 1), A_irow=geti(4, itA), A_icol=geti(5, itA), A_coef=getd(20, itA),
+                   AC_ptr=geti(6, n_act + 2), AC_irow=geti(7, itAC), AC_icol=geti(8, itAC), AC_coef=getd(21, itAC),
+                   T_con=geti(10, nT), T_val=getd(22, nT), C_onP=getd(23, psize), c_rank1=float(getd(24, 1)[0]))
+        if not dense:
+            out.update(T_ptr=geti(9, psize + 1), adj_ptr=geti(11, n + 1), adj_col=geti(12, nadj), adj_pos=geti(13, nadj))
+        return out
+    finally:
+        lib.lb2_layout_free(h)
 
 
 def read_sdpa(path: str, save_binary: str | None = None) -> Instance:

@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <string>
 
 #include "solver.hpp"
@@ -237,6 +238,49 @@ int lb2_host_presolve(lb2_int n, lb2_int m, const lb2_int *beg, const lb2_int *i
         for (size_t p = 0; p < L.P_row.size(); ++p) { rows[p] = L.P_row[p]; cols[p] = L.P_col[p]; }
     LB2_CATCH
 }
+
+struct lb2_layout { ConeLayout L; };
+
+int lb2_layout_build(lb2_int n, lb2_int m, const lb2_int *beg, const lb2_int *idx, const double *elem, lb2_layout **out) {
+    if (!beg || !out || n <= 0 || m <= 0) { g_err = "lb2_layout_build: bad argument"; return LB2_ERR_ARG; }
+    LB2_TRY
+    std::unique_ptr<lb2_layout> h(new lb2_layout());
+    h->L = build_cone_layout(n, m, beg, idx, elem);
+    if (h->L.c_rank1 != 0.0 && h->L.dense_path) h->L = build_cone_layout(n, m, beg, idx, elem, false);   // as Solver::preprocess
+    *out = h.release();
+    LB2_CATCH
+}
+
+lb2_int lb2_layout_info(const lb2_layout *l, int what) {
+    if (!l) return -1;
+    const ConeLayout &L = l->L;
+    switch (what) {
+    case 0: return L.n; case 1: return L.psize(); case 2: return L.dense_path; case 3: return L.n_act; case 4: return L.nnzA;
+    case 5: return L.listA.n_items(); case 6: return L.listAC.n_items(); case 7: return (lb2_int)L.adj_col.size();
+    case 8: return L.listA.tile; case 9: return L.listAC.tile; case 10: return (lb2_int)L.T_con.size();
+    case 11: return (lb2_int)L.listAC.split_row.size();
+    }
+    return -1;
+}
+
+int lb2_layout_get(const lb2_layout *l, int which, void *dst) {
+    if (!l || !dst) return LB2_ERR_ARG;
+    const ConeLayout &L = l->L;
+    auto put = [&](const auto &v) { if (!v.empty()) std::memcpy(dst, v.data(), sizeof(v[0]) * v.size()); return LB2_OK; };
+    switch (which) {
+    case 0: return put(L.act_idx); case 1: return put(L.P_row); case 2: return put(L.P_col);
+    case 3: return put(L.listA.ptr); case 4: return put(L.listA.irow); case 5: return put(L.listA.icol);
+    case 6: return put(L.listAC.ptr); case 7: return put(L.listAC.irow); case 8: return put(L.listAC.icol);
+    case 9: return put(L.T_ptr); case 10: return put(L.T_con);
+    case 11: return put(L.adj_ptr); case 12: return put(L.adj_col); case 13: return put(L.adj_pos);
+    case 20: return put(L.listA.coef); case 21: return put(L.listAC.coef); case 22: return put(L.T_val); case 23: return put(L.C_onP);
+    case 24: *(double *)dst = L.c_rank1; return LB2_OK;
+    }
+    g_err = "lb2_layout_get: unknown array";
+    return LB2_ERR_ARG;
+}
+
+void lb2_layout_free(lb2_layout *l) { delete l; }
 
 lb2_int lb2_host_line_search(double rho, const double *sums, double p1, double p2, double *tau) {
     return line_search(rho, sums, p1, p2, tau);

@@ -1,0 +1,83 @@
+"""Host logic of the product, checked on the CPU: the device layouts the pre-solve builds (item lists of A and
+[A;C], the constraint table transposed by pattern position, C on the pattern, the symmetric adjacency, the rank-one
+objective split) are exported by the host-only lb2_layout_* entry points and evaluated HERE in numpy against the
+golden outputs of the reference's A(UV^T), objective and (C + A^*(w)) X.  No GPU, no library arithmetic."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from lorads_b200 import capi, sdpa
+
+TOL = 1e-12
+
+
+def item_values(lay, which, U, V):
+    irow, icol, coef, ptr = lay[which + "_irow"], lay[which + "_icol"], lay[which + "_coef"], lay[which + "_ptr"]
+    n = lay["n"]
+    if lay["dense_path"]:
+        i, j = sdpa.unpack_idx(n, irow.astype(np.int64))
+    else:
+        i, j = irow.astype(np.int64), icol.astype(np.int64)
+    z = 0.5 * (np.einsum("ij,ij->i", U[i], V[j]) + np.einsum("ij,ij->i", U[j], V[i]))
+    rows = np.repeat(np.arange(ptr.size - 1), np.diff(ptr))
+    out = np.zeros(ptr.size - 1)
+    np.add.at(out, rows, coef * z)
+    return out
+
+
+def test_layout_reproduces_reference_operators(golden):
+    name, g, inst = golden
+    w = g["w"]
+    for c, cone in enumerate(inst.cones):
+        lay = capi.host_layout(cone, inst.m)
+        U, V = g[f"U{c}"], g[f"V{c}"]
+        # tiles: short lists use 128-item tiles, rows never straddle more tiles than recorded
+        assert lay["tile_A"] in (128, 512) and lay["tile_AC"] in (128, 512)
+        # A(sym(U V^T)) from the constraint item list, scattered to the global constraint index
+        compact = item_values(lay, "A", U, V)
+        full = np.zeros(inst.m)
+        full[lay["act_idx"]] = compact
+        assert rel_err(full, g[f"auv_UV{c}"]) < TOL
+        # [A;C] list: same constraint rows, last row = <C, sym(U V^T)> (+ the rank-one part kept outside the list)
+        ac = item_values(lay, "AC", U, V)
+        assert rel_err(ac[:-1], compact) < TOL
+        obj = ac[-1] + lay["c_rank1"] * float(U.sum(axis=0) @ V.sum(axis=0))
+        assert abs(obj - float(g[f"obj_UV{c}"])) <= TOL * max(1.0, abs(float(g[f"obj_UV{c}"])))
+        if lay["dense_path"]:
+            continue
+        # S = C + A^*(w) on the pattern from the transposed table, then Y = S V through the adjacency
+        npat = lay["psize"]
+        wc = w[lay["act_idx"]]
+        S = lay["C_onP"].copy()
+        pos = np.repeat(np.arange(npat), np.diff(lay["T_ptr"]))
+        np.add.at(S, pos, wc[lay["T_con"]] * lay["T_val"])
+        rows = np.repeat(np.arange(lay["n"]), np.diff(lay["adj_ptr"]))
+        Y = np.zeros_like(V)
+        np.add.at(Y, rows, S[lay["adj_pos"]][:, None] * V[lay["adj_col"]])
+        Y += lay["c_rank1"] * V.sum(axis=0)[None, :]
+        assert rel_err(Y, g[f"wsum_C{c}"]) < TOL
+        # the adjacency lists every off-diagonal pattern entry twice and every diagonal entry once, rows sorted
+        assert lay["adj_col"].size == 2 * npat - int((lay["P_row"] == lay["P_col"]).sum())
+        for i in range(0, lay["n"], max(1, lay["n"] // 50)):
+            seg = lay["adj_col"][lay["adj_ptr"][i]:lay["adj_ptr"][i + 1]]
+            assert np.all(np.diff(seg) > 0)
+
+
+def test_layout_of_shuffled_constraints():
+    """Constraint order in the file must not change the operators (sorted-run merge vs sort fallback in the pre-solve)."""
+    inst = sdpa.matrix_completion(40, 30, 400, 2, 3)
+    cone = inst.cones[0]
+    rng = np.random.default_rng(2)
+    perm = rng.permutation(inst.m)
+    counts = np.diff(cone.beg)
+    take = np.concatenate([np.arange(cone.beg[0], cone.beg[1])] + [np.arange(cone.beg[1 + p], cone.beg[2 + p]) for p in perm])
+    beg = np.concatenate([[0], np.cumsum([counts[0]] + [counts[1 + p] for p in perm])]).astype(np.int64)
+    sh = sdpa.Cone(n=cone.n, beg=beg, idx=cone.idx[take], elem=cone.elem[take])
+    a, b = capi.host_layout(cone, inst.m), capi.host_layout(sh, inst.m)
+    U, V = rng.standard_normal((cone.n, 5)), rng.standard_normal((cone.n, 5))
+    va, vb = item_values(a, "A", U, V), item_values(b, "A", U, V)
+    fa, fb = np.zeros(inst.m), np.zeros(inst.m)
+    fa[a["act_idx"]] = va
+    fb[b["act_idx"]] = vb
+    assert rel_err(fb, fa[perm]) < TOL          # new constraint k is old constraint perm[k]
+    assert np.array_equal(a["P_row"], b["P_row"]) and np.array_equal(a["P_col"], b["P_col"])
