@@ -2,7 +2,7 @@
 import os, sys, time, tempfile, functools
 print = functools.partial(print, flush=True)
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from lorads_b200 import sdpa
 from lorads_b200.capi import Solver, default_params
 from oracle import ref

@@ -1,11 +1,11 @@
 """Mixed SDP + LP instances: reference CPU binary vs the GPU drop-in binary vs the Python API, side by side."""
 import os, re, subprocess, sys, tempfile
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from lorads_b200 import sdpa
 from lorads_b200.capi import Solver, default_params
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REF = os.path.join(ROOT, "oracle", "_ref", "lorads_ref32")
 GPU = os.path.join(ROOT, "oracle", "_ref", "lorads_gpu32")
 CLI = os.path.join(ROOT, "lorads_b200", "lorads_b200_cli")
