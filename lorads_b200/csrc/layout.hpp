@@ -128,6 +128,22 @@ struct PhaseTimer {
     }
 };
 
+// Runs fn(lo, hi) over [0, total) cut into nth contiguous chunks, one thread each (nth == 1: inline).
+template <class F>
+inline void parallel_chunks(int64_t total, int nth, F fn) {
+    if (nth <= 1 || total < 2 * (int64_t)nth) { fn((int64_t)0, total); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nth; ++t) th.emplace_back(fn, total * t / nth, total * (t + 1) / nth);
+    for (std::thread &x : th) x.join();
+}
+
+// threads used by the pre-solve on large cones (LORADS_B200_PRESOLVE_THREADS overrides; every phase produces the
+// same arrays for any thread count)
+inline int presolve_threads(int64_t nnz_all) {
+    if (const char *e = getenv("LORADS_B200_PRESOLVE_THREADS")) return std::max(1, atoi(e));
+    return nnz_all > 2000000 ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+}
+
 // Build the layout of one cone from the reader's arrays (column 0 = C, column i = A_i).
 inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in, const int64_t *idx, const double *elem,
                                     bool allow_rank_one = true) {
@@ -155,13 +171,24 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
     pt.lap("copy + per-column order");
     // objective norms on the ORIGINAL C (dataMatSparseNrm1/Nrm2Square/NrmInf lorads_sdp_data.c:148-183; the dense
     // variants :227-272 are the same sums over the packed array)
-    for (int64_t k = beg_in[0]; k < beg_in[1]; ++k) {
-        int64_t r_, c_; unpack_lower(n, sidx[k], r_, c_);
-        const double v = sval[k], a = std::fabs(v);
-        const bool diag = r_ == c_;
-        L.cNrm1 += diag ? a : 2 * a;
-        L.cNrm2Sq += diag ? v * v : 2 * v * v;
-        L.cNrmInf = std::max(L.cNrmInf, a);
+    {
+        // the entries of C are sorted by packed index: an entry is diagonal iff it is the first position of its matrix
+        // column, found by walking the column starts (a closed-form unpack only after a long jump)
+        int64_t j = 0, start = 0, next = n;
+        for (int64_t k = beg_in[0]; k < beg_in[1]; ++k) {
+            const int64_t p = sidx[k];
+            if (p < start) { j = 0; start = 0; next = n; }
+            if (p - next > 8 * n) {
+                int64_t r_, c_; unpack_lower(n, p, r_, c_);
+                j = c_; start = j * n - j * (j - 1) / 2; next = start + (n - j);
+            }
+            while (p >= next) { start = next; ++j; next = start + (n - j); }
+            const double v = sval[k], a = std::fabs(v);
+            const bool diag = (p == start);
+            L.cNrm1 += diag ? a : 2 * a;
+            L.cNrm2Sq += diag ? v * v : 2 * v * v;
+            L.cNrmInf = std::max(L.cNrmInf, a);
+        }
     }
 
     // --- rank-one objective: a fully populated C whose entries are (almost) all one value c is stored as
@@ -187,6 +214,7 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
     }
     const int64_t *beg = vbeg.data();
     const int64_t nnz_all = beg[m + 1];
+    const int nthreads = presolve_threads(nnz_all);
 
     // --- classification (lorads_sdp_data.c:818-824) and statistics
     auto is_dense_type = [&](int64_t nnz) { return (double)nnz > 0.1 * packedSize; };
@@ -209,9 +237,12 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
     {
         // entries inside a column are sorted by packed index => columns of the matrix ascend; walk instead
         // of calling the closed form for every entry
-        for (int64_t c = 0; c <= m; ++c) {
+        parallel_chunks(nnz_all, nthreads, [&](int64_t lo, int64_t hi) {
+            if (lo >= hi) return;
+            int64_t c = (std::upper_bound(beg, beg + m + 2, lo) - beg) - 1;      // coefficient column holding entry lo
             int64_t j = 0, start = 0, next = n;   // packed range of matrix column j is [start, next)
-            for (int64_t k = beg[c]; k < beg[c + 1]; ++k) {
+            for (int64_t k = lo; k < hi; ++k) {
+                while (k >= beg[c + 1]) { ++c; j = 0; start = 0; next = n; }        // next coefficient: restart the walk
                 int64_t p = sidx[k];
                 if (p < start) { j = 0; start = 0; next = n; }
                 if (p - next > 8 * n) {           // far jump: use the closed form
@@ -222,7 +253,7 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
                 erow[k] = (int32_t)(p - start + j);
                 ecol[k] = (int32_t)j;
             }
-        }
+        });
     }
 
     pt.lap("norms, classes, rows/cols");
@@ -234,7 +265,9 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
         // constraints are one more whenever their keys happen to ascend (MaxCut, theta, matrix completion files do):
         // sort only what is not sorted, then merge the two runs.
         keys.resize(nnz_all);
-        for (int64_t k = 0; k < nnz_all; ++k) keys[k] = (int64_t)ecol[k] * n + erow[k];
+        parallel_chunks(nnz_all, nthreads, [&](int64_t lo, int64_t hi) {
+            for (int64_t k = lo; k < hi; ++k) keys[k] = (int64_t)ecol[k] * n + erow[k];
+        });
         auto mid = keys.begin() + beg[1];
         if (!std::is_sorted(keys.begin(), mid)) std::sort(keys.begin(), mid);
         if (!std::is_sorted(mid, keys.end())) std::sort(mid, keys.end());
@@ -315,9 +348,9 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
     // (merge-join: while the keys of consecutive entries ascend, the search continues from the previous hit with a
     //  galloping step; a binary search over the whole pattern is the fallback for a descending step)
     std::vector<int32_t> epos(nnz_all);
-    {
+    parallel_chunks(nnz_all, nthreads, [&](int64_t klo, int64_t khi) {
         int64_t prev_key = -1, prev_pos = 0;
-        for (int64_t k = 0; k < nnz_all; ++k) {
+        for (int64_t k = klo; k < khi; ++k) {
             const int64_t key = (int64_t)ecol[k] * n + erow[k];
             int64_t lo, hi;
             if (key >= prev_key) {
@@ -331,7 +364,7 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
             prev_key = key;
             epos[k] = (int32_t)prev_pos;
         }
-    }
+    });
     pt.lap("pattern positions");
     fill_items(L.listA, false);
     fill_items(L.listAC, true);
@@ -376,7 +409,7 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
         // The first pass scatters by ROW over the whole array (cache hostile at n = 1e6): it is split over threads by
         // row range, every thread scans P once and fills only the rows it owns, in the same order as a single scan.
         std::vector<int32_t> cur(L.adj_ptr.begin(), L.adj_ptr.end() - 1);
-        const int nth = (np > 2000000) ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+        const int nth = nthreads;
         auto lower_pass = [&](int64_t r0, int64_t r1) {
             for (int64_t p = 0; p < np; ++p) {       // lower part seen from the row: (row, col<row)
                 const int32_t r = L.P_row[p], c = L.P_col[p];
@@ -389,10 +422,16 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
             for (int t = 0; t < nth; ++t) th.emplace_back(lower_pass, n * t / nth, n * (t + 1) / nth);
             for (std::thread &x : th) x.join();
         }
-        for (int64_t p = 0; p < np; ++p) {           // diagonal and upper part: row c gets (r >= c)
-            int32_t r = L.P_row[p], c = L.P_col[p];
-            int32_t q = cur[c]++; L.adj_col[q] = r; L.adj_pos[q] = (int32_t)p;
-        }
+        // diagonal and upper part: row c gets (r >= c).  P is sorted by column, so a range of columns is a contiguous
+        // range of p and the threads touch disjoint rows.
+        parallel_chunks(n, nth, [&](int64_t c0, int64_t c1) {
+            const int64_t p0 = std::lower_bound(L.P_col.begin(), L.P_col.end(), (int32_t)c0) - L.P_col.begin();
+            const int64_t p1 = std::lower_bound(L.P_col.begin(), L.P_col.end(), (int32_t)c1) - L.P_col.begin();
+            for (int64_t p = p0; p < p1; ++p) {
+                int32_t r = L.P_row[p], c = L.P_col[p];
+                int32_t q = cur[c]++; L.adj_col[q] = r; L.adj_pos[q] = (int32_t)p;
+            }
+        });
     }
     pt.lap("adjacency");
     return L;

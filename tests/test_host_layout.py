@@ -81,3 +81,20 @@ def test_layout_of_shuffled_constraints():
     fb[b["act_idx"]] = vb
     assert rel_err(fb, fa[perm]) < TOL          # new constraint k is old constraint perm[k]
     assert np.array_equal(a["P_row"], b["P_row"]) and np.array_equal(a["P_col"], b["P_col"])
+
+
+def test_layout_is_independent_of_the_thread_count(monkeypatch):
+    """The pre-solve splits its passes over threads on large cones; every array must come out identical."""
+    inst = sdpa.lovasz_theta(150, 1200, 8)
+    mc = sdpa.maxcut(4000, 30000, 4)
+    for cone, m in ((inst.cones[0], inst.m), (mc.cones[0], mc.m)):
+        monkeypatch.setenv("LORADS_B200_PRESOLVE_THREADS", "1")
+        a = capi.host_layout(cone, m)
+        monkeypatch.setenv("LORADS_B200_PRESOLVE_THREADS", "7")
+        b = capi.host_layout(cone, m)
+        assert a.keys() == b.keys()
+        for k in a:
+            if isinstance(a[k], np.ndarray):
+                assert np.array_equal(a[k], b[k]), k
+            else:
+                assert a[k] == b[k], k
