@@ -98,3 +98,44 @@ def test_layout_is_independent_of_the_thread_count(monkeypatch):
                 assert np.array_equal(a[k], b[k]), k
             else:
                 assert a[k] == b[k], k
+
+
+EDGE = {
+    "maxcut_split_rows": lambda: sdpa.maxcut(500, 1800, 41),
+    "maxcut_n2000": lambda: sdpa.maxcut(2000, 19000, 42),
+    "maxcut_isolated": lambda: sdpa.maxcut(200, 60, 46),
+    "mcomp": lambda: sdpa.matrix_completion(150, 120, 3000, 3, 47),
+    "theta_dense": lambda: sdpa.lovasz_theta(90, 500, 48),
+    "tiny_dense": lambda: sdpa.maxcut(16, 40, 49),
+    "theta_rank_one": lambda: sdpa.lovasz_theta(300, 1500, 50),
+}
+
+
+@pytest.mark.parametrize("case", sorted(EDGE))
+def test_layout_edge_shapes_against_the_restatement(case):
+    """The edge shapes of the GPU parity suite, checked on the CPU: layout evaluated in numpy vs the C restatement of
+    the reference operators (oracle/lorads_oracle.c) on its srand(925) start."""
+    from oracle import restate
+    inst = EDGE[case]()
+    O = restate.OracleSolver(inst)
+    lay = capi.host_layout(inst.cones[0], inst.m)
+    U, V = O.factor("U").copy(), O.factor("V").copy()
+    compact = item_values(lay, "A", U, V)
+    full = np.zeros(inst.m)
+    full[lay["act_idx"]] = compact
+    assert rel_err(full, O.auv("U", "V")) < TOL
+    ac = item_values(lay, "AC", U, V)
+    obj = ac[-1] + lay["c_rank1"] * float(U.sum(axis=0) @ V.sum(axis=0))
+    ref_obj = O.obj_auv("U", "V")
+    assert abs(obj - ref_obj) <= TOL * max(1.0, abs(ref_obj))
+    if lay["dense_path"]:
+        return
+    w = np.random.default_rng(3).standard_normal(inst.m)
+    S = lay["C_onP"].copy()
+    pos = np.repeat(np.arange(lay["psize"]), np.diff(lay["T_ptr"]))
+    np.add.at(S, pos, w[lay["act_idx"]][lay["T_con"]] * lay["T_val"])
+    rows = np.repeat(np.arange(lay["n"]), np.diff(lay["adj_ptr"]))
+    Y = np.zeros_like(V)
+    np.add.at(Y, rows, S[lay["adj_pos"]][:, None] * V[lay["adj_col"]])
+    Y += lay["c_rank1"] * V.sum(axis=0)[None, :]
+    assert rel_err(Y, O.wsum_mulrk(w, True, "V")) < TOL
