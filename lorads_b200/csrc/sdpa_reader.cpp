@@ -85,18 +85,27 @@ int load_binary(const char *p, const char *end, lb2_sdpa **out) {
         S->rhs.resize((size_t)S->m);
         take(S->rhs.data(), sizeof(double) * (size_t)S->m);
         S->blocks.resize((size_t)nblk);
-        auto block = [&](lb2_sdpa::Block &B) {
+        auto block = [&](lb2_sdpa::Block &B, lb2_int index_limit) {
             lb2_int nnz = 0;
             take(&nnz, sizeof(nnz));
-            if (nnz < 0) throw std::runtime_error("bad binary instance block");
+            if (nnz < 0 || (size_t)nnz > (size_t)(end - p) / sizeof(double)) throw std::runtime_error("bad binary instance block");
             B.beg.resize((size_t)S->m + 2); B.idx.resize((size_t)nnz); B.elem.resize((size_t)nnz);
             take(B.beg.data(), sizeof(lb2_int) * B.beg.size());
             take(B.idx.data(), sizeof(lb2_int) * (size_t)nnz);
             take(B.elem.data(), sizeof(double) * (size_t)nnz);
-            if (B.beg.back() != nnz) throw std::runtime_error("bad binary instance block");
+            // a cache file is data from outside: column pointers must ascend from 0 to nnz, indices must be in range
+            if (B.beg.front() != 0 || B.beg.back() != nnz) throw std::runtime_error("bad binary instance block");
+            for (size_t c = 0; c + 1 < B.beg.size(); ++c)
+                if (B.beg[c] > B.beg[c + 1]) throw std::runtime_error("bad binary instance block");
+            for (lb2_int v : B.idx)
+                if (v < 0 || v >= index_limit) throw std::runtime_error("bad binary instance block");
         };
-        for (lb2_int k = 0; k < nblk; ++k) block(S->blocks[(size_t)k]);
-        if (S->nLpCols > 0) block(S->lp);
+        for (lb2_int k = 0; k < nblk; ++k) {
+            const lb2_int n = S->dims[(size_t)k];
+            if (n <= 0 || n > (lb2_int)3000000000LL) throw std::runtime_error("bad binary instance header");
+            block(S->blocks[(size_t)k], n * (n + 1) / 2);
+        }
+        if (S->nLpCols > 0) block(S->lp, S->nLpCols);
         *out = S.release();
     } catch (const std::exception &e) {
         g_reader_err = e.what();
