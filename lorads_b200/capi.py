@@ -204,6 +204,16 @@ def host_layout(cone, m: int) -> dict:
                    T_con=geti(10, nT), T_val=getd(22, nT), C_onP=getd(23, psize), c_rank1=float(getd(24, 1)[0]))
         if not dense:
             out.update(T_ptr=geti(9, psize + 1), adj_ptr=geti(11, n + 1), adj_col=geti(12, nadj), adj_pos=geti(13, nadj))
+            # vertex-centric class split (layout.hpp VcLayout)
+            vc_on, nu, nl, n_single, nnz_res, nd = (int(lib.lb2_layout_info(h, k)) for k in range(30, 36))
+            out.update(vc_on=bool(vc_on), vc_n_single=n_single, vc_nnz_res=nnz_res,
+                       vc_order=geti(30, n), vc_order_l=geti(31, n),
+                       vc_u_ptr=geti(32, n + 1), vc_u_mid=geti(33, n), vc_u_col=geti(34, nu), vc_u_tag=geti(35, nu),
+                       vc_u_val=getd(36, nu), vc_d_con=geti(37, nd), vc_d_coef=getd(38, nd),
+                       vc_l_ptr=geti(39, n + 1), vc_l_row=geti(40, nl), vc_l_con=geti(41, nl), vc_l_coef=getd(42, nl),
+                       vc_Tr_ptr=geti(43, psize + 1), vc_Tr_con=geti(44, nnz_res), vc_Tr_val=getd(45, nnz_res),
+                       vc_res_ptr=geti(46, n_act + 1), vc_res_irow=geti(47, nnz_res), vc_res_icol=geti(48, nnz_res),
+                       vc_res_coef=getd(49, nnz_res))
         return out
     finally:
         lib.lb2_layout_free(h)

@@ -528,7 +528,7 @@ void Solver::dual_infeasibility() {
     }
     for (long long c = 0; c < nCones; ++c) {
         ConeDev &K = cones[c];
-        cone_wsum(K, M1.p, false, true);
+        cone_wsum(K, M1.p, false, true, true);
         const long long n = K.n;
         int kdim = (40 > n) ? 2 : 40;       // dual_infeasible: ncv = 40, or 2 when ncv > n (lorads_sdp_conic.c:1288-1294)
         if (kdim > n) kdim = (int)n;

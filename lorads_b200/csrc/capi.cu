@@ -259,6 +259,9 @@ lb2_int lb2_layout_info(const lb2_layout *l, int what) {
     case 5: return L.listA.n_items(); case 6: return L.listAC.n_items(); case 7: return (lb2_int)L.adj_col.size();
     case 8: return L.listA.tile; case 9: return L.listAC.tile; case 10: return (lb2_int)L.T_con.size();
     case 11: return (lb2_int)L.listAC.split_row.size();
+    // vertex-centric layout
+    case 30: return L.vc.on; case 31: return (lb2_int)L.vc.u_col.size(); case 32: return (lb2_int)L.vc.l_row.size();
+    case 33: return L.vc.n_single; case 34: return L.vc.nnz_res; case 35: return (lb2_int)L.vc.d_con.size();
     }
     return -1;
 }
@@ -275,6 +278,13 @@ int lb2_layout_get(const lb2_layout *l, int which, void *dst) {
     case 11: return put(L.adj_ptr); case 12: return put(L.adj_col); case 13: return put(L.adj_pos);
     case 20: return put(L.listA.coef); case 21: return put(L.listAC.coef); case 22: return put(L.T_val); case 23: return put(L.C_onP);
     case 24: *(double *)dst = L.c_rank1; return LB2_OK;
+    case 30: return put(L.vc.order); case 31: return put(L.vc.order_l);
+    case 32: return put(L.vc.u_ptr); case 33: return put(L.vc.u_mid); case 34: return put(L.vc.u_col); case 35: return put(L.vc.u_tag);
+    case 36: return put(L.vc.u_val); case 37: return put(L.vc.d_con); case 38: return put(L.vc.d_coef);
+    case 39: return put(L.vc.l_ptr); case 40: return put(L.vc.l_row); case 41: return put(L.vc.l_con); case 42: return put(L.vc.l_coef);
+    case 43: return put(L.vc.Tr_ptr); case 44: return put(L.vc.Tr_con); case 45: return put(L.vc.Tr_val);
+    case 46: return put(L.vc.listRes.ptr); case 47: return put(L.vc.listRes.irow); case 48: return put(L.vc.listRes.icol);
+    case 49: return put(L.vc.listRes.coef);
     }
     g_err = "lb2_layout_get: unknown array";
     return LB2_ERR_ARG;
@@ -527,7 +537,10 @@ int lb2_bench_kernel(lb2_solver *s, int which, lb2_int reps, double *ms) {
         switch (which) {
         case 0:
             // what the pipelined ALM step launches: the three-output pass when it applies, else the dual pass
-            if (S.tri_ok())
+            if (S.tri_ok() && K.vc_on)
+                launch_vc_auv(S.ctx, AUV_TRI, K.vc, K.ld, true, S.R.p + K.off, S.U.p + K.off, 2.0, 1.0, K.t1.p, K.t2.p, S.q3.p,
+                              nullptr, nullptr);
+            else if (S.tri_ok())
                 launch_auv(S.ctx, AUV_TRI, K.listAC.dev, S.R.p + K.off, S.U.p + K.off, K.ld, 2.0, 1.0, K.t1.p, K.t2.p, K.carry1.p,
                            K.carry2.p, nullptr, nullptr, S.q3.p, K.carry3.p);
             else S.cone_auv_dual(K, S.R.p, S.U.p, K.t1.p, K.t2.p);

@@ -61,6 +61,34 @@ void launch_spmm(Ctx &c, long long n, int ld, const int *adj_ptr, const int *adj
                  const double *S, const double *X, double a, double b, const double *Z, const double *Z2,
                  double *Y, double *red, const double *cs = nullptr, double c1 = 0.0);
 
+// ------------------------------------------------------------------------------------------------
+// vertex-centric fast path (vc_kernels.cu; layout.hpp VcLayout): class-split adjacency, nothing materialised
+// ------------------------------------------------------------------------------------------------
+struct VcDev {
+    long long n = 0;
+    int obj_row = 0;                       // index of the objective row in the A(UV^T) outputs (= n_act)
+    const int *order = nullptr;            // rows by decreasing SpMM work
+    const int *order_l = nullptr;          // rows by decreasing A(UV^T) work
+    // adjU: row i = [u_ptr[i], u_mid[i]) weight-dependent entries (tag >= 0 singleton constraint, tag <= -2 residual
+    // pattern position -2-tag), [u_mid[i], u_ptr[i+1]) objective entries (tag -1, value inline)
+    const int *u_ptr = nullptr, *u_mid = nullptr, *u_col = nullptr, *u_tag = nullptr;
+    const double *u_val = nullptr;
+    const int *d_con = nullptr; const double *d_coef = nullptr;                                           // diagonal singletons
+    const int *l_ptr = nullptr, *l_row = nullptr, *l_con = nullptr; const double *l_coef = nullptr;       // lowA (others)
+};
+int vc_max_ld();
+// Y[i,:] = a * sum_{e in adjU(i)} s_e X[col_e,:] + b Z[i,:],  s_e = value (objective entries, only when useC),
+// w[map(tag)] * value (singleton constraints) or Sres[-2-tag] (residual positions).  w == nullptr and Sres == nullptr
+// skip the weight-dependent part; wmap (compact -> global constraint index) may be null.
+// red / cs / c1 as launch_spmm.
+void launch_vc_spmm(Ctx &c, const VcDev &V, int ld, bool useC, const double *w, const int *wmap, const double *Sres,
+                    const double *X, double a, double b, const double *Z, const double *Z2, double *Y, double *red,
+                    const double *cs = nullptr, double c1 = 0.0);
+// A(sym(U W^T)) of the singleton constraints (written straight to their rows) and, with_obj, the objective row
+// <C, sym(U W^T)> (also added to *obj1 / *obj2).  mode: AUV_SAME / AUV_PAIR / AUV_DUAL / AUV_TRI.
+void launch_vc_auv(Ctx &c, AuvMode mode, const VcDev &V, int ld, bool with_obj, const double *U, const double *W, double s1,
+                   double s2, double *out1, double *out2, double *out3, double *obj1, double *obj2);
+
 // rank-one objective C = c1 * e e^T (+ sparse remainder): column sums of a factor, and the objective terms
 // out[k] = sum_i X[i,k]  (deterministic two-level sum; scratch >= 4*148*ld doubles)
 void launch_colsum(Ctx &c, long long n, int ld, const double *X, double *out, double *scratch);

@@ -47,6 +47,30 @@ struct ItemList {
     int64_t n_tiles() const { return (n_items() + tile - 1) / tile; }
 };
 
+// Vertex-centric layout of a sparse-scratch cone (the fast path of the two gather kernels).  The coefficients are
+// split by class so that nothing has to be materialised on the pattern per evaluation.  Row i of the symmetric
+// adjacency `adjU` lists (neighbour, tag, value) entries, the weight-dependent ones first:
+//   [u_ptr[i], u_mid[i])    tag >= 0 : entry of SINGLETON constraint `tag` (exactly one stored non-zero: MaxCut
+//                                      diagonals, the edge constraints of Lovasz theta, the samples of matrix
+//                                      completion), S value = w[tag] * value;
+//                           tag <= -2: pattern position -2-tag of the remaining ("residual", multi-entry) constraints,
+//                                      whose weighted sum is still materialised on the pattern (T restricted to them);
+//   [u_mid[i], u_ptr[i+1])  tag == -1: entry of the objective C, value inline.
+// For A(UV^T) the singleton entries are needed once (lower triangle): the diagonal ones per column in d_con/d_coef
+// (read with the owner row), the others in lowA (CSC by column); residual constraints go through the generic item
+// kernel (listRes).  `order`/`order_l` list the rows by decreasing work so that the lane groups of a warp walk rows
+// of equal length.
+struct VcLayout {
+    bool on = false;
+    int64_t n_single = 0, n_res = 0, nnz_res = 0;
+    std::vector<int32_t> order, order_l;
+    std::vector<int32_t> u_ptr, u_mid, u_col, u_tag; std::vector<double> u_val;
+    std::vector<int32_t> d_con; std::vector<double> d_coef;
+    std::vector<int32_t> l_ptr, l_row, l_con; std::vector<double> l_coef;
+    std::vector<int32_t> Tr_ptr, Tr_con; std::vector<double> Tr_val;
+    ItemList listRes;
+};
+
 struct ConeLayout {
     int64_t n = 0;          // block dimension
     int64_t m = 0;          // global number of constraints
@@ -67,6 +91,7 @@ struct ConeLayout {
     ItemList listA, listAC;
     std::vector<int32_t> T_ptr, T_con; std::vector<double> T_val;   // CSC by pattern position
     std::vector<int32_t> adj_ptr, adj_col, adj_pos;                 // symmetric adjacency CSR
+    VcLayout vc;                                                    // class-split vertex-centric layout
     // dense path: positions touched by any constraint, CSR over those positions
     std::vector<long long> D_pos;                   // unique packed positions with constraint entries
     int64_t psize() const { return dense_path ? n * (n + 1) / 2 : (int64_t)P_row.size(); }
@@ -142,6 +167,27 @@ inline void parallel_chunks(int64_t total, int nth, F fn) {
 inline int presolve_threads(int64_t nnz_all) {
     if (const char *e = getenv("LORADS_B200_PRESOLVE_THREADS")) return std::max(1, atoi(e));
     return nnz_all > 2000000 ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+}
+
+
+// Symmetric CSR (rows sorted by neighbour) from lower-triangular entries (row >= col) given in (col,row) order.
+// alloc(total) is called once the slot count is known, then emit(q, k, other) once per adjacency slot q for entry k
+// with `other` = the neighbour index.
+template <class Alloc, class Emit>
+inline void sym_csr_from_lower(int64_t n, int64_t cnt, const int32_t *row, const int32_t *col, std::vector<int32_t> &ptr,
+                               Alloc alloc, Emit emit) {
+    ptr.assign(n + 1, 0);
+    for (int64_t k = 0; k < cnt; ++k) {
+        ptr[row[k] + 1]++;
+        if (row[k] != col[k]) ptr[col[k] + 1]++;
+    }
+    for (int64_t i = 0; i < n; ++i) ptr[i + 1] += ptr[i];
+    alloc((int64_t)ptr[n]);
+    std::vector<int32_t> cur(ptr.begin(), ptr.end() - 1);
+    for (int64_t k = 0; k < cnt; ++k)            // (row, col < row): columns ascend along the list
+        if (row[k] != col[k]) emit(cur[row[k]]++, k, col[k]);
+    for (int64_t k = 0; k < cnt; ++k)            // diagonal, then (col, row > col): rows ascend inside a column
+        emit(cur[col[k]]++, k, row[k]);
 }
 
 // Build the layout of one cone from the reader's arrays (column 0 = C, column i = A_i).
@@ -434,6 +480,128 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
         });
     }
     pt.lap("adjacency");
+    // ----------------------------- vertex-centric class split -----------------------------
+    {
+        VcLayout &V = L.vc;
+        // lower-triangular entries (row >= col) of the three classes, each list in (col,row) order
+        struct Ent { int32_t row, col, tag; double val; };
+        std::vector<Ent> dyn, sta;
+        // objective: entries of column 0 are already in (col,row) order
+        sta.reserve(beg[1] - beg[0]);
+        for (int64_t k = beg[0]; k < beg[1]; ++k) sta.push_back({erow[k], ecol[k], -1, sval[k]});
+        // singleton constraints
+        V.d_con.assign(n, -1); V.d_coef.assign(n, 0.0);
+        std::vector<Ent> low;
+        V.n_single = 0;
+        for (int64_t a = 0; a < L.n_act; ++a) {
+            const int64_t i = L.act_idx[a];
+            if (beg[i + 2] - beg[i + 1] != 1) continue;
+            const int64_t k = beg[i + 1];
+            V.n_single++;
+            dyn.push_back({erow[k], ecol[k], (int32_t)a, sval[k]});
+            if (erow[k] == ecol[k] && V.d_con[erow[k]] < 0) { V.d_con[erow[k]] = (int32_t)a; V.d_coef[erow[k]] = sval[k]; }
+            else low.push_back({erow[k], ecol[k], (int32_t)a, (erow[k] == ecol[k]) ? sval[k] : 2.0 * sval[k]});
+        }
+        V.n_res = L.n_act - V.n_single;
+        auto by_pos = [&](const Ent &x, const Ent &y) { return x.col != y.col ? x.col < y.col : x.row < y.row; };
+        if (!std::is_sorted(low.begin(), low.end(), by_pos)) std::stable_sort(low.begin(), low.end(), by_pos);
+        V.l_ptr.assign(n + 1, 0);
+        for (const Ent &e : low) V.l_ptr[e.col + 1]++;
+        for (int64_t j = 0; j < n; ++j) V.l_ptr[j + 1] += V.l_ptr[j];
+        V.l_row.resize(low.size()); V.l_con.resize(low.size()); V.l_coef.resize(low.size());
+        for (size_t q = 0; q < low.size(); ++q) { V.l_row[q] = low[q].row; V.l_con[q] = low[q].tag; V.l_coef[q] = low[q].val; }
+        // residual constraints: item list (all n_act rows, singleton rows empty), T restricted to them, and one
+        // weight-dependent adjacency entry per touched pattern position
+        {
+            ItemList &IL = V.listRes;
+            IL.has_obj = false;
+            IL.n_rows = L.n_act;
+            IL.ptr.assign(IL.n_rows + 1, 0);
+            int64_t total = 0;
+            for (int64_t a = 0; a < L.n_act; ++a) {
+                const int64_t i = L.act_idx[a], cntk = beg[i + 2] - beg[i + 1];
+                if (cntk != 1) total += cntk;
+            }
+            V.nnz_res = total;
+            IL.irow.resize(total); IL.icol.resize(total); IL.coef.resize(total);
+            V.Tr_ptr.assign(np + 1, 0);
+            int64_t w = 0;
+            for (int64_t a = 0; a < L.n_act; ++a) {
+                const int64_t i = L.act_idx[a], cntk = beg[i + 2] - beg[i + 1];
+                if (cntk != 1)
+                    for (int64_t k = beg[i + 1]; k < beg[i + 2]; ++k) {
+                        IL.irow[w] = erow[k]; IL.icol[w] = ecol[k];
+                        IL.coef[w] = (erow[k] == ecol[k]) ? sval[k] : 2.0 * sval[k];
+                        ++w;
+                        V.Tr_ptr[epos[k] + 1]++;
+                    }
+                IL.ptr[a + 1] = (int32_t)w;
+            }
+            finish_item_list(IL);
+            for (int64_t p = 0; p < np; ++p) V.Tr_ptr[p + 1] += V.Tr_ptr[p];
+            V.Tr_con.resize(total); V.Tr_val.resize(total);
+            std::vector<int32_t> cur(V.Tr_ptr.begin(), V.Tr_ptr.end() - 1);
+            for (int64_t a = 0; a < L.n_act; ++a) {
+                const int64_t i = L.act_idx[a], cntk = beg[i + 2] - beg[i + 1];
+                if (cntk == 1) continue;
+                for (int64_t k = beg[i + 1]; k < beg[i + 2]; ++k) {
+                    const int32_t q = cur[epos[k]]++;
+                    V.Tr_con[q] = (int32_t)a; V.Tr_val[q] = sval[k];
+                }
+            }
+            for (int64_t p = 0; p < np; ++p)
+                if (V.Tr_ptr[p + 1] > V.Tr_ptr[p]) dyn.push_back({L.P_row[p], L.P_col[p], (int32_t)(-2 - p), 0.0});
+        }
+        if (!std::is_sorted(dyn.begin(), dyn.end(), by_pos)) std::stable_sort(dyn.begin(), dyn.end(), by_pos);
+        // symmetric adjacency: per row the weight-dependent entries, then the objective entries
+        std::vector<int32_t> dptr, sptr, dslot, sslot;
+        {
+            std::vector<int32_t> r(dyn.size()), c(dyn.size());
+            for (size_t q = 0; q < dyn.size(); ++q) { r[q] = dyn[q].row; c[q] = dyn[q].col; }
+            std::vector<int32_t> okind, oother;
+            sym_csr_from_lower(n, (int64_t)dyn.size(), r.data(), c.data(), dptr, [&](int64_t t) { dslot.resize(t); oother.resize(t); },
+                               [&](int32_t q, int64_t k, int32_t other) { dslot[q] = (int32_t)k; oother[q] = other; });
+            std::vector<int32_t> r2(sta.size()), c2(sta.size()), sother;
+            for (size_t q = 0; q < sta.size(); ++q) { r2[q] = sta[q].row; c2[q] = sta[q].col; }
+            sym_csr_from_lower(n, (int64_t)sta.size(), r2.data(), c2.data(), sptr, [&](int64_t t) { sslot.resize(t); sother.resize(t); },
+                               [&](int32_t q, int64_t k, int32_t other) { sslot[q] = (int32_t)k; sother[q] = other; });
+            const int64_t total = (int64_t)dslot.size() + (int64_t)sslot.size();
+            if (total > (int64_t)2000000000) throw std::runtime_error("adjacency exceeds 2^31 entries");
+            V.u_ptr.assign(n + 1, 0); V.u_mid.assign(n, 0);
+            V.u_col.resize(total); V.u_tag.resize(total); V.u_val.resize(total);
+            int64_t w = 0;
+            for (int64_t i = 0; i < n; ++i) {
+                V.u_ptr[i] = (int32_t)w;
+                for (int32_t q = dptr[i]; q < dptr[i + 1]; ++q, ++w) {
+                    V.u_col[w] = oother[q]; V.u_tag[w] = dyn[dslot[q]].tag; V.u_val[w] = dyn[dslot[q]].val;
+                }
+                V.u_mid[i] = (int32_t)w;
+                for (int32_t q = sptr[i]; q < sptr[i + 1]; ++q, ++w) {
+                    V.u_col[w] = sother[q]; V.u_tag[w] = -1; V.u_val[w] = sta[sslot[q]].val;
+                }
+            }
+            V.u_ptr[n] = (int32_t)w;
+        }
+        // rows by decreasing work (stable counting sort).  Sorting pays while the factors are L2 resident; on very
+        // large blocks the scattered row order costs more DRAM locality than the balance gains (measured, n = 1e6)
+        auto by_work = [&](std::vector<int32_t> &out, auto work) {
+            out.resize(n);
+            if (n > 250000) { std::iota(out.begin(), out.end(), 0); return; }
+            std::vector<int32_t> deg(n);
+            int32_t dmax = 0;
+            for (int64_t i = 0; i < n; ++i) { deg[i] = work(i); dmax = std::max(dmax, deg[i]); }
+            std::vector<int64_t> start((size_t)dmax + 2, 0);
+            for (int64_t i = 0; i < n; ++i) start[dmax - deg[i] + 1]++;
+            for (int32_t d = 0; d <= dmax; ++d) start[d + 1] += start[d];
+            for (int64_t i = 0; i < n; ++i) out[start[dmax - deg[i]]++] = (int32_t)i;
+        };
+        by_work(V.order, [&](int64_t i) { return V.u_ptr[i + 1] - V.u_ptr[i]; });
+        by_work(V.order_l, [&](int64_t i) { return (V.u_ptr[i + 1] - V.u_mid[i]) + 2 * (V.l_ptr[i + 1] - V.l_ptr[i]); });
+        // the fast path pays off when singleton constraints carry most of the constraint non-zeros
+        V.on = L.nnzA == 0 || 2 * V.n_single >= L.n_act;
+        if (const char *e = getenv("LORADS_B200_VC")) V.on = atoi(e) != 0;
+    }
+    pt.lap("vertex-centric split");
     return L;
 }
 

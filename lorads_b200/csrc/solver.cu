@@ -198,7 +198,9 @@ void Solver::preprocess() {
         K.listA.upload(L.listA);
         K.listAC.upload(L.listAC);
         K.obj_item_begin = L.listAC.ptr[L.n_act];
-        const size_t ntile = (size_t)std::max<long long>(1, K.listAC.dev.n_tiles);
+        // the carry buffers serve every item list of the cone (lists of different length use different tile sizes)
+        const size_t ntile = (size_t)std::max<long long>(
+            1, std::max<long long>(std::max<long long>(K.listAC.dev.n_tiles, K.listA.dev.n_tiles), L.vc.listRes.n_tiles()));
         K.carry1.alloc(2 * ntile); K.carry2.alloc(2 * ntile); K.carry3.alloc(2 * ntile);
         K.C_onP.upload(L.C_onP);
         K.S.alloc((size_t)K.np);
@@ -210,6 +212,30 @@ void Solver::preprocess() {
         } else {
             K.adj_ptr.upload(L.adj_ptr); K.adj_col.upload(L.adj_col); K.adj_pos.upload(L.adj_pos);
             K.P_row_h = L.P_row; K.P_col_h = L.P_col;
+            K.vc_on = L.vc.on;
+            if (K.vc_on) {
+                const VcLayout &V = L.vc;
+                K.vc_nnz_res = V.nnz_res;
+                K.vc_order.upload(V.order); K.vc_order_l.upload(V.order_l);
+                K.vc.n = K.n; K.vc.obj_row = (int)K.n_act;
+                K.vc.order = K.vc_order.p; K.vc.order_l = K.vc_order_l.p;
+                K.vc_u_ptr.upload(V.u_ptr); K.vc_u_mid.upload(V.u_mid); K.vc_u_col.upload(V.u_col); K.vc_u_tag.upload(V.u_tag);
+                K.vc_u_val.upload(V.u_val);
+                K.vc.u_ptr = K.vc_u_ptr.p; K.vc.u_mid = K.vc_u_mid.p; K.vc.u_col = K.vc_u_col.p; K.vc.u_tag = K.vc_u_tag.p;
+                K.vc.u_val = K.vc_u_val.p;
+                if (V.n_single > 0) {
+                    K.vc_d_con.upload(V.d_con); K.vc_d_coef.upload(V.d_coef);
+                    K.vc.d_con = K.vc_d_con.p; K.vc.d_coef = K.vc_d_coef.p;
+                }
+                if (!V.l_row.empty()) {
+                    K.vc_l_ptr.upload(V.l_ptr); K.vc_l_row.upload(V.l_row); K.vc_l_con.upload(V.l_con); K.vc_l_coef.upload(V.l_coef);
+                    K.vc.l_ptr = K.vc_l_ptr.p; K.vc.l_row = K.vc_l_row.p; K.vc.l_con = K.vc_l_con.p; K.vc.l_coef = K.vc_l_coef.p;
+                }
+                if (V.nnz_res > 0) {
+                    K.vc_Tr_ptr.upload(V.Tr_ptr); K.vc_Tr_con.upload(V.Tr_con); K.vc_Tr_val.upload(V.Tr_val);
+                    K.vc_listRes.upload(V.listRes);
+                }
+            }
         }
         K.cv.alloc((size_t)K.n_act + 1); K.t1.alloc((size_t)K.n_act + 1); K.t2.alloc((size_t)K.n_act + 1);
         cObjNrm1 += K.cNrm1; n2 += K.cNrm2Sq; cObjNrmInf = std::max(cObjNrmInf, K.cNrmInf);
@@ -433,8 +459,17 @@ void Solver::cone_auv(ConeDev &K, bool with_obj, const double *Um, const double 
         return;
     }
     // with column sharding the objective is summed over ranks by the caller (the slot is all-reduced once)
-    launch_auv(ctx, same ? AUV_SAME : AUV_PAIR, L.dev, Um + K.off, Vm + K.off, K.ld, scale, 0.0, out, nullptr,
-               K.carry1.p, nullptr, obj, nullptr);
+    if (K.vc_on) {
+        // multi-entry constraints through the item kernel (it clears the rows it does not own), then the singleton
+        // rows and the objective row from the vertex-centric pass
+        if (K.vc_nnz_res > 0)
+            launch_auv(ctx, same ? AUV_SAME : AUV_PAIR, K.vc_listRes.dev, Um + K.off, Vm + K.off, K.ld, scale, 0.0, out, nullptr,
+                       K.carry1.p, nullptr, nullptr, nullptr);
+        launch_vc_auv(ctx, same ? AUV_SAME : AUV_PAIR, K.vc, K.ld, with_obj, Um + K.off, Vm + K.off, scale, 0.0, out, nullptr,
+                      nullptr, obj, nullptr);
+    } else
+        launch_auv(ctx, same ? AUV_SAME : AUV_PAIR, L.dev, Um + K.off, Vm + K.off, K.ld, scale, 0.0, out, nullptr,
+                   K.carry1.p, nullptr, obj, nullptr);
     if (with_obj && obj && K.c_rank1 != 0.0) {
         // <c ee^T, sym(U V^T)> = c (e^T U)(V^T e)
         launch_colsum(ctx, K.n, K.ld, Um + K.off, K.csA.p, K.cs_scratch.p);
@@ -456,7 +491,13 @@ void Solver::cone_auv_dual(ConeDev &K, const double *Rm, const double *Dm, doubl
                    nullptr);
         return;
     }
-    launch_auv(ctx, AUV_DUAL, L.dev, Rm + K.off, Dm + K.off, K.ld, 2.0, 1.0, out1, out2, K.carry1.p, K.carry2.p, obj1, obj2);
+    if (K.vc_on) {
+        if (K.vc_nnz_res > 0)
+            launch_auv(ctx, AUV_DUAL, K.vc_listRes.dev, Rm + K.off, Dm + K.off, K.ld, 2.0, 1.0, out1, out2, K.carry1.p, K.carry2.p,
+                       nullptr, nullptr);
+        launch_vc_auv(ctx, AUV_DUAL, K.vc, K.ld, true, Rm + K.off, Dm + K.off, 2.0, 1.0, out1, out2, nullptr, obj1, obj2);
+    } else
+        launch_auv(ctx, AUV_DUAL, L.dev, Rm + K.off, Dm + K.off, K.ld, 2.0, 1.0, out1, out2, K.carry1.p, K.carry2.p, obj1, obj2);
     if (K.c_rank1 != 0.0 && obj1 && obj2) {
         launch_colsum(ctx, K.n, K.ld, Rm + K.off, K.csA.p, K.cs_scratch.p);
         launch_colsum(ctx, K.n, K.ld, Dm + K.off, K.csB.p, K.cs_scratch.p);
@@ -465,9 +506,18 @@ void Solver::cone_auv_dual(ConeDev &K, const double *Rm, const double *Dm, doubl
     if (world > 1 && !(out1 == q1.p && out2 == q2.p)) { allreduce(out1, L.dev.n_rows); allreduce(out2, L.dev.n_rows); }
 }
 
-void Solver::cone_wsum(ConeDev &K, const double *w, bool w_compact, bool addC) {
+void Solver::cone_wsum(ConeDev &K, const double *w, bool w_compact, bool addC, bool materialize) {
     const int *map = K.identity_act ? nullptr : K.act_idx.p;
     K.S_has_C = addC;
+    if (K.vc_on && !materialize) {
+        // nothing is written for C and the singleton constraints: cone_mul reads w directly.  Only the weighted sum
+        // of the multi-entry constraints is materialised on the pattern.
+        K.pw = w; K.pw_compact = w_compact;
+        if (K.vc_nnz_res > 0)
+            launch_wsum(ctx, K.S.p, K.np, K.C_onP.p, K.vc_Tr_ptr.p, K.vc_Tr_con.p, K.vc_Tr_val.p, w, map, w_compact, false);
+        return;
+    }
+    K.pw = nullptr;
     if (K.dense_path)
         launch_dense_wsum(ctx, K.S.p, K.np, K.C_onP.p, K.D_pos.p, K.n_pos, K.T_ptr.p, K.T_con.p, K.T_val.p, w, map,
                           w_compact, addC);
@@ -483,6 +533,12 @@ void Solver::cone_mul(ConeDev &K, const double *X, double a, double bcoef, const
     else {
         const bool r1 = K.c_rank1 != 0.0 && K.S_has_C;      // (S + c ee^T) X = S X + c e (e^T X)
         if (r1) launch_colsum(ctx, K.n, K.ld, X + K.off, K.csA.p, K.cs_scratch.p);
+        if (K.vc_on && K.pw) {
+            const int *map = (K.pw_compact || K.identity_act) ? nullptr : K.act_idx.p;
+            launch_vc_spmm(ctx, K.vc, K.ld, K.S_has_C, K.pw, map, K.vc_nnz_res > 0 ? K.S.p : nullptr, X + K.off, a, bcoef,
+                           Z ? Z + K.off : nullptr, Z2 ? Z2 + K.off : nullptr, Y + K.off, red, r1 ? K.csA.p : nullptr, K.c_rank1);
+            return;
+        }
         launch_spmm(ctx, K.n, K.ld, K.adj_ptr.p, K.adj_col.p, K.adj_pos.p, K.S.p, X + K.off, a, bcoef,
                     Z ? Z + K.off : nullptr, Z2 ? Z2 + K.off : nullptr, Y + K.off, red, r1 ? K.csA.p : nullptr, K.c_rank1);
     }
@@ -622,8 +678,15 @@ void Solver::q12p12() {
             // third output of the same gather pass: A(RR^T) of the CURRENT point, i.e. the exact constrValSum and the
             // primal infeasibility that updateDimacsALM recomputes every iteration (lorads_alg_common.c:250-258)
             ConeDev &K = cones[0];
-            launch_auv(ctx, AUV_TRI, K.listAC.dev, R.p + K.off, U.p + K.off, K.ld, 2.0, 1.0, q1.p, q2.p, K.carry1.p, K.carry2.p,
-                       S.p + SL_P1, S.p + SL_P2, q3.p, K.carry3.p);
+            if (K.vc_on) {
+                if (K.vc_nnz_res > 0)
+                    launch_auv(ctx, AUV_TRI, K.vc_listRes.dev, R.p + K.off, U.p + K.off, K.ld, 2.0, 1.0, q1.p, q2.p, K.carry1.p,
+                               K.carry2.p, nullptr, nullptr, q3.p, K.carry3.p);
+                launch_vc_auv(ctx, AUV_TRI, K.vc, K.ld, true, R.p + K.off, U.p + K.off, 2.0, 1.0, q1.p, q2.p, q3.p, S.p + SL_P1,
+                              S.p + SL_P2);
+            } else
+                launch_auv(ctx, AUV_TRI, K.listAC.dev, R.p + K.off, U.p + K.off, K.ld, 2.0, 1.0, q1.p, q2.p, K.carry1.p, K.carry2.p,
+                           S.p + SL_P1, S.p + SL_P2, q3.p, K.carry3.p);
             if (K.c_rank1 != 0.0) {
                 launch_colsum(ctx, K.n, K.ld, R.p + K.off, K.csA.p, K.cs_scratch.p);
                 launch_colsum(ctx, K.n, K.ld, U.p + K.off, K.csB.p, K.cs_scratch.p);

@@ -58,6 +58,16 @@ struct ConeDev {
     DBuf<int> T_ptr, T_con, adj_ptr, adj_col, adj_pos;
     DBuf<long long> D_pos;
     DBuf<double> Z1, Z2;                            // dense path: packed sym(UV^T)
+    // vertex-centric fast path (layout.hpp VcLayout)
+    bool vc_on = false;
+    long long vc_nnz_res = 0;                       // non-zeros of the residual (multi-entry) constraints
+    VcDev vc;
+    DBuf<int> vc_order, vc_order_l, vc_u_ptr, vc_u_mid, vc_u_col, vc_u_tag, vc_d_con, vc_l_ptr, vc_l_row, vc_l_con, vc_Tr_ptr,
+        vc_Tr_con;
+    DBuf<double> vc_u_val, vc_d_coef, vc_l_coef, vc_Tr_val;
+    ItemListBufs vc_listRes;
+    const double *pw = nullptr;                     // weights of the pending (C + A^*(w)) product (set by cone_wsum)
+    bool pw_compact = false;
     DBuf<double> cv;                                // constrVal of the cone (compact, n_act + 1)
     DBuf<double> t1, t2;                            // compact AUV outputs (n_act + 1)
     long long cg_iter_last = 0;
@@ -190,7 +200,8 @@ struct Solver {
                   double *obj = nullptr);
     void cone_auv_dual(ConeDev &K, const double *Rm, const double *Dm, double *out1, double *out2, double *obj1 = nullptr,
                        double *obj2 = nullptr);
-    void cone_wsum(ConeDev &K, const double *w, bool w_compact, bool addC);
+    // materialize: write S = C + A^*(w) on the pattern even for vertex-centric cones (dual infeasibility SpMV)
+    void cone_wsum(ConeDev &K, const double *w, bool w_compact, bool addC, bool materialize = false);
     void cone_mul(ConeDev &K, const double *X, double a, double bcoef, const double *Z, const double *Z2, double *Y, double *red);
     // constrVal[c] = A(sym(U V^T)) for all cones, then constrValSum (LORADSInitConstrValAll + InitConstrValSum)
     void init_constr_val_all(const double *Um, const double *Vm, bool same);

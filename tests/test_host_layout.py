@@ -25,6 +25,73 @@ def item_values(lay, which, U, V):
     return out
 
 
+def vc_values(lay, U, V):
+    """A(sym(U V^T)) (compact rows) and <C, sym(U V^T)> evaluated from the vertex-centric layout exactly as
+    vc_auv_kernel does: objective = sum_j U_j . (C V)_j over the objective part of the adjacency, diagonal singleton
+    constraints from d_con/d_coef, the other singletons from the lower-triangular list, multi-entry constraints from
+    the residual item list."""
+    n = lay["n"]
+    out = np.zeros(lay["n_act"])
+    rows = np.repeat(np.arange(n), np.diff(lay["vc_u_ptr"]))
+    static = lay["vc_u_tag"] == -1
+    T = np.zeros_like(V)
+    np.add.at(T, rows[static], lay["vc_u_val"][static][:, None] * V[lay["vc_u_col"][static]])
+    obj = float(np.einsum("ij,ij->", U, T))
+    d = lay["vc_d_con"]
+    if d.size:
+        has = d >= 0
+        out[d[has]] = lay["vc_d_coef"][has] * np.einsum("ij,ij->i", U[has], V[has])
+    if lay["vc_l_row"].size:
+        j = np.repeat(np.arange(n), np.diff(lay["vc_l_ptr"]))
+        i = lay["vc_l_row"].astype(np.int64)
+        z = 0.5 * (np.einsum("ij,ij->i", U[i], V[j]) + np.einsum("ij,ij->i", U[j], V[i]))
+        assert np.all(out[lay["vc_l_con"]] == 0.0)
+        out[lay["vc_l_con"]] = lay["vc_l_coef"] * z
+    if lay["vc_nnz_res"]:
+        i, j = lay["vc_res_irow"].astype(np.int64), lay["vc_res_icol"].astype(np.int64)
+        z = 0.5 * (np.einsum("ij,ij->i", U[i], V[j]) + np.einsum("ij,ij->i", U[j], V[i]))
+        r = np.repeat(np.arange(lay["n_act"]), np.diff(lay["vc_res_ptr"]))
+        np.add.at(out, r, lay["vc_res_coef"] * z)
+    return out, obj
+
+
+def vc_product(lay, wc, X, use_c=True):
+    """(C + A^*(w)) X from the vertex-centric adjacency as vc_spmm_kernel evaluates it (wc = compact weights)."""
+    n, npat = lay["n"], lay["psize"]
+    tag, val, col = lay["vc_u_tag"], lay["vc_u_val"], lay["vc_u_col"]
+    Sres = np.zeros(npat)
+    if lay["vc_nnz_res"]:
+        pos = np.repeat(np.arange(npat), np.diff(lay["vc_Tr_ptr"]))
+        np.add.at(Sres, pos, wc[lay["vc_Tr_con"]] * lay["vc_Tr_val"])
+    s = np.where(tag == -1, val if use_c else 0.0, 0.0)
+    dyn = tag >= 0
+    s[dyn] = wc[tag[dyn]] * val[dyn]
+    res = tag <= -2
+    s[res] = Sres[-2 - tag[res]]
+    rows = np.repeat(np.arange(n), np.diff(lay["vc_u_ptr"]))
+    # weight-dependent entries come first in every row
+    assert np.all(lay["vc_u_mid"] >= lay["vc_u_ptr"][:-1]) and np.all(lay["vc_u_mid"] <= lay["vc_u_ptr"][1:])
+    first_static = np.repeat(lay["vc_u_mid"], np.diff(lay["vc_u_ptr"]))
+    assert np.array_equal(tag == -1, np.arange(tag.size) >= first_static)
+    Y = np.zeros_like(X)
+    np.add.at(Y, rows, s[:, None] * X[col])
+    return Y
+
+
+def check_vc(lay, U, V, w_full, ref_auv_full, ref_obj, ref_wsum, m):
+    compact, obj = vc_values(lay, U, V)
+    full = np.zeros(m)
+    full[lay["act_idx"]] = compact
+    assert rel_err(full, ref_auv_full) < TOL
+    obj += lay["c_rank1"] * float(U.sum(axis=0) @ V.sum(axis=0))
+    assert abs(obj - ref_obj) <= TOL * max(1.0, abs(ref_obj))
+    Y = vc_product(lay, w_full[lay["act_idx"]], V) + lay["c_rank1"] * V.sum(axis=0)[None, :]
+    assert rel_err(Y, ref_wsum) < TOL
+    # both row orders are permutations
+    for k in ("vc_order", "vc_order_l"):
+        assert np.array_equal(np.sort(lay[k]), np.arange(lay["n"]))
+
+
 def test_layout_reproduces_reference_operators(golden):
     name, g, inst = golden
     w = g["w"]
@@ -56,6 +123,8 @@ def test_layout_reproduces_reference_operators(golden):
         np.add.at(Y, rows, S[lay["adj_pos"]][:, None] * V[lay["adj_col"]])
         Y += lay["c_rank1"] * V.sum(axis=0)[None, :]
         assert rel_err(Y, g[f"wsum_C{c}"]) < TOL
+        # the same three operators from the vertex-centric class split
+        check_vc(lay, U, V, w, g[f"auv_UV{c}"], float(g[f"obj_UV{c}"]), g[f"wsum_C{c}"], inst.m)
         # the adjacency lists every off-diagonal pattern entry twice and every diagonal entry once, rows sorted
         assert lay["adj_col"].size == 2 * npat - int((lay["P_row"] == lay["P_col"]).sum())
         for i in range(0, lay["n"], max(1, lay["n"] // 50)):
@@ -139,3 +208,4 @@ def test_layout_edge_shapes_against_the_restatement(case):
     np.add.at(Y, rows, S[lay["adj_pos"]][:, None] * V[lay["adj_col"]])
     Y += lay["c_rank1"] * V.sum(axis=0)[None, :]
     assert rel_err(Y, O.wsum_mulrk(w, True, "V")) < TOL
+    check_vc(lay, U, V, w, O.auv("U", "V"), ref_obj, O.wsum_mulrk(w, True, "V"), inst.m)
