@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblorads_b200.so")
 CLI = os.path.join(HERE, "lorads_b200_cli")
-SOURCES = ["kernels.cu", "vc_kernels.cu", "solver.cu", "alg.cu", "capi.cu", "sdpa_reader.cpp"]
+SOURCES = ["kernels.cu", "vc_kernels.cu", "xfer_kernels.cu", "solver.cu", "alg.cu", "capi.cu", "sdpa_reader.cpp"]
 HEADERS = ["common.cuh", "kernels.cuh", "layout.hpp", "solver.hpp", "main_cli.cpp", os.path.join("..", "..", "include", "lorads_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

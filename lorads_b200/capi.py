@@ -106,7 +106,7 @@ def load_library():
     lib.lb2_alm_inner_iter.argtypes = [C.c_void_p, C.c_double, C.c_int64, _dp, _ip]
     lib.lb2_time_alm_inner_iters.argtypes = [C.c_void_p, C.c_double, C.c_int64, _dp, _dp]
     lib.lb2_alm_run_host.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_int64, _dp, _dp]
-    lib.lb2_bench_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp]
+    lib.lb2_bench_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, _dp]
     lib.lb2_alm_optimize.argtypes = [C.c_void_p, C.POINTER(Params), C.c_double]
     lib.lb2_alm_to_admm.argtypes = [C.c_void_p, C.POINTER(Params)]
     lib.lb2_admm_optimize.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int64, C.c_double]
@@ -433,9 +433,15 @@ class Solver:
         self._ck(self.lib.lb2_alm_run_host(self.h, _d(R_in), _d(lam_in), rho, iters, _d(R_out), _d(out)))
         return int(out[5]), out
 
-    def bench_kernel(self, which: int, reps: int) -> float:
+    def dual_infeasibility(self) -> float:
+        """DIMACS dual infeasibility sum_cones |min(lambda_min(C - A^*(lambda)), 0)| / (1 + |C|_1) at the current
+        multipliers (calculate_dual_infeasibility_solver, lorads_solver.c:1007-1037)."""
+        self._ck(self.lib.lb2_dual_infeasibility(self.h))
+        return self.dinfo(11)
+
+    def bench_kernel(self, which: int, reps: int, flush_l2: bool = False) -> float:
         ms = C.c_double(0.0)
-        self._ck(self.lib.lb2_bench_kernel(self.h, which, reps, C.byref(ms)))
+        self._ck(self.lib.lb2_bench_kernel(self.h, which, reps, int(flush_l2), C.byref(ms)))
         return ms.value
 
     # ---- phases

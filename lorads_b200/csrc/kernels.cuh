@@ -234,6 +234,10 @@ void launch_lp_dinf(Ctx &c, const LpDev &L, const double *w, double *S, int slot
 // columns of src (n x ld_old); rows i < n_diag of column (c_diag + i) get diag_val when diag_val != 0
 // (lpRandomDiag, lorads_solver.c:776-786).
 void launch_relayout(Ctx &c, long long n, int r_old, int ld_old, int ld_new, const double *src, double *dst);
+// C-ABI boundary (xfer_kernels.cu): r_own contiguous columns of length n (the caller's column-major layout) <-> the
+// row-major n x ld device layout; padding columns are zero-filled on the way in.
+void launch_cm_to_rm(Ctx &c, long long n, int r_own, int ld, const double *src, double *dst);
+void launch_rm_to_cm(Ctx &c, long long n, int r_own, int ld, const double *src, double *dst);
 // ------------------------------------------------------------------------------------------------
 // One-shot all-reduce over NVLink peer memory (column-sharded runs).  Every rank owns an exchange buffer of
 // 2 sets x world slots x cap doubles and 2 x world arrival flags, mapped into every peer through CUDA IPC.

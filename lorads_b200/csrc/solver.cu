@@ -405,29 +405,42 @@ double *Solver::vec_ptr(char which) {
     throw std::invalid_argument("unknown vector name");
 }
 
+// The caller's column-major buffer goes to the device as it is (one copy when this rank holds every column, one
+// per owned column under column sharding) and is transposed there; the copy is asynchronous when the buffer is
+// pinned.  The staging buffer is reused across calls.
 void Solver::upload_factor(double *dst, const ConeDev &K, const double *colMajor) {
-    std::vector<double> rm((size_t)(K.n * K.ld), 0.0);
     const long long c = &K - cones.data();
     const std::vector<int> &cols = my_cols[c];
-    for (int k = 0; k < K.r; ++k) {
-        const double *src = colMajor + (size_t)cols[k] * K.n;
-        for (long long i = 0; i < K.n; ++i) rm[(size_t)i * K.ld + k] = src[i];
+    const size_t need = (size_t)K.n * (size_t)std::max(K.r, 1);
+    if (xfer_stage.n < need) { retire(xfer_stage); xfer_stage.alloc(need, false); }
+    if (K.r == rank[c]) {
+        LB2_CUDA(cudaMemcpyAsync(xfer_stage.p, colMajor, sizeof(double) * need, cudaMemcpyHostToDevice, ctx.stream));
+    } else {
+        for (int k = 0; k < K.r; ++k)
+            LB2_CUDA(cudaMemcpyAsync(xfer_stage.p + (size_t)k * K.n, colMajor + (size_t)cols[k] * K.n, sizeof(double) * K.n,
+                                     cudaMemcpyHostToDevice, ctx.stream));
     }
-    LB2_CUDA(cudaMemcpyAsync(dst + K.off, rm.data(), sizeof(double) * rm.size(), cudaMemcpyHostToDevice, ctx.stream));
+    launch_cm_to_rm(ctx, K.n, K.r, K.ld, xfer_stage.p, dst + K.off);
     LB2_CUDA(cudaStreamSynchronize(ctx.stream));
 }
 
 void Solver::download_factor(const double *src, const ConeDev &K, double *colMajor) const {
-    std::vector<double> rm((size_t)(K.n * K.ld));
-    LB2_CUDA(cudaMemcpyAsync(rm.data(), src + K.off, sizeof(double) * rm.size(), cudaMemcpyDeviceToHost, ctx.stream));
-    LB2_CUDA(cudaStreamSynchronize(ctx.stream));
+    Solver &self = const_cast<Solver &>(*this);
     const long long c = &K - cones.data();
     const std::vector<int> &cols = my_cols[c];
-    std::memset(colMajor, 0, sizeof(double) * (size_t)(K.n * rank[c]));
-    for (int k = 0; k < K.r; ++k) {
-        double *dstc = colMajor + (size_t)cols[k] * K.n;
-        for (long long i = 0; i < K.n; ++i) dstc[i] = rm[(size_t)i * K.ld + k];
+    const size_t need = (size_t)K.n * (size_t)std::max(K.r, 1);
+    if (self.xfer_stage.n < need) { self.retire(self.xfer_stage); self.xfer_stage.alloc(need, false); }
+    launch_rm_to_cm(self.ctx, K.n, K.r, K.ld, src + K.off, self.xfer_stage.p);
+    if (K.r == rank[c]) {
+        LB2_CUDA(cudaMemcpyAsync(colMajor, xfer_stage.p, sizeof(double) * need, cudaMemcpyDeviceToHost, ctx.stream));
+    } else {
+        // sharded: the columns held elsewhere read as zero (the caller sums or gathers over ranks)
+        std::memset(colMajor, 0, sizeof(double) * (size_t)(K.n * rank[c]));
+        for (int k = 0; k < K.r; ++k)
+            LB2_CUDA(cudaMemcpyAsync(colMajor + (size_t)cols[k] * K.n, xfer_stage.p + (size_t)k * K.n, sizeof(double) * K.n,
+                                     cudaMemcpyDeviceToHost, ctx.stream));
     }
+    LB2_CUDA(cudaStreamSynchronize(ctx.stream));
 }
 
 void Solver::set_factor(char which, long long c, const double *colMajor) { upload_factor(factor_ptr(which), cones.at(c), colMajor); }

@@ -138,6 +138,8 @@ struct Solver {
     DBuf<double> S;
     double *S_host = nullptr;          // pinned mirror
     DBuf<double> red_partials, dense_part;
+    DBuf<double> flush_buf;            // lb2_bench_kernel: L2 eviction buffer
+    DBuf<double> xfer_stage;           // column-major staging of upload_factor / download_factor (device)
     DBuf<unsigned int> red_counter;
     double *push_host = nullptr;       // pinned staging for {tau, rho}
     // replayable CUDA graphs of the steady-state inner iteration, keyed by (L-BFGS ring head, history depth)

@@ -1,0 +1,72 @@
+// xfer_kernels.cu -- layout conversion at the C-ABI boundary, on the device.
+//
+// The reference keeps factor matrices column-major n x r (lorads_sdp_dense.matElem[row + k*nRows],
+// def_lorads_elements.h:29-33; strides at lorads_alg_common.c:40-46); the kernels here work on row-major n x ld rows
+// (ld = r rounded up to 4, zero padded).  The caller's buffer is copied to / from the device as it is and transposed
+// by these two kernels through a 32 x 32 shared-memory tile, so both sides of the copy are coalesced and the host
+// never touches the data.
+#include "kernels.cuh"
+
+namespace lb2 {
+
+namespace {
+constexpr int kT = 32;
+
+// src: r_own columns of length n, contiguous (column-major); dst: n x ld row-major, columns >= r_own zeroed
+__global__ void __launch_bounds__(kT * 8) cm_to_rm_kernel(long long n, int r_own, int ld, const double *__restrict__ src,
+                                                           double *__restrict__ dst) {
+    __shared__ double tile[kT][kT + 1];
+    const long long i0 = (long long)blockIdx.x * kT;
+    const int k0 = blockIdx.y * kT;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads
+    for (int kk = ty; kk < kT; kk += 8) {
+        const int k = k0 + kk;
+        const long long i = i0 + tx;
+        tile[kk][tx] = (k < r_own && i < n) ? src[(size_t)k * n + i] : 0.0;
+    }
+    __syncthreads();
+    for (int ii = ty; ii < kT; ii += 8) {
+        const long long i = i0 + ii;
+        const int k = k0 + tx;
+        if (i < n && k < ld) dst[(size_t)i * ld + k] = tile[tx][ii];
+    }
+}
+
+// src: n x ld row-major; dst: r_own columns of length n, contiguous
+__global__ void __launch_bounds__(kT * 8) rm_to_cm_kernel(long long n, int r_own, int ld, const double *__restrict__ src,
+                                                           double *__restrict__ dst) {
+    __shared__ double tile[kT][kT + 1];
+    const long long i0 = (long long)blockIdx.x * kT;
+    const int k0 = blockIdx.y * kT;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int ii = ty; ii < kT; ii += 8) {
+        const long long i = i0 + ii;
+        const int k = k0 + tx;
+        tile[ii][tx] = (i < n && k < ld) ? src[(size_t)i * ld + k] : 0.0;
+    }
+    __syncthreads();
+    for (int kk = ty; kk < kT; kk += 8) {
+        const int k = k0 + kk;
+        const long long i = i0 + tx;
+        if (k < r_own && i < n) dst[(size_t)k * n + i] = tile[tx][kk];
+    }
+}
+}  // namespace
+
+void launch_cm_to_rm(Ctx &c, long long n, int r_own, int ld, const double *src, double *dst) {
+    if (n == 0) return;
+    dim3 grid((unsigned)((n + kT - 1) / kT), (unsigned)((ld + kT - 1) / kT));
+    cm_to_rm_kernel<<<grid, kT * 8, 0, c.stream>>>(n, r_own, ld, src, dst);
+    c.launches++;
+    LB2_CUDA(cudaGetLastError());
+}
+
+void launch_rm_to_cm(Ctx &c, long long n, int r_own, int ld, const double *src, double *dst) {
+    if (n == 0 || r_own == 0) return;
+    dim3 grid((unsigned)((n + kT - 1) / kT), (unsigned)((r_own + kT - 1) / kT));
+    rm_to_cm_kernel<<<grid, kT * 8, 0, c.stream>>>(n, r_own, ld, src, dst);
+    c.launches++;
+    LB2_CUDA(cudaGetLastError());
+}
+
+}  // namespace lb2
