@@ -10,10 +10,12 @@ reference's random start (srand(925)).
   python bench.py --gpus N --steps K --warmup W                 our CUDA path (N > 1: launched under torchrun)
   python bench.py --impl reference --gpus N --steps K --warmup W  the reference's own CPU code on the host cores
 
-`value`   : iterations/s with everything resident in HBM (CUDA events on the solver's stream, max over ranks)
+`value`   : iterations/s with everything resident in HBM (CUDA events on the solver's stream, max over ranks); the
+            K-step region is repeated (`repeats`) and the median region is reported
 `e2e`     : the same metric through the host-buffer C-ABI call lb2_alm_run_host (R and lambda copied host->device,
-            K iterations, R copied back; wall clock)
-`roofline`: the dominant kernel's algorithmic bytes / its CUDA-event launch time vs MEASURED_PEAKS.json
+            K iterations, R copied back; wall clock, median of the repeats)
+`roofline`: the A(UV^T) gather pass of the step (north_star kernel): algorithmic bytes / CUDA-event time of a launch that
+            starts from a flushed L2, vs MEASURED_PEAKS.json; the adjoint SpMM and the other kernels beside it
 `cpu_baseline`: the compiled reference (oracle/_ref) timed on this box's host cores on a bounded sample
 """
 from __future__ import annotations
@@ -125,13 +127,15 @@ def measured_peak_gbs():
 
 def ncu_traffic(kernel_label: str):
     """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     try:
         table = json.load(open(p))["dram_bytes_per_launch"]
     except Exception:
         return None
-    key = {"auv_items_kernel<TRI>": "auv_items_kernel<4,", "auv_items_kernel<DUAL>": "auv_items_kernel<2,", "auv_items_kernel<SAME>": "auv_items_kernel<0,",
-           "spmm_sym_kernel": "spmm_sym_kernel", "axpby_dot2_kernel": "axpby_dot2_kernel", "wsum_kernel": "wsum_kernel"}
+    key = {"vc_auv_kernel<TRI>": "vc_auv_kernel<4,", "vc_auv_kernel<DUAL>": "vc_auv_kernel<2,", "vc_auv_kernel<SAME>": "vc_auv_kernel<0,",
+           "vc_spmm_kernel": "vc_spmm_kernel", "axpby_dot2_kernel": "axpby_dot2_kernel",
+           "auv_items_kernel<TRI>": "auv_items_kernel<4,", "auv_items_kernel<DUAL>": "auv_items_kernel<2,",
+           "auv_items_kernel<SAME>": "auv_items_kernel<0,", "spmm_sym_kernel": "spmm_sym_kernel", "wsum_kernel": "wsum_kernel"}
     for prefix, ncu_prefix in key.items():
         if kernel_label.startswith(prefix):
             for name, v in table.items():
@@ -141,12 +145,28 @@ def ncu_traffic(kernel_label: str):
 
 
 def kernel_bytes(S) -> dict:
-    """Algorithmic (compulsory) bytes per launch of each hot kernel; formulas in DESIGN.md section 4."""
+    """Algorithmic (compulsory) bytes per launch of each hot kernel: every array the kernel has to read or write,
+    counted once (factors 8*n*ld each, index/value arrays of the layout, m-vectors); formulas in DESIGN.md section 4."""
     n, ld, m = S.dim(0), S.info(17), S.m
     itAC, itA, nact = S.info(15), S.info(16), S.info(8)
     npat, nadj, nnzA = S.info(4), S.info(14), S.info(12)
     N = S.info(18)
-    tri = S.info(20) == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1
+    tri = S.info(20) == 1
+    nout = 3 if tri else 2
+    if S.info(21) == 1:
+        # vertex-centric layout: adjacency entry = neighbour (4) + value (8) [+ constraint tag (4) where the kernel reads it],
+        # per row two pointers + the row order (12), diagonal-singleton pair (12), lower-triangular singleton entry (16)
+        nu, ndyn, nl = S.info(22), S.info(23), S.info(24)
+        nsta = nu - ndyn
+        auv_idx = 12 * nsta + 12 * n + 12 * n + 16 * nl
+        return {
+            0: (f"vc_auv_kernel<{'TRI' if tri else 'DUAL'}> A(sym(RD^T)),A(DD^T){',A(RR^T)' if tri else ''}+obj",
+                2 * 8 * n * ld + auv_idx + nout * 8 * (nact + 1)),
+            1: ("vc_auv_kernel<SAME> A(RR^T)", 8 * n * ld + 12 * n + 12 * n + 16 * nl + 8 * nact),
+            2: ("wsum_kernel (multi-entry constraints only)", 0),
+            3: ("vc_spmm_kernel G=2(C+A^*(w))R", 16 * nu + 12 * n + 8 * nact + 2 * 8 * n * ld),
+            4: ("axpby_dot2_kernel (L-BFGS pass)", 4 * 8 * N),
+        }
     dual = (("auv_items_kernel<TRI> A(sym(RD^T)),A(DD^T),A(RR^T)+obj", 2 * 8 * n * ld + 16 * itAC + 4 * (nact + 2) + 3 * 8 * (nact + 1))
             if tri else
             ("auv_items_kernel<DUAL> A(sym(RD^T)),A(DD^T)+obj", 2 * 8 * n * ld + 16 * itAC + 4 * (nact + 2) + 2 * 8 * (nact + 1)))
@@ -157,6 +177,13 @@ def kernel_bytes(S) -> dict:
         3: ("spmm_sym_kernel G=2SR", nadj * 8 + npat * 8 + 4 * (n + 1) + 2 * 8 * n * ld),
         4: ("axpby_dot2_kernel (L-BFGS pass)", 4 * 8 * N),
     }
+
+
+def workload_config(rank_r, world, mode):
+    """The `config` object of the JSON line: identical for our arm and the reference arm."""
+    return {"workload": f"MaxCut SDP n=m={WORKLOAD['n']} edges={WORKLOAD['edges']} seed={WORKLOAD['seed']} rank={rank_r} ({WORKLOAD['label']}); one step = one ALM inner iteration, lorads_alm.c:1073-1146",
+            "l2": "step timing: no explicit flush, one step streams ~12 factor-sized vectors (19 MB each) plus 30 MB of index data (> 126 MB L2 in total); per-kernel roofline timing: L2 flushed (384 MB overwritten) before every launch",
+            "parallelism": "single GPU" if world == 1 else mode}
 
 
 class c_stdout_to_stderr:
@@ -200,8 +227,9 @@ def run_reference(args):
     if rank != 0:
         return 0
     inst = make_instance()
-    steps = max(1, min(args.steps, 30))
-    warm = min(args.warmup, 2)
+    # bounded sample: at most 60 timed and 10 warm-up iterations of the reference (0.33 s each on one core)
+    steps = max(1, min(args.steps, 60))
+    warm = max(0, min(args.warmup, 10))
     t0 = time.time()
     out = cpu_reference_rate(inst, warm + steps)
     if out is None:
@@ -212,7 +240,7 @@ def run_reference(args):
         "impl": "reference", "metric": "alm_inner_iterations_per_second", "value": rate, "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 / rate, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"MaxCut SDP n=m={WORKLOAD['n']} edges={WORKLOAD['edges']} seed={WORKLOAD['seed']} rank={r} ({WORKLOAD['label']}); one step = one ALM inner iteration, lorads_alm.c:1073-1146"},
+        "config": workload_config(r, 1, ""),
         "cpu_baseline": {"value": rate, "unit": "iterations/s", "cores": 1, "kind": "reference",
                          "sample": f"{warm + steps} inner iterations of the untouched reference (oracle/_ref, -DMAC_INT64, OpenBLAS 1 thread) from the srand(925) start, {sec:.1f} s; host has {os.cpu_count()} cores, the reference is single-threaded"},
         "e2e": {"value": rate, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -232,11 +260,15 @@ def run_ours(args):
     torch.cuda.set_device(local)
     from lorads_b200.capi import Solver, load_library
     import ctypes as C
-    comm = None
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def new_comm():
+        """A fresh library communicator (NCCL id created on rank 0, broadcast through torch.distributed)."""
+        if world == 1:
+            return None
         lib = load_library()
         uid = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
@@ -246,15 +278,21 @@ def run_ours(args):
             uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
         uid = uid.cuda()
         dist.broadcast(uid, 0)
-        uid_bytes = bytes(uid.cpu().numpy().tobytes())
-        comm = (C.create_string_buffer(uid_bytes, 128), rank, world)
+        return (C.create_string_buffer(bytes(uid.cpu().numpy().tobytes()), 128), rank, world)
 
+    comm = new_comm()
     inst = make_instance()
     t_setup = time.time()
     S = Solver(inst, device=local, comm=comm)
     t_setup = time.time() - t_setup
     rho = S.dinfo(6)
     n, r, m = S.dim(0), S.rank(0), S.m
+    shard_desc = ""
+    if world > 1:
+        shard_desc = (f"row slabs of the factors over {world} GPUs (cone blocks / rows with their pattern entries): NCCL all-reduce of the "
+                      "m-vectors per A() evaluation, scalar all-reduce per dot table, all-gather of the new direction"
+                      if S.info(28) == 1 else
+                      f"factor columns sharded over {world} GPUs, NCCL all-reduce per A() evaluation and per dot")
 
     def barrier():
         if dist is not None:
@@ -262,22 +300,34 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing ----------------
+    # The K-step region is short (K = 20 is 5 ms): it is repeated and the MEDIAN region is reported.  Every repeat
+    # restarts from the same point (ALG_START of the random start advanced by the warm-up), so all regions do the same work.
     sampler = ClockSampler(local)
     sampler.start()        # started before the warm-up so that samples are flowing when the timed region begins
     S.alm_prepare(rho)
     S.time_alm_inner_iters(rho, max(3, args.warmup))
-    S.alm_prepare(rho)     # same start for every arm: ALG_START state of the random point advanced by the warm-up
-    barrier()
-    sampler.mark()
-    l0 = S.launches
-    sec, done = S.time_alm_inner_iters(rho, args.steps)
-    launches = S.launches - l0
-    barrier()
-    clocks = sampler.stop()
+    est = S.time_alm_inner_iters(rho, min(args.steps, 20))[0] / min(args.steps, 20)
+    repeats = args.repeats if args.repeats > 0 else int(max(1, min(25, np.ceil(0.5 / max(est * args.steps, 1e-6)))))
     if dist is not None:
-        t = torch.tensor([sec], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec = float(t.item())
+        t = torch.tensor([repeats], dtype=torch.int64, device="cuda")
+        dist.broadcast(t, 0)
+        repeats = int(t.item())
+    regions, launches, done = [], 0, args.steps
+    sampler.mark()
+    for _ in range(repeats):
+        S.alm_prepare(rho)     # same start for every region
+        barrier()
+        l0 = S.launches
+        sec, done = S.time_alm_inner_iters(rho, args.steps)
+        launches = S.launches - l0
+        barrier()
+        if dist is not None:
+            t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        regions.append(sec)
+    clocks = sampler.stop()
+    sec = float(np.median(regions))
     if done != args.steps:
         log(f"warning: only {done} of {args.steps} iterations ran (line search reported no root)")
     value = done / sec
@@ -289,53 +339,110 @@ def run_ours(args):
     # sharded runs: every rank holds host buffers of the full factor and moves only the columns it owns
     Rh[:] = np.ascontiguousarray(S.get_factor("R").T).ravel()
     S.alm_run_host(Rh, lam, rho, 3, Ro)        # warm
-    barrier()
-    t0 = time.perf_counter()
-    done_e, _ = S.alm_run_host(Rh, lam, rho, args.steps, Ro)
-    torch.cuda.synchronize()
-    e2e_sec = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_sec = float(t.item())
+    e2e_regions = []
+    for _ in range(repeats):
+        barrier()
+        t0 = time.perf_counter()
+        done_e, _ = S.alm_run_host(Rh, lam, rho, args.steps, Ro)
+        torch.cuda.synchronize()
+        e2e_sec = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_sec = float(t.item())
+        e2e_regions.append(e2e_sec)
+    e2e_sec = float(np.median(e2e_regions))
     e2e = {"value": done_e / e2e_sec, "unit": "iterations/s",
            "h2d_bytes_per_step": (Rh.nbytes + world * lam.nbytes) / max(done_e, 1), "d2h_bytes_per_step": Ro.nbytes / max(done_e, 1),
-           "note": "one lb2_alm_run_host call per rank: R (the columns the rank owns), lambda host->device, K iterations, R device->host; copies amortised over the K steps of the call; bytes summed over ranks"}
+           "note": "one lb2_alm_run_host call per rank: R and lambda host->device (pinned, transposed on the device), K iterations, R device->host; copies amortised over the K steps of the call; bytes summed over ranks; median of the repeats"}
 
-    # ---------------- roofline of the hot kernels (cone 0, CUDA events, back-to-back launches) ----------------
-    # every rank takes part: with column sharding the A(UV^T) launches are followed by their all-reduce
+    # ---------------- roofline of the hot kernels (cone 0, CUDA events) ----------------
+    # every rank takes part: with sharding the A(UV^T) launches are followed by their all-reduce.
+    # cold: the L2 is flushed (a 384 MB buffer overwritten) before EVERY launch and each launch is timed on its own --
+    #       the figure the roofline uses (the 38 MB of factors would otherwise be served from the 126 MB L2);
+    # hot : 200 back-to-back launches (L2 resident), for reference.
     peak, peak_src = measured_peak_gbs()
     kb = kernel_bytes(S)
-    kt = {}
+    kt, kt_hot = {}, {}
     for which in kb:
-        kt[which] = S.bench_kernel(which, 200)
+        if kb[which][1] == 0:
+            kt[which] = kt_hot[which] = 0.0
+            continue
+        kt_hot[which] = S.bench_kernel(which, 200)
+        kt[which] = S.bench_kernel(which, 40, True)
+    barrier()
+
+    # ---------------- BASELINE.json configs[4] (MaxCut n = 1e6) at the same N: iterations/s + gather kernels, informational
+    cfg5 = None
+    if not args.no_cfg5 and WORKLOAD is WORKLOADS["cfg2"]:
+        try:
+            from lorads_b200 import sdpa as _sdpa
+            w5 = WORKLOADS["cfg5"]
+            t5 = time.time()
+            inst5 = _sdpa.maxcut(w5["n"], w5["edges"], w5["seed"])
+            S5 = Solver(inst5, device=local, comm=new_comm())
+            setup5 = time.time() - t5
+            rho5 = S5.dinfo(6)
+            S5.alm_prepare(rho5)
+            S5.time_alm_inner_iters(rho5, 5)
+            S5.alm_prepare(rho5)
+            barrier()
+            sec5, done5 = S5.time_alm_inner_iters(rho5, 40)
+            barrier()
+            if dist is not None:
+                t = torch.tensor([sec5], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sec5 = float(t.item())
+            kb5 = kernel_bytes(S5)
+            k5 = {}
+            for wk in (0, 3):
+                cold5 = S5.bench_kernel(wk, 10, True)
+                k5[kb5[wk][0]] = {"ms_cold": cold5, "alg_bytes": kb5[wk][1], "gbs": kb5[wk][1] / (cold5 * 1e-3) / 1e9,
+                                  "frac_of_peak": kb5[wk][1] / (cold5 * 1e-3) / 1e9 / peak}
+            cfg5 = {"workload": f"MaxCut SDP n=m={w5['n']} edges={w5['edges']} seed={w5['seed']} rank={S5.rank(0)} ({w5['label']})",
+                    "alm_inner_iterations_per_second": done5 / sec5, "ms_per_step": 1e3 * sec5 / max(done5, 1), "steps": done5,
+                    "n_gpus": world, "setup_seconds_incl_generation": setup5, "kernels_this_rank": k5}
+            S5.close()
+            del inst5
+        except Exception as e:
+            log("cfg5 secondary failed:", e)
     barrier()
     if rank != 0:
         S.close()
         if dist is not None:
             dist.destroy_process_group()
         return 0
-    # per-iteration share: 1 dual pass, 1 A-only pass, 1 wsum, 1 spmm, ~6 BLAS-1 passes
-    # (with the three-output gather pass the separate A(RR^T) launch is no longer part of the pipelined step)
+    # per-iteration multiplicity: 1 fused A(UV^T) pass, 1 adjoint SpMM, ~6 BLAS-1 passes
+    # (with the three-output gather pass the separate A(RR^T) launch is not part of the pipelined step)
     mult = {0: 1, 1: 0 if S.info(20) == 1 else 1, 2: 1, 3: 1, 4: 6}
-    share = {w: kt[w] * mult[w] for w in kt}
-    dom = max(share, key=share.get)
-    kernels = {kb[w][0]: {"ms": kt[w], "alg_bytes": kb[w][1], "gbs": kb[w][1] / (kt[w] * 1e-3) / 1e9,
-                          "ncu_dram_bytes": ncu_traffic(kb[w][0]) if WORKLOAD is WORKLOADS["cfg2"] else None,
-                          "frac_of_peak": kb[w][1] / (kt[w] * 1e-3) / 1e9 / peak,
-                          "share_of_step": share[w] / (1e3 * sec / done)} for w in kb}
+    ms_step = 1e3 * sec / done
+    kernels = {}
+    for w in kb:
+        if kb[w][1] == 0:
+            continue
+        gbs = kb[w][1] / (kt[w] * 1e-3) / 1e9
+        kernels[kb[w][0]] = {"ms_cold": kt[w], "ms_hot": kt_hot[w], "alg_bytes": kb[w][1], "gbs": gbs,
+                             "gbs_hot": kb[w][1] / (kt_hot[w] * 1e-3) / 1e9,
+                             "ncu_dram_bytes": ncu_traffic(kb[w][0]) if WORKLOAD is WORKLOADS["cfg2"] else None,
+                             "frac_of_peak": gbs / peak, "frac_of_peak_hot": kb[w][1] / (kt_hot[w] * 1e-3) / 1e9 / peak,
+                             "share_of_step_hot": kt_hot[w] * mult[w] / ms_step}
+    dom = 0                      # the north_star kernel: the fused A(UV^T) gather pass; the adjoint SpMM sits beside it
     achieved = kb[dom][1] / (kt[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": kb[dom][0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(kb[dom][0]) if WORKLOAD is WORKLOADS["cfg2"] else None,
-                "traffic_source": "profiles/r01_ncu_traffic.json (ncu --set full, cold-cache replay, per launch)",
-                "peak_source": peak_src, "alg_bytes_per_launch": kb[dom][1],
-                "launch_ms": kt[dom], "kernels": kernels}
+                "traffic_source": "profiles/r02_ncu_traffic.json (ncu --set full, cold-cache replay, per launch)",
+                "peak_source": peak_src, "alg_bytes_per_launch": kb[dom][1], "launch_ms": kt[dom],
+                "timing": "CUDA events around single launches, L2 flushed (384 MB overwritten) before every launch, mean of 40",
+                "adjoint": {"kernel": kb[3][0], "achieved": kb[3][1] / (kt[3] * 1e-3) / 1e9,
+                            "frac": kb[3][1] / (kt[3] * 1e-3) / 1e9 / peak, "alg_bytes_per_launch": kb[3][1], "launch_ms": kt[3],
+                            "traffic": ncu_traffic(kb[3][0]) if WORKLOAD is WORKLOADS["cfg2"] else None},
+                "kernels": kernels}
 
     # ---------------- the other BASELINE.json metrics on the same workload (N=1, informational) ----------------
-    secondary = None
+    secondary = {"cfg5": cfg5} if cfg5 is not None else None
     if world == 1:
         try:
-            secondary = {}
+            secondary = secondary or {}
             # CG iterations/s of the ADMM block solve (LORADSUpdateSDPVarOne): tolerance 0 forces exactly 60 iterations
             S.admm_init_constr()
             S.update_sdp_var_one("U", "V", rho, 0.0, 5)
@@ -358,6 +465,8 @@ def run_ours(args):
         except Exception as e:
             log("secondary metrics failed:", e)
 
+    # ---------------- BASELINE.json configs[4] (MaxCut n = 1e6) at the same N: iterations/s, informational ----------------
+    # (all ranks take part; placed after rank 0 gathered everything it needs from the cfg2 solver)
     # ---------------- CPU baseline (bounded sample) ----------------
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -375,12 +484,10 @@ def run_ours(args):
     line = {
         "secondary": secondary,
         "metric": "alm_inner_iterations_per_second", "value": value, "unit": "iterations/s", "n_gpus": world,
-        "steps": done, "warmup": max(3, args.warmup), "ms_per_step": 1e3 * sec / done, "higher_is_better": True,
+        "steps": done, "warmup": max(3, args.warmup), "repeats": repeats, "ms_per_step": 1e3 * sec / done, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"MaxCut SDP n=m={WORKLOAD['n']} edges={WORKLOAD['edges']} seed={WORKLOAD['seed']} rank={r} ({WORKLOAD['label']}); one step = one ALM inner iteration, lorads_alm.c:1073-1146",
-                   "l2": "no explicit flush: the step streams ~12 factor-sized vectors (19 MB each) plus 30 MB of index data (> 126 MB L2 in total)",
-                   "parallelism": "single GPU" if world == 1 else f"factor columns sharded over {world} GPUs, NCCL all-reduce per A() evaluation and per dot",
-                   "setup_seconds": t_setup},
+        "config": workload_config(r, world, shard_desc), "setup_seconds": t_setup,
+        "region_seconds": {"median": sec, "min": float(min(regions)), "max": float(max(regions))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -396,8 +503,10 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--repeats", type=int, default=0, help="repeats of the timed K-step region (0: enough for ~0.5 s, at most 25)")
     ap.add_argument("--cpu-iters", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the MaxCut n=1e6 secondary measurement")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     global WORKLOAD

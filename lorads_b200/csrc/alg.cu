@@ -83,7 +83,7 @@ bool Solver::aug_rank(double aug) {
         rank[c] = nr;
         my_cols[c].clear();
         for (long long k = 0; k < nr; ++k)
-            if ((int)(k % world) == myrank) my_cols[c].push_back((int)k);
+            if (!shard_cols() || (int)(k % world) == myrank) my_cols[c].push_back((int)k);
     }
     alloc_vars();
     struct Pair { DBuf<double> *src, *dst; bool diag; };
@@ -134,6 +134,7 @@ void Solver::obj_scale_dualvar(double f) {
         launch_scale(ctx, K.C_onP.p, (long long)K.C_onP.n, f);
         const long long nobj = K.listAC.dev.n_items - K.obj_item_begin;
         if (nobj > 0) launch_scale(ctx, K.listAC.coef.p + K.obj_item_begin, nobj, f);
+        if (K.vc_on) launch_scale_tagged(ctx, (long long)K.vc_u_val.n, K.vc_u_tag.p, K.vc_u_val.p, f);
         K.c_rank1 *= f;
     }
     if (nLp > 0) launch_scale(ctx, lp_c.p, nLp, f);      // lp_cone_scalObj, lorads_lp_conic.c:197-202

@@ -34,6 +34,8 @@ typedef int (*fn_get_uid)(nccl_uid *);
 typedef int (*fn_init_rank)(void **, int, nccl_uid, int);
 typedef int (*fn_allreduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
 typedef int (*fn_allgather)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef int (*fn_bcast)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_group)(void);
 typedef int (*fn_destroy)(void *);
 typedef const char *(*fn_errstr)(int);
 struct NcclApi {
@@ -42,6 +44,8 @@ struct NcclApi {
     fn_init_rank init_rank = nullptr;
     fn_allreduce allreduce = nullptr;
     fn_allgather allgather = nullptr;
+    fn_bcast bcast = nullptr;
+    fn_group group_start = nullptr, group_end = nullptr;
     fn_destroy destroy = nullptr;
     fn_errstr errstr = nullptr;
     bool load() {
@@ -53,6 +57,9 @@ struct NcclApi {
         init_rank = (fn_init_rank)dlsym(h, "ncclCommInitRank");
         allreduce = (fn_allreduce)dlsym(h, "ncclAllReduce");
         allgather = (fn_allgather)dlsym(h, "ncclAllGather");
+        bcast = (fn_bcast)dlsym(h, "ncclBroadcast");
+        group_start = (fn_group)dlsym(h, "ncclGroupStart");
+        group_end = (fn_group)dlsym(h, "ncclGroupEnd");
         destroy = (fn_destroy)dlsym(h, "ncclCommDestroy");
         errstr = (fn_errstr)dlsym(h, "ncclGetErrorString");
         return get_uid && init_rank && allreduce;
@@ -69,6 +76,20 @@ void Solver::allreduce(double *p, long long count) {
     // ncclDouble = 8, ncclSum = 0
     int rc = g_nccl.allreduce(p, p, (size_t)count, 8, 0, nccl, ctx.stream);
     if (rc != 0) throw CudaError(std::string("ncclAllReduce failed: ") + (g_nccl.errstr ? g_nccl.errstr(rc) : "?"));
+}
+
+// Row sharding: every rank broadcasts the part of its owned slab that lies in [lo, hi) of a concatenated vector, in
+// place, as one NCCL group (the slabs have different lengths, so this is an all-gather with per-rank counts).
+void Solver::bcast_ranges(double *X, long long lo, long long hi) {
+    if (world <= 1) return;
+    if (!g_nccl.bcast || !g_nccl.group_start || !g_nccl.group_end) throw CudaError("NCCL broadcast entry points missing");
+    int rc = g_nccl.group_start();
+    for (int k = 0; k < world && rc == 0; ++k) {
+        const long long a = std::max(own_off[(size_t)k], lo), b = std::min(own_off[(size_t)k] + own_cnt[(size_t)k], hi);
+        if (b > a) rc = g_nccl.bcast(X + a, X + a, (size_t)(b - a), 8 /* ncclDouble */, k, nccl, ctx.stream);
+    }
+    const int rc2 = g_nccl.group_end();
+    if (rc != 0 || rc2 != 0) throw CudaError(std::string("ncclBroadcast failed: ") + (g_nccl.errstr ? g_nccl.errstr(rc ? rc : rc2) : "?"));
 }
 
 // Exchange buffers for the peer-memory all-reduce: allocate, publish through CUDA IPC (handles travel by
@@ -128,6 +149,16 @@ static void setup_p2p(Solver &S) {
     LB2_CUDA(cudaStreamSynchronize(S.ctx.stream));
     LB2_CUDA(cudaMemcpy(&sum, S.S.p + SL_T1, sizeof(double), cudaMemcpyDeviceToHost));
     S.p2p_on = (sum == (double)S.world);
+}
+
+// Shared guard of the hot-path entry points: the solver must be initialised (lb2_init_vars) and the calling thread is
+// switched to the solver's device, so that one thread can drive solvers on several GPUs and calls made out of order
+// fail with LB2_ERR_STATE instead of launching kernels on null buffers.
+static void ready(const lb2_solver *s, bool need_vars = true) {
+    const Solver &S = s->impl;
+    if (!S.preprocessed) throw std::logic_error("call lb2_preprocess first");
+    if (need_vars && !S.vars_ready) throw std::logic_error("call lb2_init_vars first");
+    LB2_CUDA(cudaSetDevice(S.device));
 }
 
 extern "C" {
@@ -208,7 +239,8 @@ int lb2_set_lp_vec(lb2_solver *s, char which, const double *in) {
 int lb2_comm_init(lb2_solver *s, const void *id128, int rank, int world) {
     if (!s || world < 1 || rank < 0 || rank >= world) { g_err = "lb2_comm_init: bad argument"; return LB2_ERR_ARG; }
     if (world == 1) return LB2_OK;
-    if (s->impl.nLp > 0) { g_err = "column sharding with an LP block is not supported"; return LB2_ERR_UNSUPPORTED; }
+    if (s->impl.nLp > 0) { g_err = "sharding a problem with an LP block is not supported"; return LB2_ERR_UNSUPPORTED; }
+    if (!s->impl.preprocessed || s->impl.vars_ready) { g_err = "lb2_comm_init: call after lb2_preprocess and before lb2_init_vars"; return LB2_ERR_STATE; }
     if (!g_nccl.load()) { g_err = "NCCL library not found"; return LB2_ERR_UNSUPPORTED; }
     LB2_TRY
     LB2_CUDA(cudaSetDevice(s->impl.device));
@@ -220,6 +252,10 @@ int lb2_comm_init(lb2_solver *s, const void *id128, int rank, int world) {
     // sharded runs use the Gram-table L-BFGS: one all-reduce of 8 scalars per iteration instead of five
     // sequential scalar all-reduces (LORADS_B200_EXACT_LBFGS=1 keeps the two-loop recursion)
     if (getenv("LORADS_B200_EXACT_LBFGS") == nullptr) s->impl.vf_lbfgs = true;
+    // rows (north_star: cone blocks / row slabs) unless LORADS_B200_SHARD=cols asks for the column scheme
+    const char *mode = getenv("LORADS_B200_SHARD");
+    s->impl.shard_mode = (mode && std::string(mode) == "cols") ? 0 : 1;
+    if (s->impl.shard_mode == 1) s->impl.setup_row_partition();
     setup_p2p(s->impl);
     LB2_CATCH
 }
@@ -336,6 +372,16 @@ lb2_int lb2_info(const lb2_solver *s, int what, lb2_int c) {
     case 18: return S.N;
     case 19: return S.nLp;
     case 20: return S.tri_ok() ? 1 : 0;
+    // vertex-centric fast path: on, adjacency entries, of which weight-dependent, lower-triangular singleton entries,
+    // non-zeros of the residual constraints, rows owned by this rank, first owned row
+    case 21: return K.vc_on ? 1 : 0;
+    case 22: return (long long)K.vc_u_col.n;
+    case 23: return (long long)K.vc_u_col.n - K.nnzC_adj;
+    case 24: return (long long)K.vc_l_row.n;
+    case 25: return K.vc_nnz_res;
+    case 26: return K.row_hi - K.row_lo;
+    case 27: return K.row_lo;
+    case 28: return S.shard_rows() ? 1 : 0;
     }
     return -1;
 }
@@ -362,15 +408,15 @@ int lb2_get_pattern(const lb2_solver *s, lb2_int c, lb2_int *rows, lb2_int *cols
 
 int lb2_set_factor(lb2_solver *s, char which, lb2_int c, const double *cm) {
     if (!s || !cm) return LB2_ERR_ARG;
-    LB2_TRY if (!s->impl.vars_ready) throw std::logic_error("variables not initialised"); s->impl.set_factor(which, c, cm); LB2_CATCH
+    LB2_TRY ready(s, true); if (!s->impl.vars_ready) throw std::logic_error("variables not initialised"); s->impl.set_factor(which, c, cm); LB2_CATCH
 }
 int lb2_get_factor(const lb2_solver *s, char which, lb2_int c, double *cm) {
     if (!s || !cm) return LB2_ERR_ARG;
-    LB2_TRY if (!s->impl.vars_ready) throw std::logic_error("variables not initialised"); s->impl.get_factor(which, c, cm); LB2_CATCH
+    LB2_TRY ready(s, true); if (!s->impl.vars_ready) throw std::logic_error("variables not initialised"); s->impl.get_factor(which, c, cm); LB2_CATCH
 }
 int lb2_set_vec(lb2_solver *s, char which, const double *v) {
     if (!s || !v) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, false);
     Solver &S = s->impl;
     LB2_CUDA(cudaMemcpyAsync(S.vec_ptr(which), v, sizeof(double) * S.m, cudaMemcpyHostToDevice, S.ctx.stream));
     S.sync();
@@ -378,7 +424,7 @@ int lb2_set_vec(lb2_solver *s, char which, const double *v) {
 }
 int lb2_get_vec(const lb2_solver *s, char which, double *v) {
     if (!s || !v) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, false);
     Solver &S = const_cast<Solver &>(s->impl);
     LB2_CUDA(cudaMemcpyAsync(v, S.vec_ptr(which), sizeof(double) * S.m, cudaMemcpyDeviceToHost, S.ctx.stream));
     S.sync();
@@ -387,7 +433,7 @@ int lb2_get_vec(const lb2_solver *s, char which, double *v) {
 
 int lb2_auv(lb2_solver *s, lb2_int c, char u, char v, double *constrVal, double *obj) {
     if (!s || !constrVal) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, true);
     Solver &S = s->impl;
     ConeDev &K = S.cones.at(c);
     const bool same = (u == v);
@@ -403,7 +449,7 @@ int lb2_auv(lb2_solver *s, lb2_int c, char u, char v, double *constrVal, double 
 
 int lb2_wsum_mulrk(lb2_solver *s, lb2_int c, const double *w, int addC, char x, double *out) {
     if (!s || !w || !out) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, true);
     Solver &S = s->impl;
     ConeDev &K = S.cones.at(c);
     LB2_CUDA(cudaMemcpyAsync(S.M1.p, w, sizeof(double) * S.m, cudaMemcpyHostToDevice, S.ctx.stream));
@@ -415,23 +461,24 @@ int lb2_wsum_mulrk(lb2_solver *s, lb2_int c, const double *w, int addC, char x, 
 
 int lb2_alm_cal_grad(lb2_solver *s, double rho, double *lag) {
     if (!s || !lag) return LB2_ERR_ARG;
-    LB2_TRY *lag = s->impl.cal_grad(rho); LB2_CATCH
+    LB2_TRY ready(s, true); *lag = s->impl.cal_grad(rho); LB2_CATCH
 }
 
 int lb2_cg_matvec(lb2_solver *s, lb2_int c, char noUpdate, const double *x, double *res) {
     if (!s || !x || !res) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, true);
     Solver &S = s->impl;
     ConeDev &K = S.cones.at(c);
     S.upload_factor(S.cg_p.p, K, x);
     S.cg_matvec(K, S.cg_p.p, S.factor_ptr(noUpdate), S.cg_Q.p, nullptr, nullptr);
+    S.allgather_cone(K, S.cg_Q.p);       // row sharding: every rank computed its rows of the product
     S.download_factor(S.cg_Q.p, K, res);
     LB2_CATCH
 }
 
 int lb2_admm_init_constr(lb2_solver *s) {
     if (!s) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, true);
     Solver &S = s->impl;
     if (!S.vars_ready) throw std::logic_error("call lb2_init_vars first");
     S.init_constr_val_all(S.U.p, S.V.p, false);
@@ -441,7 +488,7 @@ int lb2_admm_init_constr(lb2_solver *s) {
 }
 int lb2_admm_update_var(lb2_solver *s, double rho, double cgTol, lb2_int cgMaxIter) {
     if (!s) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, true);
     Solver &S = s->impl;
     if (!S.vars_ready) throw std::logic_error("call lb2_init_vars first");
     S.update_sdp_var(rho, cgTol, cgMaxIter);
@@ -450,7 +497,7 @@ int lb2_admm_update_var(lb2_solver *s, double rho, double cgTol, lb2_int cgMaxIt
 }
 int lb2_update_sdp_var_one(lb2_solver *s, lb2_int c, char upd, char noupd, double rho, double tol, lb2_int maxit, lb2_int *iters) {
     if (!s) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, true);
     Solver &S = s->impl;
     S.cones.at(c);
     S.update_sdp_var_one(c, S.factor_ptr(upd), S.factor_ptr(noupd), rho, tol, maxit);
@@ -461,7 +508,7 @@ int lb2_update_sdp_var_one(lb2_solver *s, lb2_int c, char upd, char noupd, doubl
 
 int lb2_alm_prepare(lb2_solver *s, double rho, double *lag) {
     if (!s) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, true);
     Solver &S = s->impl;
     S.init_constr_val_all(S.R.p, S.R.p, true);
     S.constr_val_sum();
@@ -472,7 +519,7 @@ int lb2_alm_prepare(lb2_solver *s, double rho, double *lag) {
 
 int lb2_alm_inner_iter(lb2_solver *s, double rho, lb2_int counter, double *out, lb2_int *rootNum) {
     if (!s || !out) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, true);
     Solver &S = s->impl;
     double tau = 0.0, p12[2], lag = 0, pinf = 0;
     long long rn = 0;
@@ -488,7 +535,7 @@ int lb2_alm_inner_iter(lb2_solver *s, double rho, lb2_int counter, double *out, 
 
 int lb2_time_alm_inner_iters(lb2_solver *s, double rho, lb2_int iters, double *out, double *seconds) {
     if (!s || !out || !seconds) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, true);
     Solver &S = s->impl;
     cudaEvent_t e0, e1;
     LB2_CUDA(cudaEventCreate(&e0)); LB2_CUDA(cudaEventCreate(&e1));
@@ -506,7 +553,7 @@ int lb2_time_alm_inner_iters(lb2_solver *s, double rho, lb2_int iters, double *o
 int lb2_alm_run_host(lb2_solver *s, const double *R_in, const double *lambda_in, double rho, lb2_int iters,
                      double *R_out, double *out) {
     if (!s || !R_in || !lambda_in || !R_out || !out) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, true);
     Solver &S = s->impl;
     size_t off = 0;
     for (long long c = 0; c < S.nCones; ++c) {
@@ -528,7 +575,7 @@ int lb2_alm_run_host(lb2_solver *s, const double *R_in, const double *lambda_in,
 
 int lb2_bench_kernel(lb2_solver *s, int which, lb2_int reps, int flush_l2, double *ms) {
     if (!s || !ms || reps < 1) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, true);
     Solver &S = s->impl;
     ConeDev &K = S.cones.at(0);
     cudaEvent_t e0, e1;
@@ -584,19 +631,21 @@ int lb2_bench_kernel(lb2_solver *s, int which, lb2_int reps, int flush_l2, doubl
 
 int lb2_alm_optimize(lb2_solver *s, lb2_params *p, double timeSolveStart) {
     if (!s || !p) return LB2_ERR_ARG;
-    LB2_TRY s->impl.alm_optimize(p, 0.0, timeSolveStart, false, false, 0.0); LB2_CATCH
+    LB2_TRY ready(s, true); s->impl.alm_optimize(p, 0.0, timeSolveStart, false, false, 0.0); LB2_CATCH
 }
-int lb2_alm_to_admm(lb2_solver *s, lb2_params *p) { if (!s || !p) return LB2_ERR_ARG; LB2_TRY s->impl.alm_to_admm(p); LB2_CATCH }
+int lb2_alm_to_admm(lb2_solver *s, lb2_params *p) { if (!s || !p) return LB2_ERR_ARG; LB2_TRY ready(s, true); s->impl.alm_to_admm(p); LB2_CATCH }
 int lb2_admm_optimize(lb2_solver *s, lb2_params *p, lb2_int iterCelling, double timeSolveStart) {
     if (!s || !p) return LB2_ERR_ARG;
     try {
+        ready(s, true);
         return s->impl.admm_optimize(p, iterCelling, timeSolveStart, false);
+    } catch (const std::logic_error &e) { g_err = e.what(); return LB2_ERR_STATE;
     } catch (const std::exception &e) { g_err = e.what(); return LB2_ERR_CUDA; }
 }
-int lb2_dual_infeasibility(lb2_solver *s) { if (!s) return LB2_ERR_ARG; LB2_TRY s->impl.dual_infeasibility(); LB2_CATCH }
+int lb2_dual_infeasibility(lb2_solver *s) { if (!s) return LB2_ERR_ARG; LB2_TRY ready(s, true); s->impl.dual_infeasibility(); LB2_CATCH }
 int lb2_solve(lb2_solver *s, lb2_params *p, lb2_result *res) {
     if (!s || !p) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, true);
     if (!s->impl.vars_ready) throw std::logic_error("call lb2_init_vars before lb2_solve");
     s->impl.solve(p, res);
     LB2_CATCH
@@ -604,16 +653,16 @@ int lb2_solve(lb2_solver *s, lb2_params *p, lb2_result *res) {
 int lb2_reopt(lb2_solver *s, lb2_params *p, double *reoptParam, lb2_int *almIter, lb2_int *admmIter, double timeSolveStart,
               int *badFlag, int level, double *seconds) {
     if (!s || !p || !reoptParam || !almIter || !admmIter || !badFlag) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, true);
     long long a = *almIter, b = *admmIter;
     double t = s->impl.reopt(p, reoptParam, &a, &b, timeSolveStart, badFlag, level);
     if (seconds) *seconds = t;
     LB2_CATCH
 }
-int lb2_average_uv(lb2_solver *s) { if (!s) return LB2_ERR_ARG; LB2_TRY s->impl.average_uv(); s->impl.sync(); LB2_CATCH }
+int lb2_average_uv(lb2_solver *s) { if (!s) return LB2_ERR_ARG; LB2_TRY ready(s, true); s->impl.average_uv(); s->impl.sync(); LB2_CATCH }
 int lb2_copy_r_to_v(lb2_solver *s) {
     if (!s) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, true);
     Solver &S = s->impl;
     LB2_CUDA(cudaMemcpyAsync(S.V.p, S.R.p, sizeof(double) * S.Nt, cudaMemcpyDeviceToDevice, S.ctx.stream));
     S.sync();
@@ -654,7 +703,7 @@ int lb2_set_state(lb2_solver *s, const double *a, const double *d) {
 
 int lb2_get_solution(const lb2_solver *s, lb2_int c, double *R, double *dualVar) {
     if (!s) return LB2_ERR_ARG;
-    LB2_TRY
+    LB2_TRY ready(s, true);
     if (R) s->impl.get_factor('R', c, R);
     if (dualVar) {
         Solver &S = const_cast<Solver &>(s->impl);

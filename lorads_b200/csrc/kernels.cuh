@@ -238,6 +238,10 @@ void launch_relayout(Ctx &c, long long n, int r_old, int ld_old, int ld_new, con
 // row-major n x ld device layout; padding columns are zero-filled on the way in.
 void launch_cm_to_rm(Ctx &c, long long n, int r_own, int ld, const double *src, double *dst);
 void launch_rm_to_cm(Ctx &c, long long n, int r_own, int ld, const double *src, double *dst);
+// val[e] *= f for the objective entries (tag == -1) of a vertex-centric adjacency
+void launch_scale_tagged(Ctx &c, long long n, const int *tag, double *val, double f);
+// R += (*tau_p) * D with the same fma as launch_alm_step (rows not owned under row sharding)
+void launch_axpy_slot(Ctx &c, long long n, const double *tau_p, const double *D, double *R);
 // ------------------------------------------------------------------------------------------------
 // One-shot all-reduce over NVLink peer memory (column-sharded runs).  Every rank owns an exchange buffer of
 // 2 sets x world slots x cap doubles and 2 x world arrival flags, mapped into every peer through CUDA IPC.

@@ -197,6 +197,14 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
     PhaseTimer pt;
     L.n = n; L.m = m;
     const double packedSize = (double)(n * (n + 1) / 2);
+    // raw arrays from the C ABI (lb2_layout_build, lb2_host_presolve, lb2_set_cone_data): refuse what would send the
+    // column walk below out of range
+    if (!beg_in || beg_in[0] != 0) throw std::invalid_argument("cone data: column pointers must start at 0");
+    for (int64_t c = 0; c <= m; ++c)
+        if (beg_in[c + 1] < beg_in[c]) throw std::invalid_argument("cone data: column pointers must not decrease");
+    if (beg_in[m + 1] > 0 && (!idx || !elem)) throw std::invalid_argument("cone data: null index / value array");
+    for (int64_t k = 0; k < beg_in[m + 1]; ++k)
+        if (idx[k] < 0 || idx[k] >= n * (n + 1) / 2) throw std::invalid_argument("cone data: packed index outside [0, n(n+1)/2)");
     if (beg_in[m + 1] > (int64_t)2000000000) throw std::runtime_error("cone has more than 2^31 non-zeros");
 
     // --- per-column sorted copies (dataMatCreateSparseImpl sorts when needed, lorads_sdp_data.c:106-108)

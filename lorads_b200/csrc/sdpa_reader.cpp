@@ -40,9 +40,11 @@ inline void skip_line(const char *&p, const char *end) {
     while (p < end && *p != '\n') ++p;
     if (p < end) ++p;
 }
+// Both number parsers stop at the end of the current line: strtoll / strtod would skip the newline as white space and
+// silently take a token of the next entry (or of the next thread's chunk), where the reference's per-line sscanf fails.
 inline bool parse_int(const char *&p, const char *end, long long &v) {
     skip_ws(p, end);
-    if (p >= end) return false;
+    if (p >= end || *p == '\n') return false;
     char *q = nullptr;
     errno = 0;
     v = std::strtoll(p, &q, 10);
@@ -52,7 +54,7 @@ inline bool parse_int(const char *&p, const char *end, long long &v) {
 }
 inline bool parse_double(const char *&p, const char *end, double &v) {
     skip_ws(p, end);
-    if (p >= end) return false;
+    if (p >= end || *p == '\n') return false;
     char *q = nullptr;
     v = std::strtod(p, &q);
     if (q == p) return false;
@@ -149,9 +151,9 @@ int lb2_read_sdpa(const char *path, lb2_sdpa **out) {
     *out = nullptr;
     FILE *f = std::fopen(path, "rb");
     if (!f) { g_reader_err = std::string("cannot open ") + path; return LB2_ERR_ARG; }
-    std::fseek(f, 0, SEEK_END);
+    if (std::fseek(f, 0, SEEK_END) != 0) { std::fclose(f); g_reader_err = "cannot seek in the instance file"; return LB2_ERR_ARG; }
     const long sz = std::ftell(f);
-    std::fseek(f, 0, SEEK_SET);
+    if (sz < 0 || std::fseek(f, 0, SEEK_SET) != 0) { std::fclose(f); g_reader_err = "cannot determine the size of the instance file"; return LB2_ERR_ARG; }
     std::vector<char> buf((size_t)sz + 1);
     if (sz > 0 && std::fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { std::fclose(f); g_reader_err = "short read"; return LB2_ERR_ARG; }
     std::fclose(f);
@@ -240,6 +242,7 @@ int lb2_read_sdpa(const char *path, lb2_sdpa **out) {
                 if (con == 0) val = -val;
                 blk -= 1; i -= 1; j -= 1;
                 if (nlp > 0 && blk == nsdp) {
+                    if (i < 0 || i >= nlp) { P.err = "LP column index out of range"; return; }
                     P.lp.push_back({(lb2_int)con, (lb2_int)i, val});
                 } else {
                     const long long n = bdims[(size_t)blk];

@@ -86,6 +86,19 @@ void Solver::create(long long nRows, long long nC, const lb2_int *dims, const do
 
 void Solver::set_cone(long long i, const lb2_int *beg, const lb2_int *idx, const double *elem) {
     if (i < 0 || i >= nCones) throw std::invalid_argument("cone index out of range");
+    // the arrays come straight from the caller (reader format, lorads_file_io.c:325-340): column pointers over
+    // columns 0..m ascending from 0, packed lower-triangular positions inside [0, n(n+1)/2)
+    if (!beg) throw std::invalid_argument("cone data: null column pointer array");
+    if (beg[0] != 0) throw std::invalid_argument("cone data: column pointers must start at 0");
+    for (long long c = 0; c <= m; ++c)
+        if (beg[c + 1] < beg[c]) throw std::invalid_argument("cone data: column pointers must not decrease");
+    if (beg[m + 1] > 0 && (!idx || !elem)) throw std::invalid_argument("cone data: null index / value array with non-zeros present");
+    {
+        const long long nn = blkDims[i];
+        const long long packed = nn * (nn + 1) / 2;
+        for (long long k = 0; k < beg[m + 1]; ++k)
+            if (idx[k] < 0 || idx[k] >= packed) throw std::invalid_argument("cone data: packed index outside [0, n(n+1)/2)");
+    }
     ConeInput &in = inputs[i];
     in.beg.assign(beg, beg + m + 2);
     in.idx.assign(idx, idx + beg[m + 1]);
@@ -216,7 +229,13 @@ void Solver::preprocess() {
             if (K.vc_on) {
                 const VcLayout &V = L.vc;
                 K.vc_nnz_res = V.nnz_res;
+                K.nnzC_adj = 0;
+                for (int32_t t : V.u_tag) K.nnzC_adj += (t == -1);
                 K.vc_order.upload(V.order); K.vc_order_l.upload(V.order_l);
+                K.vc_order_h = V.order; K.vc_order_l_h = V.order_l;
+                K.row_weight_h.resize((size_t)K.n);
+                for (long long i = 0; i < K.n; ++i)
+                    K.row_weight_h[(size_t)i] = 8 + (V.u_ptr[i + 1] - V.u_ptr[i]) + 2 * (V.l_ptr[i + 1] - V.l_ptr[i]);
                 K.vc.n = K.n; K.vc.obj_row = (int)K.n_act;
                 K.vc.order = K.vc_order.p; K.vc.order_l = K.vc_order_l.p;
                 K.vc_u_ptr.upload(V.u_ptr); K.vc_u_mid.upload(V.u_mid); K.vc_u_col.upload(V.u_col); K.vc_u_tag.upload(V.u_tag);
@@ -237,6 +256,7 @@ void Solver::preprocess() {
                 }
             }
         }
+        K.row_lo = 0; K.row_hi = K.n; K.lead = true;
         K.cv.alloc((size_t)K.n_act + 1); K.t1.alloc((size_t)K.n_act + 1); K.t2.alloc((size_t)K.n_act + 1);
         cObjNrm1 += K.cNrm1; n2 += K.cNrm2Sq; cObjNrmInf = std::max(cObjNrmInf, K.cNrmInf);
         inputs[c] = ConeInput();   // the reader arrays are no longer needed
@@ -286,7 +306,10 @@ void Solver::determine_rank(double timesRank) {
     for (long long c = 0; c < nCones; ++c) {
         lb2_int cap = 0;
         rank[c] = lb2_host_rank_rule(blkDims[c], cones[c].n_nonzero_coeff, nCones, timesRank, &cap);
-        rank_max[c] = cap;
+        // the gather kernels hold a factor row in at most 8 passes of 32 columns: the rank (and with it the growth of
+        // AUG_RANK) stops at that width; reaching it counts as "rank at its maximum"
+        rank_max[c] = std::min<long long>(cap, kMaxRank);
+        rank[c] = std::min<long long>(rank[c], rank_max[c]);
     }
 }
 
@@ -301,6 +324,7 @@ void Solver::alloc_vars() {
         N += K.n * K.ld;
     }
     Nt = N + nLp;
+    compute_owned_ranges();
     for (DBuf<double> *v : {&R, &U, &V, &G, &M2, &Bls, &cg_r, &cg_p, &cg_Q, &Dtemp}) { retire(*v); v->alloc((size_t)Nt); }
     {
         // split-K scratch of the dense symmetric product: up to 32 partial n x ldp blocks of the largest dense cone
@@ -326,13 +350,110 @@ static void assign_columns(std::vector<int> &cols, long long r, int world, int m
         if ((int)(k % world) == myrank) cols.push_back((int)k);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// row sharding: partition of the concatenated rows (by cone block, huge blocks by row slabs)
+// ---------------------------------------------------------------------------------------------------
+void Solver::setup_row_partition() {
+    // weight of a row = its share of the gather work; cones that cannot be split (dense scratch, generic item path)
+    // count as one lump and go to the rank their centre of mass falls into
+    std::vector<double> cone_w((size_t)nCones, 0.0);
+    double total = 0.0;
+    for (long long c = 0; c < nCones; ++c) {
+        const ConeDev &K = cones[c];
+        double w = 0.0;
+        if (K.vc_on) for (int32_t x : K.row_weight_h) w += x;
+        else w = (double)K.np * 4.0 + (double)K.n * 8.0;
+        cone_w[(size_t)c] = w; total += w;
+    }
+    part_rows.assign((size_t)world + 1, 0);
+    long long rows_total = 0;
+    for (long long c = 0; c < nCones; ++c) rows_total += cones[c].n;
+    part_rows[(size_t)world] = rows_total;
+    {
+        double acc = 0.0;
+        long long row0 = 0;
+        int next = 1;
+        for (long long c = 0; c < nCones && next < world; ++c) {
+            const ConeDev &K = cones[c];
+            if (K.vc_on) {
+                for (long long i = 0; i < K.n && next < world; ++i) {
+                    acc += K.row_weight_h[(size_t)i];
+                    while (next < world && acc >= total * next / world) part_rows[(size_t)next++] = row0 + i + 1;
+                }
+                if (next >= world) break;
+            } else {
+                const double mid = acc + 0.5 * cone_w[(size_t)c];
+                acc += cone_w[(size_t)c];
+                // every boundary that falls inside the lump moves to the nearer end of the cone
+                while (next < world && acc >= total * next / world)
+                    part_rows[(size_t)next] = (total * next / world <= mid) ? row0 : row0 + K.n, ++next;
+            }
+            row0 += K.n;
+        }
+        for (; next < world; ++next) part_rows[(size_t)next] = rows_total;
+        for (int k = 1; k <= world; ++k) part_rows[(size_t)k] = std::max(part_rows[(size_t)k], part_rows[(size_t)k - 1]);
+    }
+    // this rank's rows of every cone, its filtered row orders, the lead rank of every cone
+    long long row0 = 0;
+    for (long long c = 0; c < nCones; ++c) {
+        ConeDev &K = cones[c];
+        const long long lo = part_rows[(size_t)myrank], hi = part_rows[(size_t)myrank + 1];
+        K.row_lo = std::min(std::max(lo - row0, 0LL), K.n);
+        K.row_hi = std::min(std::max(hi - row0, 0LL), K.n);
+        int lead_rank = 0;
+        while (lead_rank + 1 < world && part_rows[(size_t)lead_rank + 1] <= row0) ++lead_rank;     // owner of the cone's row 0
+        K.lead = (lead_rank == myrank);
+        if (!K.vc_on && K.row_hi > K.row_lo && (K.row_lo != 0 || K.row_hi != K.n))
+            throw std::logic_error("row partition split a cone that cannot be split");
+        if (K.vc_on) {
+            std::vector<int32_t> o, ol;
+            for (int32_t i : K.vc_order_h) if (i >= K.row_lo && i < K.row_hi) o.push_back(i);
+            for (int32_t i : K.vc_order_l_h) if (i >= K.row_lo && i < K.row_hi) ol.push_back(i);
+            if (o.empty()) { o.push_back(0); ol.push_back(0); }      // keep the device arrays non-null
+            K.vc_order.upload(o); K.vc_order_l.upload(ol);
+            K.vc.order = K.vc_order.p; K.vc.order_l = K.vc_order_l.p;
+            K.vc.n = K.row_hi - K.row_lo;
+        }
+        row0 += K.n;
+    }
+}
+
+void Solver::compute_owned_ranges() {
+    vo = 0; vn = Nt;
+    own_off.assign((size_t)world, 0); own_cnt.assign((size_t)world, 0);
+    if (!shard_rows()) return;
+    if (part_rows.empty()) throw std::logic_error("row partition missing");
+    // element offset of a concatenated row index
+    auto elem_of = [&](long long row) {
+        long long row0 = 0;
+        for (long long c = 0; c < nCones; ++c) {
+            const ConeDev &K = cones[c];
+            if (row < row0 + K.n) return K.off + (row - row0) * (long long)K.ld;
+            row0 += K.n;
+        }
+        return N;
+    };
+    for (int k = 0; k < world; ++k) {
+        own_off[(size_t)k] = elem_of(part_rows[(size_t)k]);
+        own_cnt[(size_t)k] = elem_of(part_rows[(size_t)k + 1]) - own_off[(size_t)k];
+    }
+    vo = own_off[(size_t)myrank]; vn = own_cnt[(size_t)myrank];
+}
+
+void Solver::allgather_owned(double *X) { if (shard_rows()) bcast_ranges(X, 0, N); }
+
+void Solver::allgather_cone(const ConeDev &K, double *X) {
+    if (shard_rows()) bcast_ranges(X, K.off, K.off + K.n * (long long)K.ld);
+}
+
 void Solver::init_vars(long long lbfgsLen, double initRho) {
     if (rank.empty()) throw std::logic_error("determine the rank first");
     if (lbfgsLen < 1 || lbfgsLen > kMaxLbfgs) throw std::invalid_argument("lbfgsListLength must be in 1..16");
     LB2_CUDA(cudaSetDevice(device));
     lbfgs_len = (int)lbfgsLen;
     my_cols.resize(nCones);
-    for (long long c = 0; c < nCones; ++c) assign_columns(my_cols[c], rank[c], world, myrank);
+    // column sharding deals the factor columns round-robin; row sharding (and one GPU) keeps every column everywhere
+    for (long long c = 0; c < nCones; ++c) assign_columns(my_cols[c], rank[c], shard_cols() ? world : 1, shard_cols() ? myrank : 0);
     alloc_vars();
     // the reference's libc draw order: srand(925); R of every cone (lorads_solver.c:415-446), later U then V of
     // every cone (lorads_solver.c:631-658); each element is rand()/RAND_MAX - rand()/RAND_MAX (:361-370)
@@ -445,7 +566,11 @@ void Solver::download_factor(const double *src, const ConeDev &K, double *colMaj
 
 void Solver::set_factor(char which, long long c, const double *colMajor) { upload_factor(factor_ptr(which), cones.at(c), colMajor); }
 void Solver::get_factor(char which, long long c, double *colMajor) const {
-    download_factor(const_cast<Solver *>(this)->factor_ptr(which), cones.at(c), colMajor);
+    Solver &self = const_cast<Solver &>(*this);
+    // row sharding: R, U, V are replicated; the others hold only this rank's rows -- complete them first (collective:
+    // every rank has to ask for the same factor)
+    if (shard_rows() && which != 'R' && which != 'U' && which != 'V') self.allgather_cone(cones.at(c), self.factor_ptr(which));
+    download_factor(self.factor_ptr(which), cones.at(c), colMajor);
 }
 
 void Solver::sync() { LB2_CUDA(cudaStreamSynchronize(ctx.stream)); }
@@ -461,29 +586,37 @@ void Solver::read_slots() {
 void Solver::cone_auv(ConeDev &K, bool with_obj, const double *Um, const double *Vm, bool same, double scale, double *out,
                       double *obj) {
     ItemListBufs &L = with_obj ? K.listAC : K.listA;
+    const bool rows = shard_rows();
+    // row sharding: every rank adds its part into zeroed outputs, the all-reduce below completes them; the parts that
+    // cannot be split are evaluated by the cone's lead rank only
+    if (rows) LB2_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)L.dev.n_rows, ctx.stream));
     if (K.dense_path) {
         // <C,Z> is taken inside the tile kernel from this rank's share of Z (the slot is summed over ranks by the
         // caller); the constraint rows come from the A-only item list over the all-reduced Z
-        launch_dense_uvt(ctx, K.n, K.r, K.ld, Um + K.off, Vm + K.off, K.Z1.p, same, with_obj ? K.C_onP.p : nullptr, scale,
-                         with_obj ? obj : nullptr);
-        if (world > 1) allreduce(K.Z1.p, K.np);
-        launch_auv(ctx, AUV_FROMZ, K.listA.dev, K.Z1.p, nullptr, K.ld, scale, 0.0, out, nullptr, K.carry1.p, nullptr, nullptr,
-                   nullptr);
+        if (!rows || K.lead) {
+            launch_dense_uvt(ctx, K.n, K.r, K.ld, Um + K.off, Vm + K.off, K.Z1.p, same, with_obj ? K.C_onP.p : nullptr, scale,
+                             with_obj ? obj : nullptr);
+            if (shard_cols()) allreduce(K.Z1.p, K.np);
+            launch_auv(ctx, AUV_FROMZ, K.listA.dev, K.Z1.p, nullptr, K.ld, scale, 0.0, out, nullptr, K.carry1.p, nullptr, nullptr,
+                       nullptr);
+        }
+        if (rows) allreduce(out, K.listA.dev.n_rows);
         return;
     }
-    // with column sharding the objective is summed over ranks by the caller (the slot is all-reduced once)
+    // with sharding the objective is summed over ranks by the caller (the slot is all-reduced once)
     if (K.vc_on) {
         // multi-entry constraints through the item kernel (it clears the rows it does not own), then the singleton
         // rows and the objective row from the vertex-centric pass
-        if (K.vc_nnz_res > 0)
+        if (K.vc_nnz_res > 0 && (!rows || K.lead))
             launch_auv(ctx, same ? AUV_SAME : AUV_PAIR, K.vc_listRes.dev, Um + K.off, Vm + K.off, K.ld, scale, 0.0, out, nullptr,
                        K.carry1.p, nullptr, nullptr, nullptr);
-        launch_vc_auv(ctx, same ? AUV_SAME : AUV_PAIR, K.vc, K.ld, with_obj, Um + K.off, Vm + K.off, scale, 0.0, out, nullptr,
-                      nullptr, obj, nullptr);
-    } else
+        if (K.vc.n > 0)
+            launch_vc_auv(ctx, same ? AUV_SAME : AUV_PAIR, K.vc, K.ld, with_obj, Um + K.off, Vm + K.off, scale, 0.0, out, nullptr,
+                          nullptr, obj, nullptr);
+    } else if (!rows || K.lead)
         launch_auv(ctx, same ? AUV_SAME : AUV_PAIR, L.dev, Um + K.off, Vm + K.off, K.ld, scale, 0.0, out, nullptr,
                    K.carry1.p, nullptr, obj, nullptr);
-    if (with_obj && obj && K.c_rank1 != 0.0) {
+    if (with_obj && obj && K.c_rank1 != 0.0 && (!rows || K.lead)) {
         // <c ee^T, sym(U V^T)> = c (e^T U)(V^T e)
         launch_colsum(ctx, K.n, K.ld, Um + K.off, K.csA.p, K.cs_scratch.p);
         if (!same) launch_colsum(ctx, K.n, K.ld, Vm + K.off, K.csB.p, K.cs_scratch.p);
@@ -495,23 +628,32 @@ void Solver::cone_auv(ConeDev &K, bool with_obj, const double *Um, const double 
 void Solver::cone_auv_dual(ConeDev &K, const double *Rm, const double *Dm, double *out1, double *out2, double *obj1,
                            double *obj2) {
     ItemListBufs &L = K.listAC;
+    const bool rows = shard_rows();
+    if (rows) {
+        LB2_CUDA(cudaMemsetAsync(out1, 0, sizeof(double) * (size_t)L.dev.n_rows, ctx.stream));
+        LB2_CUDA(cudaMemsetAsync(out2, 0, sizeof(double) * (size_t)L.dev.n_rows, ctx.stream));
+    }
     if (K.dense_path) {
-        launch_dense_uvt_dual(ctx, K.n, K.r, K.ld, Rm + K.off, Dm + K.off, K.Z1.p, K.Z2.p, K.C_onP.p, 2.0, 1.0, obj1, obj2);
-        if (world > 1) { allreduce(K.Z1.p, K.np); allreduce(K.Z2.p, K.np); }
-        launch_auv(ctx, AUV_FROMZ, K.listA.dev, K.Z1.p, nullptr, K.ld, 2.0, 0.0, out1, nullptr, K.carry1.p, nullptr, nullptr,
-                   nullptr);
-        launch_auv(ctx, AUV_FROMZ, K.listA.dev, K.Z2.p, nullptr, K.ld, 1.0, 0.0, out2, nullptr, K.carry1.p, nullptr, nullptr,
-                   nullptr);
+        if (!rows || K.lead) {
+            launch_dense_uvt_dual(ctx, K.n, K.r, K.ld, Rm + K.off, Dm + K.off, K.Z1.p, K.Z2.p, K.C_onP.p, 2.0, 1.0, obj1, obj2);
+            if (shard_cols()) { allreduce(K.Z1.p, K.np); allreduce(K.Z2.p, K.np); }
+            launch_auv(ctx, AUV_FROMZ, K.listA.dev, K.Z1.p, nullptr, K.ld, 2.0, 0.0, out1, nullptr, K.carry1.p, nullptr, nullptr,
+                       nullptr);
+            launch_auv(ctx, AUV_FROMZ, K.listA.dev, K.Z2.p, nullptr, K.ld, 1.0, 0.0, out2, nullptr, K.carry1.p, nullptr, nullptr,
+                       nullptr);
+        }
+        if (rows && !(out1 == q1.p && out2 == q2.p)) { allreduce(out1, K.listA.dev.n_rows); allreduce(out2, K.listA.dev.n_rows); }
         return;
     }
     if (K.vc_on) {
-        if (K.vc_nnz_res > 0)
+        if (K.vc_nnz_res > 0 && (!rows || K.lead))
             launch_auv(ctx, AUV_DUAL, K.vc_listRes.dev, Rm + K.off, Dm + K.off, K.ld, 2.0, 1.0, out1, out2, K.carry1.p, K.carry2.p,
                        nullptr, nullptr);
-        launch_vc_auv(ctx, AUV_DUAL, K.vc, K.ld, true, Rm + K.off, Dm + K.off, 2.0, 1.0, out1, out2, nullptr, obj1, obj2);
-    } else
+        if (K.vc.n > 0)
+            launch_vc_auv(ctx, AUV_DUAL, K.vc, K.ld, true, Rm + K.off, Dm + K.off, 2.0, 1.0, out1, out2, nullptr, obj1, obj2);
+    } else if (!rows || K.lead)
         launch_auv(ctx, AUV_DUAL, L.dev, Rm + K.off, Dm + K.off, K.ld, 2.0, 1.0, out1, out2, K.carry1.p, K.carry2.p, obj1, obj2);
-    if (K.c_rank1 != 0.0 && obj1 && obj2) {
+    if (K.c_rank1 != 0.0 && obj1 && obj2 && (!rows || K.lead)) {
         launch_colsum(ctx, K.n, K.ld, Rm + K.off, K.csA.p, K.cs_scratch.p);
         launch_colsum(ctx, K.n, K.ld, Dm + K.off, K.csB.p, K.cs_scratch.p);
         launch_rank1_obj(ctx, K.ld, K.csA.p, K.csB.p, 2.0 * K.c_rank1, obj1, K.c_rank1, obj2);
@@ -540,6 +682,11 @@ void Solver::cone_wsum(ConeDev &K, const double *w, bool w_compact, bool addC, b
 
 void Solver::cone_mul(ConeDev &K, const double *X, double a, double bcoef, const double *Z, const double *Z2, double *Y,
                       double *red) {
+    if (shard_rows() && (K.row_hi == K.row_lo || (K.vc_on && K.vc.n == 0))) {
+        // nothing of this cone lives here: only the reduction slots are cleared so that the all-reduce sums the owners
+        if (red) LB2_CUDA(cudaMemsetAsync(red, 0, 2 * sizeof(double), ctx.stream));
+        return;
+    }
     if (K.dense_path)
         launch_dense_symm(ctx, K.n, K.r, K.ld, K.S.p, X + K.off, a, bcoef, Z ? Z + K.off : nullptr,
                           Z2 ? Z2 + K.off : nullptr, Y + K.off, red);
@@ -622,37 +769,44 @@ double Solver::cal_grad(double rho) {
 void Solver::lbfgs_direction(long long counter) {
     // LBFGSDirection, lorads_alm.c:230-391 (history ring of lbfgs_len nodes, lb_head = oldest) followed by
     // LBFGSDirectionUseGrad, lorads_alm.c:469-489.  The search direction lives in U, as in the reference.
+    // every vector pass runs on the rows this rank owns ([vo, vo + vn) of the concatenated vectors; everything without
+    // row sharding); the finished direction is then gathered, because A(UV^T) and the R update need all of its rows
     const int L = lbfgs_len;
-    double *D = U.p, *q = Dtemp.p;
+    double *D = U.p + vo, *q = Dtemp.p + vo;
+    const double *Gv = G.p + vo;
+    auto sv = [&](int k) { return lb_s[k].p + vo; };
+    auto yv = [&](int k) { return lb_y[k].p + vo; };
     if (vf_lbfgs && L == 2) {
         // vector-free form: two passes over the factor vectors, every inner product from the Gram table
         const int depth = (int)std::min<long long>(counter, 2);
         const int a = (lb_head + 1) % 2, bnode = lb_head;       // a = newest pair, bnode = the older one
         if (depth >= 1 && !vf_valid) {
-            launch_lbfgs_pair(ctx, Nt, false, lb_y[a].p, G.p, lb_s[a].p, lb_y[bnode].p, lb_s[bnode].p, S.p, SL_VF_D,
+            launch_lbfgs_pair(ctx, vn, false, yv(a), Gv, sv(a), yv(bnode), sv(bnode), S.p, SL_VF_D,
                               SL_BETA0 + a, SL_VF_YY + a, world == 1);
             if (world > 1) { allreduce(S.p + SL_VF_D, 8); launch_lbfgs_pair_finalize(ctx, S.p, SL_VF_D, SL_BETA0 + a, SL_VF_YY + a); }
             vf_valid = true;
         }
-        launch_lbfgs_dir(ctx, Nt, depth, D, G.p, lb_y[a].p, lb_s[a].p, lb_y[bnode].p, lb_s[bnode].p, S.p, SL_VF_D,
+        launch_lbfgs_dir(ctx, vn, depth, D, Gv, yv(a), sv(a), yv(bnode), sv(bnode), S.p, SL_VF_D,
                          SL_BETA0 + a, SL_BETA0 + bnode, SL_VF_YY + bnode, S.p + kNumSlots, (int)nCones + 1);
+        allgather_owned(U.p);
         return;
     }
     if (counter == 0) {
         // D = -G; the <D,G> >= 0 test of LBFGSDirectionUseGrad can only fire for G = 0, where it is a no-op
-        launch_axpby_dot(ctx, Nt, D, coef_const(-1.0), G.p, coef_const(0.0), nullptr, nullptr, S.p, SL_DG, false);
+        launch_axpby_dot(ctx, vn, D, coef_const(-1.0), Gv, coef_const(0.0), nullptr, nullptr, S.p, SL_DG, false);
+        allgather_owned(U.p);
         return;
     }
     const int K = (int)((counter <= L - 1) ? counter : L);
     auto node = [&](int i) { return ((lb_head - i) % L + L) % L; };   // i = 1 newest ... K oldest used
-    launch_dot(ctx, Nt, lb_s[node(1)].p, G.p, S.p, SL_T0);
+    launch_dot(ctx, vn, sv(node(1)), Gv, S.p, SL_T0);
     if (world > 1) allreduce(S.p + SL_T0, 1);
     for (int i = 1; i <= K; ++i) {
         const int nd = node(i);
-        const double *zvec = (i < K) ? lb_s[node(i + 1)].p : lb_y[nd].p;
+        const double *zvec = (i < K) ? sv(node(i + 1)) : yv(nd);
         // q = q - alpha*y, alpha = beta*<s,q>; -alpha is remembered for the second loop
-        launch_axpby_dot(ctx, Nt, q, coef_const(1.0), (i == 1) ? G.p : q,
-                         coef_prod(SL_BETA0 + nd, SL_T0, -1.0, SL_NEGALPHA0 + nd), lb_y[nd].p, zvec, S.p, SL_T0, false);
+        launch_axpby_dot(ctx, vn, q, coef_const(1.0), (i == 1) ? Gv : q,
+                         coef_prod(SL_BETA0 + nd, SL_T0, -1.0, SL_NEGALPHA0 + nd), yv(nd), zvec, S.p, SL_T0, false);
         if (world > 1) allreduce(S.p + SL_T0, 1);
     }
     for (int i = K; i >= 1; --i) {
@@ -660,16 +814,17 @@ void Solver::lbfgs_direction(long long counter) {
         if (i > 1) {
             // q = q + (alpha - beta*<y,q>) s
             Coef w{-1.0, SL_NEGALPHA0 + nd, -1.0, SL_BETA0 + nd, SL_T0, -1};
-            launch_axpby_dot(ctx, Nt, q, coef_const(1.0), q, w, lb_s[nd].p, lb_y[node(i - 1)].p, S.p, SL_T0, false);
+            launch_axpby_dot(ctx, vn, q, coef_const(1.0), q, w, sv(nd), yv(node(i - 1)), S.p, SL_T0, false);
             if (world > 1) allreduce(S.p + SL_T0, 1);
         } else {
             // D = -(q + w s)
             Coef negw{1.0, SL_NEGALPHA0 + nd, 1.0, SL_BETA0 + nd, SL_T0, -1};
-            launch_axpby_dot(ctx, Nt, D, coef_const(-1.0), q, negw, lb_s[nd].p, G.p, S.p, SL_DG, false);
+            launch_axpby_dot(ctx, vn, D, coef_const(-1.0), q, negw, sv(nd), Gv, S.p, SL_DG, false);
             if (world > 1) allreduce(S.p + SL_DG, 1);
         }
     }
-    launch_neg_if_nonneg(ctx, Nt, D, G.p, S.p, SL_DG);
+    launch_neg_if_nonneg(ctx, vn, D, Gv, S.p, SL_DG);
+    allgather_owned(U.p);
 }
 
 bool Solver::p12_from_rows() const {
@@ -691,16 +846,18 @@ void Solver::q12p12() {
             // third output of the same gather pass: A(RR^T) of the CURRENT point, i.e. the exact constrValSum and the
             // primal infeasibility that updateDimacsALM recomputes every iteration (lorads_alg_common.c:250-258)
             ConeDev &K = cones[0];
+            if (shard_rows()) LB2_CUDA(cudaMemsetAsync(q12.p, 0, sizeof(double) * (size_t)((q3.p - q1.p) + m + 1), ctx.stream));
             if (K.vc_on) {
-                if (K.vc_nnz_res > 0)
+                if (K.vc_nnz_res > 0 && (!shard_rows() || K.lead))
                     launch_auv(ctx, AUV_TRI, K.vc_listRes.dev, R.p + K.off, U.p + K.off, K.ld, 2.0, 1.0, q1.p, q2.p, K.carry1.p,
                                K.carry2.p, nullptr, nullptr, q3.p, K.carry3.p);
-                launch_vc_auv(ctx, AUV_TRI, K.vc, K.ld, true, R.p + K.off, U.p + K.off, 2.0, 1.0, q1.p, q2.p, q3.p, S.p + SL_P1,
-                              S.p + SL_P2);
-            } else
+                if (K.vc.n > 0)
+                    launch_vc_auv(ctx, AUV_TRI, K.vc, K.ld, true, R.p + K.off, U.p + K.off, 2.0, 1.0, q1.p, q2.p, q3.p, S.p + SL_P1,
+                                  S.p + SL_P2);
+            } else if (!shard_rows() || K.lead)
                 launch_auv(ctx, AUV_TRI, K.listAC.dev, R.p + K.off, U.p + K.off, K.ld, 2.0, 1.0, q1.p, q2.p, K.carry1.p, K.carry2.p,
                            S.p + SL_P1, S.p + SL_P2, q3.p, K.carry3.p);
-            if (K.c_rank1 != 0.0) {
+            if (K.c_rank1 != 0.0 && (!shard_rows() || K.lead)) {
                 launch_colsum(ctx, K.n, K.ld, R.p + K.off, K.csA.p, K.cs_scratch.p);
                 launch_colsum(ctx, K.n, K.ld, U.p + K.off, K.csB.p, K.cs_scratch.p);
                 launch_rank1_obj(ctx, K.ld, K.csA.p, K.csB.p, 2.0 * K.c_rank1, S.p + SL_P1, K.c_rank1, S.p + SL_P2);
@@ -708,7 +865,10 @@ void Solver::q12p12() {
         } else {
             cone_auv_dual(cones[0], R.p, U.p, q1.p, q2.p, S.p + SL_P1, S.p + SL_P2);
         }
-        if (world > 1) {
+        // column sharding on a dense-scratch cone: cone_auv_dual all-reduced Z1 / Z2 and every rank already holds the
+        // complete q1, q2 -- summing them again would scale them by `world`
+        const bool complete = shard_cols() && cones[0].dense_path;
+        if (world > 1 && !complete) {
             allreduce(q12.p, (long long)((tri ? q3.p : q2.p) - q1.p) + m + 1);
             if (p12_from_rows()) {
                 // the reduced objective rows ARE p1 and p2: no separate scalar all-reduce
@@ -873,14 +1033,19 @@ long long Solver::finish_front(double rho, double *tau, double *p12) {
 void Solver::enqueue_back(double rho, double tau, bool front_follows) {
     (void)rho; (void)tau;     // both are read from the scalar slots S[SL_RHO], S[SL_TAU] (push_scalars)
     const int head = lb_head;
-    launch_alm_step(ctx, Nt, S.p + SL_TAU, G.p, U.p, R.p, lb_y[head].p, lb_s[head].p);
+    launch_alm_step(ctx, vn, S.p + SL_TAU, G.p + vo, U.p + vo, R.p + vo, lb_y[head].p + vo, lb_s[head].p + vo);
+    if (shard_rows()) {
+        // R is replicated: the rows owned elsewhere take the same fused multiply-add from the gathered direction
+        launch_axpy_slot(ctx, vo, S.p + SL_TAU, U.p, R.p);
+        launch_axpy_slot(ctx, N - (vo + vn), S.p + SL_TAU, U.p + vo + vn, R.p + vo + vn);
+    }
     launch_alm_m_update(ctx, m, S.p + SL_TAU, q1.p, q2.p, s.p, lam.p, b.p, S.p + SL_RHO, M1.p);
     grad_from_M1(*this);
     // setlbfgsHisTwo, lorads_alm.c:657-678: y += G_new, beta = 1/<y,s>, advance the ring
     if (vf_lbfgs && lbfgs_len == 2) {
         const int other = (head + 1) % 2;
-        launch_lbfgs_pair(ctx, Nt, true, lb_y[head].p, G.p, lb_s[head].p, lb_y[other].p, lb_s[other].p, S.p, SL_VF_D,
-                          SL_BETA0 + head, SL_VF_YY + head, world == 1);
+        launch_lbfgs_pair(ctx, vn, true, lb_y[head].p + vo, G.p + vo, lb_s[head].p + vo, lb_y[other].p + vo, lb_s[other].p + vo,
+                          S.p, SL_VF_D, SL_BETA0 + head, SL_VF_YY + head, world == 1);
         if (world > 1) {
             // one all-reduce for the 8 dots (slots 64..71) and the per-cone gradient sums (slots 80..): 72..79 are unused
             allreduce(S.p + SL_VF_D, (kNumSlots - SL_VF_D) + 2 * (nCones + 1));
@@ -889,8 +1054,8 @@ void Solver::enqueue_back(double rho, double tau, bool front_follows) {
         vf_valid = true;
     } else {
         if (world > 1) allreduce(S.p + kNumSlots, 2 * (nCones + 1));
-        launch_axpby_dot(ctx, Nt, lb_y[head].p, coef_const(1.0), lb_y[head].p, coef_const(1.0), G.p, lb_s[head].p, S.p,
-                         SL_BETA0 + head, world == 1);
+        launch_axpby_dot(ctx, vn, lb_y[head].p + vo, coef_const(1.0), lb_y[head].p + vo, coef_const(1.0), G.p + vo,
+                         lb_s[head].p + vo, S.p, SL_BETA0 + head, world == 1);
         if (world > 1) {
             allreduce(S.p + SL_BETA0 + head, 1);
             launch_recip(ctx, S.p, SL_BETA0 + head);
@@ -997,7 +1162,10 @@ void Solver::cg_matvec(ConeDev &K, const double *x, const double *Vn, double *re
 
 void Solver::update_sdp_var_one(long long c, double *upd, const double *noupd, double rho, double tol, long long maxit) {
     ConeDev &K = cones[c];
-    const long long nk = K.n * K.ld, off = K.off;
+    // row sharding: every vector pass of the CG runs on this rank's rows of the cone; the vectors the mat-vec gathers
+    // from (the iterate at a restart, the search direction every iteration) are completed by an all-gather
+    const long long off = K.off + (shard_rows() ? K.row_lo * (long long)K.ld : 0);
+    const long long nk = (shard_rows() ? (K.row_hi - K.row_lo) : K.n) * (long long)K.ld;
     // M1 = rho (constrValSum - constrVal[c] - b) - lambda
     const double *cvf = nullptr;
     if (K.identity_act) cvf = K.cv.p; else { expand_cv(K, cvfull.p); cvf = cvfull.p; }
@@ -1006,7 +1174,7 @@ void Solver::update_sdp_var_one(long long c, double *upd, const double *noupd, d
     cone_wsum(K, M1.p, false, true);
     cone_mul(K, noupd, -1.0 / rho, 1.0, noupd, nullptr, Bls.p, nullptr);
 
-    double *x = upd + off, *bl = Bls.p + off, *r = cg_r.p + off, *p = cg_p.p + off, *Q = cg_Q.p + off;
+    double *x = upd + off, *bl = Bls.p + off, *r = cg_r.p + off, *p = cg_p.p + off;
     // shifted views so that the cone_* helpers (which add K.off) see this cone's slice
     double *r0 = cg_r.p, *p0 = cg_p.p, *Q0 = cg_Q.p;
     const double t0 = wall_time();
@@ -1024,13 +1192,14 @@ void Solver::update_sdp_var_one(long long c, double *upd, const double *noupd, d
         cgIter += K.cg_iter_last;
         return;
     }
-    LB2_CUDA(cudaMemcpyAsync(p, r, sizeof(double) * nk, cudaMemcpyDeviceToDevice, ctx.stream));
+    if (nk > 0) LB2_CUDA(cudaMemcpyAsync(p, r, sizeof(double) * nk, cudaMemcpyDeviceToDevice, ctx.stream));
     long long iter = 0;
     for (long long k = 0; k < maxit; ++k) {
         iter += 1;
+        allgather_cone(K, p0);
         cg_matvec(K, p0, noupd, Q0, p0, S.p + SL_CG_RED);       // Q = A p, S[SL_CG_RED+1] = <p,Q>
         if (world > 1) allreduce(S.p + SL_CG_RED, 2);
-        launch_cg_update(ctx, nk, x, r, p, Q, S.p, rrA, SL_CG_RED + 1, rrB);
+        launch_cg_update(ctx, nk, x, r, p, cg_Q.p + off, S.p, rrA, SL_CG_RED + 1, rrB);
         if (world > 1) allreduce(S.p + rrB, 1);
         read_slots();
         double rrNew = S_host[rrB];
@@ -1039,10 +1208,11 @@ void Solver::update_sdp_var_one(long long c, double *upd, const double *noupd, d
         double beta;
         if (k % 20 == 0) {
             // restart (also at k = 0, lorads_cgs.c:195): r = b - A x, p = q = r, then beta = <r,r>/<r,r>
+            allgather_cone(K, upd);
             cg_matvec(K, upd, noupd, r0, nullptr, nullptr);
             launch_axpby_dot(ctx, nk, r, coef_const(-1.0), r, coef_const(1.0), bl, r, S.p, rrB, false);
             if (world > 1) allreduce(S.p + rrB, 1);
-            LB2_CUDA(cudaMemcpyAsync(p, r, sizeof(double) * nk, cudaMemcpyDeviceToDevice, ctx.stream));
+            if (nk > 0) LB2_CUDA(cudaMemcpyAsync(p, r, sizeof(double) * nk, cudaMemcpyDeviceToDevice, ctx.stream));
             beta = 1.0;
         } else {
             beta = rrNew / rr;
@@ -1054,6 +1224,7 @@ void Solver::update_sdp_var_one(long long c, double *upd, const double *noupd, d
         std::swap(rrA, rrB);
         if (resi != resi) printf("File [%30s] Line [%d]\n", "lorads_b200 cg", (int)k);   // NaN trace, as the reference
     }
+    allgather_cone(K, upd);        // the other half of the sweep and A(UV^T) gather from every row of the new iterate
     K.cg_iter_last = iter;
     cgTime += wall_time() - t0;
     cgIter += iter;

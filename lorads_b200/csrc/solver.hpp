@@ -29,6 +29,7 @@ enum Slot : int {
     kNumSlots = 80        // followed by 2 slots per cone (sum G.G, sum G.Z2 of that cone) and 2 for the LP block
 };
 constexpr int kMaxLbfgs = 16;
+constexpr long long kMaxRank = 256;      // widest factor the gather kernels take (vc_kernels.cu vc_passes, kernels.cu)
 
 struct ItemListBufs {
     DBuf<int> ptr, irow, icol, split_row, split_first_slot, split_tile_a, split_tile_b, tile_row_lo, tile_row_hi;
@@ -61,11 +62,17 @@ struct ConeDev {
     // vertex-centric fast path (layout.hpp VcLayout)
     bool vc_on = false;
     long long vc_nnz_res = 0;                       // non-zeros of the residual (multi-entry) constraints
+    long long nnzC_adj = 0;                         // objective entries of the vertex-centric adjacency
     VcDev vc;
     DBuf<int> vc_order, vc_order_l, vc_u_ptr, vc_u_mid, vc_u_col, vc_u_tag, vc_d_con, vc_l_ptr, vc_l_row, vc_l_con, vc_Tr_ptr,
         vc_Tr_con;
     DBuf<double> vc_u_val, vc_d_coef, vc_l_coef, vc_Tr_val;
     ItemListBufs vc_listRes;
+    // row sharding (Solver::shard_rows): rows [row_lo, row_hi) of this cone are owned by this rank; `lead` marks the
+    // rank that evaluates the unsplittable parts (residual item list, rank-one objective term, dense / generic cones)
+    long long row_lo = 0, row_hi = 0;
+    bool lead = true;
+    std::vector<int32_t> vc_order_h, vc_order_l_h, row_weight_h;   // host copies, kept for the partition
     const double *pw = nullptr;                     // weights of the pending (C + A^*(w)) product (set by cone_wsum)
     bool pw_compact = false;
     DBuf<double> cv;                                // constrVal of the cone (compact, n_act + 1)
@@ -153,9 +160,27 @@ struct Solver {
 
     // ranks
     std::vector<long long> rank, rank_max;
-    // communicator (column sharding)
+    // communicator.  Two ways to shard a solve over the GPUs of a node:
+    //   rows (default, north_star): the concatenated factor rows of all cones are cut into `world` contiguous slabs of
+    //     equal work -- small cones go to one rank as a whole (partition by cone block), a huge cone is split by rows.
+    //     Every rank keeps full copies of the gathered operands (R, the direction, U, V) and computes only its slab:
+    //     its rows of the gradient / CG vectors, the pattern entries of its columns in A(UV^T).  Per A() evaluation
+    //     one all-reduce of the m-vectors, per dot product a scalar all-reduce, per new direction one all-gather.
+    //   columns (LORADS_B200_SHARD=cols): every rank holds all rows of r/world factor columns; no factor traffic,
+    //     but every rank still walks the whole pattern.
     int world = 1, myrank = 0;
     void *nccl = nullptr;
+    int shard_mode = 1;                        // 1 = rows, 0 = columns
+    bool shard_rows() const { return world > 1 && shard_mode == 1; }
+    bool shard_cols() const { return world > 1 && shard_mode == 0; }
+    long long vo = 0, vn = 0;                  // owned range [vo, vo + vn) of the concatenated factor vectors
+    std::vector<long long> part_rows;          // world + 1 boundaries in the concatenated row index space
+    std::vector<long long> own_off, own_cnt;   // owned element range of every rank (all-gather schedule)
+    void setup_row_partition();                // after preprocess + comm init
+    void compute_owned_ranges();               // after alloc_vars (leading dimensions known)
+    void allgather_owned(double *X);           // every rank broadcasts its slab of a concatenated vector
+    void allgather_cone(const ConeDev &K, double *X);   // the same restricted to one cone's slice
+    void bcast_ranges(double *X, long long lo, long long hi);
     // one-shot all-reduce over NVLink peer memory (kernels.cuh P2PDev); messages above p2p.cap go through NCCL
     P2PDev p2p;
     bool p2p_on = false;

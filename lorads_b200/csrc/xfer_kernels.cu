@@ -53,6 +53,43 @@ __global__ void __launch_bounds__(kT * 8) rm_to_cm_kernel(long long n, int r_own
 }
 }  // namespace
 
+// R[q] = fma(tau, D[q], R[q]) -- the R update of launch_alm_step on the rows a rank does not own (row sharding keeps a
+// full copy of R on every rank; the same fused multiply-add as alm_step_kernel, so all copies stay bit-identical)
+namespace {
+__global__ void __launch_bounds__(kBlock) axpy_slot_kernel(long long n, const double *tau_p, const double *__restrict__ D,
+                                                           double *__restrict__ R) {
+    const double tau = *tau_p;
+    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n; q += (long long)gridDim.x * kBlock)
+        R[q] = fma(tau, D[q], R[q]);
+}
+}  // namespace
+
+void launch_axpy_slot(Ctx &c, long long n, const double *tau_p, const double *D, double *R) {
+    if (n <= 0) return;
+    long long g = (n + (long long)kBlock * 4 - 1) / ((long long)kBlock * 4);
+    g = g > (long long)c.num_sms * 8 ? (long long)c.num_sms * 8 : g;
+    axpy_slot_kernel<<<(int)g, kBlock, 0, c.stream>>>(n, tau_p, D, R);
+    c.launches++;
+    LB2_CUDA(cudaGetLastError());
+}
+
+// val[e] *= f where tag[e] == -1: the objective entries of the vertex-centric adjacency (objScale_dualvar)
+namespace {
+__global__ void __launch_bounds__(kBlock) scale_tagged_kernel(long long n, const int *__restrict__ tag, double *__restrict__ val, double f) {
+    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n; q += (long long)gridDim.x * kBlock)
+        if (tag[q] == -1) val[q] *= f;
+}
+}  // namespace
+
+void launch_scale_tagged(Ctx &c, long long n, const int *tag, double *val, double f) {
+    if (n <= 0) return;
+    long long g = (n + (long long)kBlock * 4 - 1) / ((long long)kBlock * 4);
+    g = g > (long long)c.num_sms * 8 ? (long long)c.num_sms * 8 : g;
+    scale_tagged_kernel<<<(int)g, kBlock, 0, c.stream>>>(n, tag, val, f);
+    c.launches++;
+    LB2_CUDA(cudaGetLastError());
+}
+
 void launch_cm_to_rm(Ctx &c, long long n, int r_own, int ld, const double *src, double *dst) {
     if (n == 0) return;
     dim3 grid((unsigned)((n + kT - 1) / kT), (unsigned)((ld + kT - 1) / kT));
