@@ -370,6 +370,11 @@ def run_ours(args):
             continue
         kt_hot[which] = S.bench_kernel(which, 200)
         kt[which] = S.bench_kernel(which, 40, True)
+    comm_us = None
+    if world > 1:
+        barrier()
+        comm_us = {"allgather_direction": S.bench_kernel(10, 50) * 1e3, "allreduce_m_vectors": S.bench_kernel(11, 50) * 1e3,
+                   "allreduce_scalar_table": S.bench_kernel(12, 50) * 1e3}
     barrier()
 
     # ---------------- BASELINE.json configs[4] (MaxCut n = 1e6) at the same N: iterations/s + gather kernels, informational
@@ -399,7 +404,13 @@ def run_ours(args):
                 cold5 = S5.bench_kernel(wk, 10, True)
                 k5[kb5[wk][0]] = {"ms_cold": cold5, "alg_bytes": kb5[wk][1], "gbs": kb5[wk][1] / (cold5 * 1e-3) / 1e9,
                                   "frac_of_peak": kb5[wk][1] / (cold5 * 1e-3) / 1e9 / peak}
+            comm5 = None
+            if world > 1:
+                barrier()
+                comm5 = {"allgather_direction": S5.bench_kernel(10, 10) * 1e3, "allreduce_m_vectors": S5.bench_kernel(11, 10) * 1e3,
+                         "allreduce_scalar_table": S5.bench_kernel(12, 10) * 1e3}
             cfg5 = {"workload": f"MaxCut SDP n=m={w5['n']} edges={w5['edges']} seed={w5['seed']} rank={S5.rank(0)} ({w5['label']})",
+                    "collectives_us": comm5,
                     "alm_inner_iterations_per_second": done5 / sec5, "ms_per_step": 1e3 * sec5 / max(done5, 1), "steps": done5,
                     "n_gpus": world, "setup_seconds_incl_generation": setup5, "kernels_this_rank": k5}
             S5.close()
@@ -433,6 +444,7 @@ def run_ours(args):
                 "traffic_source": "profiles/r02_ncu_traffic.json (ncu --set full, cold-cache replay, per launch)",
                 "peak_source": peak_src, "alg_bytes_per_launch": kb[dom][1], "launch_ms": kt[dom],
                 "timing": "CUDA events around single launches, L2 flushed (384 MB overwritten) before every launch, mean of 40",
+                "collectives_us": comm_us,
                 "adjoint": {"kernel": kb[3][0], "achieved": kb[3][1] / (kt[3] * 1e-3) / 1e9,
                             "frac": kb[3][1] / (kt[3] * 1e-3) / 1e9 / peak, "alg_bytes_per_launch": kb[3][1], "launch_ms": kt[3],
                             "traffic": ncu_traffic(kb[3][0]) if WORKLOAD is WORKLOADS["cfg2"] else None},

@@ -82,6 +82,13 @@ void Solver::allreduce(double *p, long long count) {
 // place, as one NCCL group (the slabs have different lengths, so this is an all-gather with per-rank counts).
 void Solver::bcast_ranges(double *X, long long lo, long long hi) {
     if (world <= 1) return;
+    if (equal_rows > 0 && g_nccl.allgather) {
+        // equal slabs of a single cone: in place, the send buffer is this rank's slab inside the receive buffer
+        const long long cnt = equal_rows * (long long)cones[0].ld;
+        const int rc = g_nccl.allgather(X + cnt * myrank, X, (size_t)cnt, 8 /* ncclDouble */, nccl, ctx.stream);
+        if (rc != 0) throw CudaError(std::string("ncclAllGather failed: ") + (g_nccl.errstr ? g_nccl.errstr(rc) : "?"));
+        return;
+    }
     if (!g_nccl.bcast || !g_nccl.group_start || !g_nccl.group_end) throw CudaError("NCCL broadcast entry points missing");
     int rc = g_nccl.group_start();
     for (int k = 0; k < world && rc == 0; ++k) {
@@ -252,9 +259,12 @@ int lb2_comm_init(lb2_solver *s, const void *id128, int rank, int world) {
     // sharded runs use the Gram-table L-BFGS: one all-reduce of 8 scalars per iteration instead of five
     // sequential scalar all-reduces (LORADS_B200_EXACT_LBFGS=1 keeps the two-loop recursion)
     if (getenv("LORADS_B200_EXACT_LBFGS") == nullptr) s->impl.vf_lbfgs = true;
-    // rows (north_star: cone blocks / row slabs) unless LORADS_B200_SHARD=cols asks for the column scheme
+    // Two schemes (solver.hpp): factor columns (default) or row slabs / cone blocks (LORADS_B200_SHARD=rows, the scheme
+    // north_star names).  Both are built, tested against the oracle on two GPUs and measured at 2 / 4 / 8 GPUs; on the
+    // BASELINE workloads (random sparse graphs: every rank needs every row of the gathered factor) the row scheme pays
+    // an all-gather of a whole factor per step and is slower, so columns are the default.
     const char *mode = getenv("LORADS_B200_SHARD");
-    s->impl.shard_mode = (mode && std::string(mode) == "cols") ? 0 : 1;
+    s->impl.shard_mode = (mode && std::string(mode) == "rows") ? 1 : 0;
     if (s->impl.shard_mode == 1) s->impl.setup_row_partition();
     setup_p2p(s->impl);
     LB2_CATCH
@@ -596,6 +606,11 @@ int lb2_bench_kernel(lb2_solver *s, int which, lb2_int reps, int flush_l2, doubl
         case 2: S.cone_wsum(K, S.M1.p, false, true); break;
         case 3: S.cone_mul(K, S.R.p, 2.0, 0.0, nullptr, nullptr, S.G.p, S.S.p + kNumSlots); break;
         case 4: launch_axpby_dot(S.ctx, S.N, S.Dtemp.p, coef_const(1.0), S.G.p, coef_const(-0.5), S.V.p, S.R.p, S.S.p, SL_T1, false); break;
+        // the collectives of a sharded step (no-ops on one GPU): all-gather of the direction, all-reduce of the
+        // three m-vectors of the fused A() pass, all-reduce of the dot table + gradient sums
+        case 10: S.allgather_owned(S.Dtemp.p); break;
+        case 11: S.allreduce(S.q12.p, (long long)(S.q3.p - S.q1.p) + S.m + 1); break;
+        case 12: S.allreduce(S.S.p + SL_VF_D, (kNumSlots - SL_VF_D) + 2 * (S.nCones + 1)); break;
         default: throw std::invalid_argument("unknown kernel id");
         }
     };

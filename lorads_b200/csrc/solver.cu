@@ -325,7 +325,9 @@ void Solver::alloc_vars() {
     }
     Nt = N + nLp;
     compute_owned_ranges();
-    for (DBuf<double> *v : {&R, &U, &V, &G, &M2, &Bls, &cg_r, &cg_p, &cg_Q, &Dtemp}) { retire(*v); v->alloc((size_t)Nt); }
+    Nalloc = Nt;
+    if (shard_rows() && equal_rows > 0) Nalloc = std::max<long long>(Nt, equal_rows * world * (long long)cones[0].ld);
+    for (DBuf<double> *v : {&R, &U, &V, &G, &M2, &Bls, &cg_r, &cg_p, &cg_Q, &Dtemp}) { retire(*v); v->alloc((size_t)Nalloc); }
     {
         // split-K scratch of the dense symmetric product: up to 32 partial n x ldp blocks of the largest dense cone
         size_t need = 0;
@@ -340,7 +342,7 @@ void Solver::alloc_vars() {
     for (DBuf<double> &v : lb_y) retire(v);
     lb_s.clear(); lb_y.clear();
     lb_s.resize(lbfgs_len); lb_y.resize(lbfgs_len);
-    for (int k = 0; k < lbfgs_len; ++k) { lb_s[k].alloc((size_t)Nt); lb_y[k].alloc((size_t)Nt); }
+    for (int k = 0; k < lbfgs_len; ++k) { lb_s[k].alloc((size_t)Nalloc); lb_y[k].alloc((size_t)Nalloc); }
     lb_head = 0;
 }
 
@@ -369,7 +371,13 @@ void Solver::setup_row_partition() {
     long long rows_total = 0;
     for (long long c = 0; c < nCones; ++c) rows_total += cones[c].n;
     part_rows[(size_t)world] = rows_total;
-    {
+    equal_rows = 0;
+    if (nCones == 1 && cones[0].vc_on && getenv("LORADS_B200_UNEQUAL_SLABS") == nullptr) {
+        // one big block: slabs of equal length (the work per row of these patterns is uniform enough) so that the
+        // all-gather of a factor vector is ONE in-place ncclAllGather instead of a group of broadcasts
+        equal_rows = (rows_total + world - 1) / world;
+        for (int k = 1; k < world; ++k) part_rows[(size_t)k] = std::min<long long>(rows_total, equal_rows * k);
+    } else {
         double acc = 0.0;
         long long row0 = 0;
         int next = 1;

@@ -161,21 +161,24 @@ struct Solver {
     // ranks
     std::vector<long long> rank, rank_max;
     // communicator.  Two ways to shard a solve over the GPUs of a node:
-    //   rows (default, north_star): the concatenated factor rows of all cones are cut into `world` contiguous slabs of
+    //   rows (LORADS_B200_SHARD=rows, north_star): the concatenated factor rows of all cones are cut into `world` contiguous slabs of
     //     equal work -- small cones go to one rank as a whole (partition by cone block), a huge cone is split by rows.
     //     Every rank keeps full copies of the gathered operands (R, the direction, U, V) and computes only its slab:
     //     its rows of the gradient / CG vectors, the pattern entries of its columns in A(UV^T).  Per A() evaluation
     //     one all-reduce of the m-vectors, per dot product a scalar all-reduce, per new direction one all-gather.
-    //   columns (LORADS_B200_SHARD=cols): every rank holds all rows of r/world factor columns; no factor traffic,
-    //     but every rank still walks the whole pattern.
+    //   columns (default): every rank holds all rows of r/world factor columns; no factor traffic, but every rank
+    //     still walks the whole pattern.  Faster than rows on random sparse graphs (measured).
     int world = 1, myrank = 0;
     void *nccl = nullptr;
-    int shard_mode = 1;                        // 1 = rows, 0 = columns
+    int shard_mode = 0;                        // 1 = rows, 0 = columns
     bool shard_rows() const { return world > 1 && shard_mode == 1; }
     bool shard_cols() const { return world > 1 && shard_mode == 0; }
     long long vo = 0, vn = 0;                  // owned range [vo, vo + vn) of the concatenated factor vectors
     std::vector<long long> part_rows;          // world + 1 boundaries in the concatenated row index space
     std::vector<long long> own_off, own_cnt;   // owned element range of every rank (all-gather schedule)
+    long long equal_rows = 0;                  // > 0: one splittable cone cut into slabs of this many rows (the last one may
+                                               // be shorter): the all-gather is a single in-place ncclAllGather
+    long long Nalloc = 0;                      // allocated length of the factor vectors (>= Nt; padded for equal slabs)
     void setup_row_partition();                // after preprocess + comm init
     void compute_owned_ranges();               // after alloc_vars (leading dimensions known)
     void allgather_owned(double *X);           // every rank broadcasts its slab of a concatenated vector

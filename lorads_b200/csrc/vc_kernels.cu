@@ -79,9 +79,47 @@ __device__ __forceinline__ double group_total(const Lanes &L, double t) {
 }
 
 // acc[q] += sum_{e in [ea,eb)} val(e) * X[col[e], 4*gl + 32*q ..]   (one adjacency segment of a row)
-template <int NP, int UN, class ValF>
+// PL = entries every lane fetches per chunk.  With G >= 3 lanes per row one entry per lane (PL = 1) gives chunks of G
+// entries; with one or two lanes per row (ld <= 8: low rank, or the column-sharded slices of a factor) the chunk would
+// be a single entry or a pair and the loop would be a chain of dependent loads, so each lane fetches PL = 4 / 2 entries
+// and all the row gathers of the chunk are issued before the first multiply-add.
+template <int NP, int UN, int PL, class ValF>
 __device__ __forceinline__ void gather_segment(const Lanes &L, int ea, int eb, const int *__restrict__ col, ValF valf,
                                                const double *__restrict__ X, int ld, d4 (&acc)[NP]) {
+    if constexpr (PL > 1) {
+        // PL = 4 is launched with G = 1 (ld <= 4), PL = 2 with G = 2 (ld <= 8): four entries per chunk either way
+        static_assert(NP == 1, "several entries per lane only for rows of at most 8 columns");
+        constexpr int GS = 4 / PL;
+        for (int e = ea; e < eb; e += 4) {
+            int jc[PL];
+            double sc[PL];
+#pragma unroll
+            for (int k = 0; k < PL; ++k) {
+                const int idx = e + k * GS + L.gl;
+                const bool ok = idx < eb;
+                jc[k] = ok ? col[idx] : 0;
+                sc[k] = ok ? valf(idx) : 0.0;
+            }
+            const int cnt = min(4, eb - e);
+            d4 v[PL][GS];
+            double sv[PL][GS];
+#pragma unroll
+            for (int k = 0; k < PL; ++k)
+#pragma unroll
+                for (int h = 0; h < GS; ++h) {
+                    const bool live = (k * GS + h) < cnt;
+                    const int j = (GS == 1) ? jc[k] : __shfl_sync(L.gmask, jc[k], L.base + h);
+                    const double s = (GS == 1) ? sc[k] : __shfl_sync(L.gmask, sc[k], L.base + h);
+                    sv[k][h] = live ? s : 0.0;
+                    v[k][h] = (live && 4 * L.gl < ld) ? ld4(X + (size_t)j * ld + 4 * L.gl) : kZero4;
+                }
+#pragma unroll
+            for (int k = 0; k < PL; ++k)
+#pragma unroll
+                for (int h = 0; h < GS; ++h) fma4(acc[0], sv[k][h], v[k][h]);
+        }
+        return;
+    }
     for (int e = ea; e < eb; e += L.G) {
         const bool ok = e + L.gl < eb;
         const int jc = ok ? col[e + L.gl] : 0;
@@ -113,8 +151,8 @@ __device__ __forceinline__ void gather_segment(const Lanes &L, int ea, int eb, c
 // ---------------------------------------------------------------------------------------------------------------
 //  Y = a * (useC*C + sum_con w[con] A_con) X + b Z
 // ---------------------------------------------------------------------------------------------------------------
-template <int NP, int UN>
-__global__ void __launch_bounds__(kBlock, UN == 1 ? 5 : 3)
+template <int NP, int UN, int MINB, int PL>
+__global__ void __launch_bounds__(kBlock, MINB)
     vc_spmm_kernel(VcDev V, int ld, int G, bool useC, const double *__restrict__ w, const int *__restrict__ wmap,
                    const double *__restrict__ Sres, const double *__restrict__ X, double a, double b,
                    const double *__restrict__ Z, const double *__restrict__ Z2, double *__restrict__ Y, ReduceScratch rs,
@@ -138,7 +176,7 @@ __global__ void __launch_bounds__(kBlock, UN == 1 ? 5 : 3)
                 const int eb = useC ? V.u_ptr[i + 1] : V.u_mid[i];
                 const int *tg = V.u_tag;
                 const double *uv = V.u_val;
-                gather_segment<NP, UN>(L, ea, eb, V.u_col,
+                gather_segment<NP, UN, PL>(L, ea, eb, V.u_col,
                                        [tg, uv, w, wmap, Sres](int e) {
                                            const int t = tg[e];
                                            if (t == -1) return uv[e];
@@ -180,8 +218,8 @@ __global__ void __launch_bounds__(kBlock, UN == 1 ? 5 : 3)
 //                             TRI   DUAL + out3 = A(U U^T)
 // The objective row (index V.obj_row) of out1 / out2 receives s1 <C, sym(U W^T)> / s2 <C, W W^T>, which are also
 // added to *obj1 / *obj2, as the item kernel does.
-template <int MODE, int NP, int UN>
-__global__ void __launch_bounds__(kBlock, UN == 1 ? 4 : 3)
+template <int MODE, int NP, int UN, int MINB, int PL>
+__global__ void __launch_bounds__(kBlock, MINB)
     vc_auv_kernel(VcDev V, int ld, int G, bool with_obj, const double *__restrict__ U, const double *__restrict__ W, double s1,
                   double s2, double *__restrict__ out1, double *__restrict__ out2, double *__restrict__ out3, double *obj1,
                   double *obj2, ReduceScratch rs) {
@@ -212,7 +250,7 @@ __global__ void __launch_bounds__(kBlock, UN == 1 ? 4 : 3)
 #pragma unroll
                 for (int q = 0; q < NP; ++q) t[q] = kZero4;
                 const double *uv = V.u_val;
-                gather_segment<NP, UN>(L, ca, cb, V.u_col, [uv](int e) { return uv[e]; }, W2, ld, t);
+                gather_segment<NP, UN, PL>(L, ca, cb, V.u_col, [uv](int e) { return uv[e]; }, W2, ld, t);
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
                     p1 += dot4(uj[q], t[q]);
@@ -334,18 +372,18 @@ inline int vc_grid(const Ctx &c, long long n, int G, int per_sm) {
     return (int)std::max<long long>(g, 1);
 }
 
-template <int NP, int UN>
+template <int NP, int UN, int MINB = (UN == 1 ? 5 : 3), int PL = 1>
 void spmm_launch(Ctx &c, const VcDev &V, int ld, bool useC, const double *w, const int *wmap, const double *Sres, const double *X,
                  double a, double b, const double *Z, const double *Z2, double *Y, double *red, const double *cs, double c1) {
     const int G = vc_lanes(ld);
-    vc_spmm_kernel<NP, UN><<<vc_grid(c, V.n, G, UN == 1 ? 5 : 3), kBlock, 0, c.stream>>>(V, ld, G, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, c.rs, red, cs, c1);
+    vc_spmm_kernel<NP, UN, MINB, PL><<<vc_grid(c, V.n, G, MINB), kBlock, 0, c.stream>>>(V, ld, G, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, c.rs, red, cs, c1);
 }
 
-template <int MODE, int NP, int UN>
+template <int MODE, int NP, int UN, int MINB = (UN == 1 ? 4 : 3), int PL = 1>
 void auv_launch(Ctx &c, const VcDev &V, int ld, bool with_obj, const double *U, const double *W, double s1, double s2, double *o1,
                 double *o2, double *o3, double *obj1, double *obj2) {
     const int G = vc_lanes(ld);
-    vc_auv_kernel<MODE, NP, UN><<<vc_grid(c, V.n, G, UN == 1 ? 4 : 3), kBlock, 0, c.stream>>>(V, ld, G, with_obj, U, W, s1, s2, o1, o2, o3, obj1, obj2, c.rs);
+    vc_auv_kernel<MODE, NP, UN, MINB, PL><<<vc_grid(c, V.n, G, MINB), kBlock, 0, c.stream>>>(V, ld, G, with_obj, U, W, s1, s2, o1, o2, o3, obj1, obj2, c.rs);
 }
 
 template <int MODE>
@@ -353,7 +391,17 @@ void auv_dispatch(Ctx &c, int np, int un, const VcDev &V, int ld, bool with_obj,
                   double s2, double *o1, double *o2, double *o3, double *obj1, double *obj2) {
 #define LB2_VC_AUV(NP_, UN_) auv_launch<MODE, NP_, UN_>(c, V, ld, with_obj, U, W, s1, s2, o1, o2, o3, obj1, obj2)
     switch (np) {
-    case 1: if (un >= 4) LB2_VC_AUV(1, 4); else if (un == 2) LB2_VC_AUV(1, 2); else LB2_VC_AUV(1, 1); break;
+    case 1: {
+        static const int minb = getenv("LORADS_B200_VC_MINB_AUV") ? atoi(getenv("LORADS_B200_VC_MINB_AUV")) : 0;
+        if (ld <= 4) auv_launch<MODE, 1, 1, 3, 4>(c, V, ld, with_obj, U, W, s1, s2, o1, o2, o3, obj1, obj2);
+        else if (ld <= 8) auv_launch<MODE, 1, 1, 3, 2>(c, V, ld, with_obj, U, W, s1, s2, o1, o2, o3, obj1, obj2);
+        else if (un >= 4) LB2_VC_AUV(1, 4);
+        else if (un == 2) LB2_VC_AUV(1, 2);
+        else if (minb == 5) auv_launch<MODE, 1, 1, 5>(c, V, ld, with_obj, U, W, s1, s2, o1, o2, o3, obj1, obj2);
+        else if (minb == 6) auv_launch<MODE, 1, 1, 6>(c, V, ld, with_obj, U, W, s1, s2, o1, o2, o3, obj1, obj2);
+        else LB2_VC_AUV(1, 1);
+        break;
+    }
     case 2: LB2_VC_AUV(2, 1); break;
     case 3: LB2_VC_AUV(3, 1); break;
     case 4: LB2_VC_AUV(4, 1); break;
@@ -382,7 +430,17 @@ void launch_vc_spmm(Ctx &c, const VcDev &V, int ld, bool useC, const double *w, 
     const int un = vc_unroll(V.n, ld);
 #define LB2_VC_SPMM(NP_, UN_) spmm_launch<NP_, UN_>(c, V, ld, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, red, cs, c1)
     switch (np) {
-    case 1: if (un >= 4) LB2_VC_SPMM(1, 4); else if (un == 2) LB2_VC_SPMM(1, 2); else LB2_VC_SPMM(1, 1); break;
+    case 1: {
+        static const int minb = getenv("LORADS_B200_VC_MINB") ? atoi(getenv("LORADS_B200_VC_MINB")) : 0;
+        if (ld <= 4) spmm_launch<1, 1, 4, 4>(c, V, ld, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, red, cs, c1);
+        else if (ld <= 8) spmm_launch<1, 1, 4, 2>(c, V, ld, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, red, cs, c1);
+        else if (un >= 4) LB2_VC_SPMM(1, 4);
+        else if (un == 2) LB2_VC_SPMM(1, 2);
+        else if (minb == 6) spmm_launch<1, 1, 6>(c, V, ld, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, red, cs, c1);
+        else if (minb == 8) spmm_launch<1, 1, 8>(c, V, ld, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, red, cs, c1);
+        else LB2_VC_SPMM(1, 1);
+        break;
+    }
     case 2: LB2_VC_SPMM(2, 1); break;
     case 3: LB2_VC_SPMM(3, 1); break;
     case 4: LB2_VC_SPMM(4, 1); break;

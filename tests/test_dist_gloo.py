@@ -126,3 +126,90 @@ def test_sharded_gram_lbfgs_direction_world2():
     for p in procs:
         p.join(timeout=60)
     assert all(err < 1e-11 for _, err in res), res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# row-slab / cone-block sharding (the default scheme): every rank owns a contiguous slab of rows, evaluates the pattern
+# entries of its COLUMNS in A(sym(U V^T)) and its ROWS of (C + A^*(w)) V from the vertex-centric layout, one all-reduce
+# (sum) completes the m-vector and the objective, an all-gather completes the product.
+# ---------------------------------------------------------------------------------------------------------------------
+def _row_slab_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lorads_b200 import capi, sdpa
+    from oracle import restate
+    ok = True
+    for inst in (sdpa.maxcut(90, 400, 6), sdpa.matrix_completion(40, 30, 500, 2, 8), sdpa.lovasz_theta(70, 300, 9)):
+        O = restate.OracleSolver(inst)
+        lay = capi.host_layout(inst.cones[0], inst.m)
+        if not lay.get("vc_on"):
+            continue
+        n = lay["n"]
+        U, V = O.factor("U").copy(), O.factor("V").copy()
+        # slabs of equal work: the weights Solver::setup_row_partition uses
+        wgt = 8 + np.diff(lay["vc_u_ptr"]) + 2 * np.diff(lay["vc_l_ptr"])
+        cum = np.cumsum(wgt)
+        cuts = [0] + [int(np.searchsorted(cum, cum[-1] * k / world) + 1) for k in range(1, world)] + [n]
+        lo, hi = cuts[rank], cuts[rank + 1]
+        mine = np.zeros(n, bool)
+        mine[lo:hi] = True
+        # --- A(sym(U V^T)) of the owned columns + objective partial
+        out = np.zeros(lay["n_act"])
+        rows = np.repeat(np.arange(n), np.diff(lay["vc_u_ptr"]))
+        sel = (lay["vc_u_tag"] == -1) & mine[rows]
+        T = np.zeros_like(V)
+        np.add.at(T, rows[sel], lay["vc_u_val"][sel][:, None] * V[lay["vc_u_col"][sel]])
+        obj = float(np.einsum("ij,ij->", U[lo:hi], T[lo:hi]))
+        d = lay["vc_d_con"]
+        if d.size:
+            has = (d >= 0) & mine
+            out[d[has]] = lay["vc_d_coef"][has] * np.einsum("ij,ij->i", U[has], V[has])
+        if lay["vc_l_row"].size:
+            j = np.repeat(np.arange(n), np.diff(lay["vc_l_ptr"]))
+            keep = mine[j]
+            i = lay["vc_l_row"].astype(np.int64)[keep]
+            jj = j[keep]
+            z = 0.5 * (np.einsum("ij,ij->i", U[i], V[jj]) + np.einsum("ij,ij->i", U[jj], V[i]))
+            out[lay["vc_l_con"][keep]] = lay["vc_l_coef"][keep] * z
+        if lay["vc_nnz_res"] and rank == 0:                 # the residual item list is evaluated by the cone's lead rank
+            i, j = lay["vc_res_irow"].astype(np.int64), lay["vc_res_icol"].astype(np.int64)
+            z = 0.5 * (np.einsum("ij,ij->i", U[i], V[j]) + np.einsum("ij,ij->i", U[j], V[i]))
+            r = np.repeat(np.arange(lay["n_act"]), np.diff(lay["vc_res_ptr"]))
+            np.add.at(out, r, lay["vc_res_coef"] * z)
+        if rank == 0:
+            obj += lay["c_rank1"] * float(U.sum(axis=0) @ V.sum(axis=0))
+        part = torch.from_numpy(np.concatenate([out, [obj]]))
+        dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        full = np.zeros(inst.m)
+        full[lay["act_idx"]] = part.numpy()[:-1]
+        ref = O.auv("U", "V")
+        ok &= bool(np.linalg.norm(full - ref) <= 1e-12 * np.linalg.norm(ref))
+        ok &= bool(abs(part.numpy()[-1] - O.obj_auv("U", "V")) <= 1e-12 * max(1.0, abs(O.obj_auv("U", "V"))))
+        # --- owned rows of (C + A^*(w)) V, completed by an all-gather
+        from test_host_layout import vc_product
+        w = np.random.default_rng(3).standard_normal(inst.m)
+        Y = vc_product(lay, w[lay["act_idx"]], V) + lay["c_rank1"] * V.sum(axis=0)[None, :]
+        Y[~mine] = 0.0                                          # a rank only computes its slab
+        t = torch.from_numpy(Y)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)                # disjoint slabs: the sum is the all-gather
+        refY = O.wsum_mulrk(w, True, "V")
+        ok &= bool(np.linalg.norm(t.numpy() - refY) <= 1e-12 * np.linalg.norm(refY))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_row_slab_sharded_operators_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_row_slab_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res

@@ -78,7 +78,9 @@ def test_golden_alm_inner_iterations(golden):
     for k in range(len(g["it_tau"])):
         root, o = G.alm_inner_iter(rho, k)
         assert root == int(g["it_root"][k])
-        tol = 1e-11 * 10 ** k      # rounding noise is amplified by the L-BFGS recursion iteration after iteration
+        # measured deviation over the eight stored iterations of all golden cases: <= 1.1e-11 (scripts/inner_iter_errors.py,
+        # profiles/r02_inner_iter_errors.log); the bound is flat, ten times that, with the first iteration at 1e-12
+        tol = 1e-12 if k == 0 else 1e-10
         assert abs(o["tau"] - g["it_tau"][k]) <= tol * max(1.0, abs(g["it_tau"][k]))
         assert abs(o["lag_norm_sq"] - g["it_lag"][k]) <= tol * abs(g["it_lag"][k])
         assert abs(o["pinf"] - g["it_pinf"][k]) <= tol * abs(g["it_pinf"][k])
@@ -118,6 +120,10 @@ EDGE_CASES = {
     # ld = 4: the two-lane groups of the gather kernels (also what an 8-way column shard of a rank-24 factor sees)
     "rank_one": (lambda: sdpa.maxcut(300, 900, 45), dict(times_log_rank=0.1)),
     "maxcut_rank4": (lambda: sdpa.maxcut(600, 4000, 53), dict(times_log_rank=0.6)),
+    # ld = 8: two lanes per row, two adjacency entries per lane and chunk
+    "maxcut_rank8": (lambda: sdpa.maxcut(600, 4000, 54), dict(times_log_rank=1.2)),
+    "mcomp_rank8": (lambda: sdpa.matrix_completion(150, 120, 3000, 3, 55), dict(times_log_rank=1.2)),
+    "mcomp_rank4": (lambda: sdpa.matrix_completion(150, 120, 3000, 3, 56), dict(times_log_rank=0.6)),
     # isolated vertices: zero diagonal entries of C are dropped by the reader, pattern still has the diagonal
     "maxcut_isolated": (lambda: sdpa.maxcut(200, 60, 46), {}),
     # m > n, single-entry off-diagonal constraints, diagonal C
@@ -185,10 +191,10 @@ def test_against_restatement(case):
         rg, og = G.alm_inner_iter(rho, k)
         ro, oo = O.alm_inner_iter(rho, k)
         assert rg == ro
-        tol = 1e-11 * 10 ** k
+        tol = 1e-12 if k == 0 else 1e-9      # flat bound (was 1e-11 * 10^k); ill-conditioned edge shapes included
         assert abs(og["tau"] - oo["tau"]) <= tol * max(1.0, abs(oo["tau"]))
         assert abs(og["lag_norm_sq"] - oo["lag_norm_sq"]) <= tol * oo["lag_norm_sq"]
-    assert rel_err(G.get_factor("R"), O.factor("R")) < 1e-7
+    assert rel_err(G.get_factor("R"), O.factor("R")) < 1e-9
 
 
 def test_multi_block_with_sparse_constraint_cone():
@@ -211,7 +217,7 @@ def test_multi_block_with_sparse_constraint_cone():
     assert abs(G.alm_prepare(rho) - O.alm_prepare(rho)) <= KTOL * O.alm_prepare(rho)
     for k in range(4):
         (rg, og), (ro, oo) = G.alm_inner_iter(rho, k), O.alm_inner_iter(rho, k)
-        assert rg == ro and abs(og["tau"] - oo["tau"]) <= 1e-10 * 10 ** k
+        assert rg == ro and abs(og["tau"] - oo["tau"]) <= (1e-12 if k == 0 else 1e-10)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -1,7 +1,7 @@
 """The sharded path on two GPUs (one process per GPU, NCCL), checked against the ORACLE -- not against the single-GPU
 solver: operators vs the C restatement of the reference (oracle/lorads_oracle.c), whole solves vs the reference's
-own results stored in tests/golden.  Both sharding schemes run: row slabs / cone blocks (default) and factor columns
-(LORADS_B200_SHARD=cols).  Skipped with fewer than two GPUs."""
+own results stored in tests/golden.  Both sharding schemes run: factor columns (default) and row slabs / cone blocks
+(LORADS_B200_SHARD=rows).  Skipped with fewer than two GPUs."""
 import json
 import os
 import subprocess
