@@ -210,7 +210,7 @@ def host_layout(cone, m: int) -> dict:
                        vc_order=geti(30, n), vc_order_l=geti(31, n),
                        vc_u_ptr=geti(32, n + 1), vc_u_mid=geti(33, n), vc_u_col=geti(34, nu), vc_u_tag=geti(35, nu),
                        vc_u_val=getd(36, nu), vc_d_con=geti(37, nd), vc_d_coef=getd(38, nd),
-                       vc_l_ptr=geti(39, n + 1), vc_l_row=geti(40, nl), vc_l_con=geti(41, nl), vc_l_coef=getd(42, nl),
+                       vc_l_ptr=geti(39, n + 1), vc_l_row=geti(40, nl), vc_l_col=geti(50, nl), vc_l_con=geti(41, nl), vc_l_coef=getd(42, nl),
                        vc_Tr_ptr=geti(43, psize + 1), vc_Tr_con=geti(44, nnz_res), vc_Tr_val=getd(45, nnz_res),
                        vc_res_ptr=geti(46, n_act + 1), vc_res_irow=geti(47, nnz_res), vc_res_icol=geti(48, nnz_res),
                        vc_res_coef=getd(49, nnz_res))

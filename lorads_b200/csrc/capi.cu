@@ -328,6 +328,7 @@ int lb2_layout_get(const lb2_layout *l, int which, void *dst) {
     case 32: return put(L.vc.u_ptr); case 33: return put(L.vc.u_mid); case 34: return put(L.vc.u_col); case 35: return put(L.vc.u_tag);
     case 36: return put(L.vc.u_val); case 37: return put(L.vc.d_con); case 38: return put(L.vc.d_coef);
     case 39: return put(L.vc.l_ptr); case 40: return put(L.vc.l_row); case 41: return put(L.vc.l_con); case 42: return put(L.vc.l_coef);
+    case 50: return put(L.vc.l_col);
     case 43: return put(L.vc.Tr_ptr); case 44: return put(L.vc.Tr_con); case 45: return put(L.vc.Tr_val);
     case 46: return put(L.vc.listRes.ptr); case 47: return put(L.vc.listRes.irow); case 48: return put(L.vc.listRes.icol);
     case 49: return put(L.vc.listRes.coef);

@@ -74,7 +74,9 @@ struct VcDev {
     const int *u_ptr = nullptr, *u_mid = nullptr, *u_col = nullptr, *u_tag = nullptr;
     const double *u_val = nullptr;
     const int *d_con = nullptr; const double *d_coef = nullptr;                                           // diagonal singletons
-    const int *l_ptr = nullptr, *l_row = nullptr, *l_con = nullptr; const double *l_coef = nullptr;       // lowA (others)
+    // lowA: the other singleton entries, flat in (col,row) order; [l_lo, l_hi) is the part this rank evaluates
+    const int *l_ptr = nullptr, *l_row = nullptr, *l_col = nullptr, *l_con = nullptr; const double *l_coef = nullptr;
+    long long l_lo = 0, l_hi = 0;
 };
 int vc_max_ld();
 // Y[i,:] = a * sum_{e in adjU(i)} s_e X[col_e,:] + b Z[i,:],  s_e = value (objective entries, only when useC),

@@ -57,8 +57,9 @@ struct ItemList {
 //                                      whose weighted sum is still materialised on the pattern (T restricted to them);
 //   [u_mid[i], u_ptr[i+1])  tag == -1: entry of the objective C, value inline.
 // For A(UV^T) the singleton entries are needed once (lower triangle): the diagonal ones per column in d_con/d_coef
-// (read with the owner row), the others in lowA (CSC by column); residual constraints go through the generic item
-// kernel (listRes).  `order`/`order_l` list the rows by decreasing work so that the lane groups of a warp walk rows
+// (read with the owner row), the others in lowA, a flat list in (col,row) order walked entry-parallel (every entry is
+// an output of its own, so long columns -- matrix completion: 100 entries per column -- split over many lane groups);
+// residual constraints go through the generic item kernel (listRes).  `order`/`order_l` list the rows by decreasing work so that the lane groups of a warp walk rows
 // of equal length.
 struct VcLayout {
     bool on = false;
@@ -66,7 +67,7 @@ struct VcLayout {
     std::vector<int32_t> order, order_l;
     std::vector<int32_t> u_ptr, u_mid, u_col, u_tag; std::vector<double> u_val;
     std::vector<int32_t> d_con; std::vector<double> d_coef;
-    std::vector<int32_t> l_ptr, l_row, l_con; std::vector<double> l_coef;
+    std::vector<int32_t> l_ptr, l_row, l_col, l_con; std::vector<double> l_coef;
     std::vector<int32_t> Tr_ptr, Tr_con; std::vector<double> Tr_val;
     ItemList listRes;
 };
@@ -516,8 +517,10 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
         V.l_ptr.assign(n + 1, 0);
         for (const Ent &e : low) V.l_ptr[e.col + 1]++;
         for (int64_t j = 0; j < n; ++j) V.l_ptr[j + 1] += V.l_ptr[j];
-        V.l_row.resize(low.size()); V.l_con.resize(low.size()); V.l_coef.resize(low.size());
-        for (size_t q = 0; q < low.size(); ++q) { V.l_row[q] = low[q].row; V.l_con[q] = low[q].tag; V.l_coef[q] = low[q].val; }
+        V.l_row.resize(low.size()); V.l_col.resize(low.size()); V.l_con.resize(low.size()); V.l_coef.resize(low.size());
+        for (size_t q = 0; q < low.size(); ++q) {
+            V.l_row[q] = low[q].row; V.l_col[q] = low[q].col; V.l_con[q] = low[q].tag; V.l_coef[q] = low[q].val;
+        }
         // residual constraints: item list (all n_act rows, singleton rows empty), T restricted to them, and one
         // weight-dependent adjacency entry per touched pattern position
         {
@@ -604,7 +607,7 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
             for (int64_t i = 0; i < n; ++i) out[start[dmax - deg[i]]++] = (int32_t)i;
         };
         by_work(V.order, [&](int64_t i) { return V.u_ptr[i + 1] - V.u_ptr[i]; });
-        by_work(V.order_l, [&](int64_t i) { return (V.u_ptr[i + 1] - V.u_mid[i]) + 2 * (V.l_ptr[i + 1] - V.l_ptr[i]); });
+        by_work(V.order_l, [&](int64_t i) { return V.u_ptr[i + 1] - V.u_mid[i]; });     // objective entries of the row
         // the fast path pays off when singleton constraints carry most of the constraint non-zeros
         V.on = L.nnzA == 0 || 2 * V.n_single >= L.n_act;
         if (const char *e = getenv("LORADS_B200_VC")) V.on = atoi(e) != 0;

@@ -247,8 +247,12 @@ void Solver::preprocess() {
                     K.vc.d_con = K.vc_d_con.p; K.vc.d_coef = K.vc_d_coef.p;
                 }
                 if (!V.l_row.empty()) {
-                    K.vc_l_ptr.upload(V.l_ptr); K.vc_l_row.upload(V.l_row); K.vc_l_con.upload(V.l_con); K.vc_l_coef.upload(V.l_coef);
-                    K.vc.l_ptr = K.vc_l_ptr.p; K.vc.l_row = K.vc_l_row.p; K.vc.l_con = K.vc_l_con.p; K.vc.l_coef = K.vc_l_coef.p;
+                    K.vc_l_ptr.upload(V.l_ptr); K.vc_l_row.upload(V.l_row); K.vc_l_col.upload(V.l_col); K.vc_l_con.upload(V.l_con);
+                    K.vc_l_coef.upload(V.l_coef);
+                    K.vc.l_ptr = K.vc_l_ptr.p; K.vc.l_row = K.vc_l_row.p; K.vc.l_col = K.vc_l_col.p; K.vc.l_con = K.vc_l_con.p;
+                    K.vc.l_coef = K.vc_l_coef.p;
+                    K.vc.l_lo = 0; K.vc.l_hi = (long long)V.l_row.size();
+                    K.vc_l_ptr_h = V.l_ptr;
                 }
                 if (V.nnz_res > 0) {
                     K.vc_Tr_ptr.upload(V.Tr_ptr); K.vc_Tr_con.upload(V.Tr_con); K.vc_Tr_val.upload(V.Tr_val);
@@ -421,6 +425,10 @@ void Solver::setup_row_partition() {
             K.vc_order.upload(o); K.vc_order_l.upload(ol);
             K.vc.order = K.vc_order.p; K.vc.order_l = K.vc_order_l.p;
             K.vc.n = K.row_hi - K.row_lo;
+            if (!K.vc_l_ptr_h.empty()) {      // lowA is sorted by column: the owned columns are one contiguous range
+                K.vc.l_lo = K.vc_l_ptr_h[(size_t)K.row_lo];
+                K.vc.l_hi = K.vc_l_ptr_h[(size_t)K.row_hi];
+            }
         }
         row0 += K.n;
     }
@@ -807,14 +815,19 @@ void Solver::lbfgs_direction(long long counter) {
     }
     const int K = (int)((counter <= L - 1) ? counter : L);
     auto node = [&](int i) { return ((lb_head - i) % L + L) % L; };   // i = 1 newest ... K oldest used
-    launch_dot(ctx, vn, sv(node(1)), Gv, S.p, SL_T0);
-    if (world > 1) allreduce(S.p + SL_T0, 1);
+    // <s_newest, G>: the pass that completed the newest pair (enqueue_back) already produced it next to <y,s>
+    int t0_slot = SL_T0;
+    if (vf_valid) t0_slot = SL_VF_D + 4;
+    else {
+        launch_dot(ctx, vn, sv(node(1)), Gv, S.p, SL_T0);
+        if (world > 1) allreduce(S.p + SL_T0, 1);
+    }
     for (int i = 1; i <= K; ++i) {
         const int nd = node(i);
         const double *zvec = (i < K) ? sv(node(i + 1)) : yv(nd);
         // q = q - alpha*y, alpha = beta*<s,q>; -alpha is remembered for the second loop
         launch_axpby_dot(ctx, vn, q, coef_const(1.0), (i == 1) ? Gv : q,
-                         coef_prod(SL_BETA0 + nd, SL_T0, -1.0, SL_NEGALPHA0 + nd), yv(nd), zvec, S.p, SL_T0, false);
+                         coef_prod(SL_BETA0 + nd, (i == 1) ? t0_slot : SL_T0, -1.0, SL_NEGALPHA0 + nd), yv(nd), zvec, S.p, SL_T0, false);
         if (world > 1) allreduce(S.p + SL_T0, 1);
     }
     for (int i = K; i >= 1; --i) {
@@ -1061,12 +1074,25 @@ void Solver::enqueue_back(double rho, double tau, bool front_follows) {
         }
         vf_valid = true;
     } else {
-        if (world > 1) allreduce(S.p + kNumSlots, 2 * (nCones + 1));
-        launch_axpby_dot(ctx, vn, lb_y[head].p + vo, coef_const(1.0), lb_y[head].p + vo, coef_const(1.0), G.p + vo,
-                         lb_s[head].p + vo, S.p, SL_BETA0 + head, world == 1);
-        if (world > 1) {
-            allreduce(S.p + SL_BETA0 + head, 1);
-            launch_recip(ctx, S.p, SL_BETA0 + head);
+        if ((vn & 1) == 0) {
+            // y += G_new, beta = 1/<y,s> and, from the same pass, <s,G_new> for the first step of the next two-loop
+            // recursion (the pair kernel works on double2: an odd length -- LP block -- takes the plain path below)
+            launch_lbfgs_pair(ctx, vn, true, lb_y[head].p + vo, G.p + vo, lb_s[head].p + vo, nullptr, nullptr, S.p, SL_VF_D,
+                              SL_BETA0 + head, SL_VF_YY + head, world == 1);
+            if (world > 1) {
+                allreduce(S.p + SL_VF_D, (kNumSlots - SL_VF_D) + 2 * (nCones + 1));
+                launch_lbfgs_pair_finalize(ctx, S.p, SL_VF_D, SL_BETA0 + head, SL_VF_YY + head);
+            }
+            vf_valid = true;
+        } else {
+            if (world > 1) allreduce(S.p + kNumSlots, 2 * (nCones + 1));
+            launch_axpby_dot(ctx, vn, lb_y[head].p + vo, coef_const(1.0), lb_y[head].p + vo, coef_const(1.0), G.p + vo,
+                             lb_s[head].p + vo, S.p, SL_BETA0 + head, world == 1);
+            if (world > 1) {
+                allreduce(S.p + SL_BETA0 + head, 1);
+                launch_recip(ctx, S.p, SL_BETA0 + head);
+            }
+            vf_valid = false;
         }
     }
     lb_head = (head + 1) % lbfgs_len;

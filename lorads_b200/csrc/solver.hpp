@@ -64,7 +64,7 @@ struct ConeDev {
     long long vc_nnz_res = 0;                       // non-zeros of the residual (multi-entry) constraints
     long long nnzC_adj = 0;                         // objective entries of the vertex-centric adjacency
     VcDev vc;
-    DBuf<int> vc_order, vc_order_l, vc_u_ptr, vc_u_mid, vc_u_col, vc_u_tag, vc_d_con, vc_l_ptr, vc_l_row, vc_l_con, vc_Tr_ptr,
+    DBuf<int> vc_order, vc_order_l, vc_u_ptr, vc_u_mid, vc_u_col, vc_u_tag, vc_d_con, vc_l_ptr, vc_l_row, vc_l_col, vc_l_con, vc_Tr_ptr,
         vc_Tr_con;
     DBuf<double> vc_u_val, vc_d_coef, vc_l_coef, vc_Tr_val;
     ItemListBufs vc_listRes;
@@ -72,7 +72,7 @@ struct ConeDev {
     // rank that evaluates the unsplittable parts (residual item list, rank-one objective term, dense / generic cones)
     long long row_lo = 0, row_hi = 0;
     bool lead = true;
-    std::vector<int32_t> vc_order_h, vc_order_l_h, row_weight_h;   // host copies, kept for the partition
+    std::vector<int32_t> vc_order_h, vc_order_l_h, row_weight_h, vc_l_ptr_h;   // host copies, kept for the partition
     const double *pw = nullptr;                     // weights of the pending (C + A^*(w)) product (set by cone_wsum)
     bool pw_compact = false;
     DBuf<double> cv;                                // constrVal of the cone (compact, n_act + 1)

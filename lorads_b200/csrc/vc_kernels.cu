@@ -234,10 +234,9 @@ __global__ void __launch_bounds__(kBlock, MINB)
     if (L.valid)
         for (long long slot = wg * L.RW + L.grp; slot < V.n; slot += nw * L.RW) {
             const int j = V.order_l[slot];
-            const int la = V.l_ptr ? V.l_ptr[j] : 0, lb = V.l_ptr ? V.l_ptr[j + 1] : 0;
             const int ca = with_obj ? V.u_mid[j] : 0, cb = with_obj ? V.u_ptr[j + 1] : 0;
             const int dc = V.d_con ? V.d_con[j] : -1;
-            if (la == lb && ca == cb && dc < 0) continue;
+            if (ca == cb && dc < 0) continue;
             d4 uj[NP], wj[NP];
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
@@ -276,68 +275,6 @@ __global__ void __launch_bounds__(kBlock, MINB)
                     if constexpr (TRI) out3[dc] = cf * a4;
                 }
             }
-            // singleton constraints of column j (lower triangle): full dot products, one entry at a time per group
-            for (int e = la; e < lb; e += L.G) {
-                constexpr int UL = UN > 2 ? 2 : UN;            // entries in flight (two factors per entry)
-                const bool ok = e + L.gl < lb;
-                const int ic = ok ? V.l_row[e + L.gl] : 0;
-                const int cc = ok ? V.l_con[e + L.gl] : 0;
-                const double fc = ok ? V.l_coef[e + L.gl] : 0.0;
-                const int cnt = min(L.G, lb - e);
-#pragma unroll 1
-                for (int h = 0; h < cnt; h += UL) {
-                    d4 ui[UL][NP], wi[UL][NP];
-                    int irow[UL], con[UL];
-                    double cf[UL];
-                    bool live[UL];
-#pragma unroll
-                    for (int u = 0; u < UL; ++u) {
-                        const int hh = min(h + u, L.G - 1);
-                        live[u] = (h + u) < cnt;
-                        irow[u] = __shfl_sync(L.gmask, ic, L.base + hh);
-                        con[u] = __shfl_sync(L.gmask, cc, L.base + hh);
-                        cf[u] = __shfl_sync(L.gmask, fc, L.base + hh);
-                        const bool far = live[u] && irow[u] != j;
-#pragma unroll
-                        for (int q = 0; q < NP; ++q) {
-                            const int col = 4 * L.gl + 32 * q;
-                            const bool in = far && col < ld;
-                            ui[u][q] = in ? ld4(U + (size_t)irow[u] * ld + col) : uj[q];
-                            if constexpr (!SAME) wi[u][q] = in ? ld4(W + (size_t)irow[u] * ld + col) : wj[q];
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < UL; ++u) {
-                        if (!live[u]) continue;                    // group-uniform
-                        const bool diag = irow[u] == j;
-                        double a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
-#pragma unroll
-                        for (int q = 0; q < NP; ++q) {
-                            if constexpr (SAME) {
-                                a1 += dot4(ui[u][q], uj[q]);
-                            } else {
-                                a1 += dot4(ui[u][q], wj[q]);                           // U_i . W_j
-                                a2 += dot4(uj[q], wi[u][q]);                           // U_j . W_i
-                                if constexpr (DUAL) a3 += dot4(wi[u][q], wj[q]);       // W_i . W_j
-                                if constexpr (TRI) a4 += dot4(ui[u][q], uj[q]);        // U_i . U_j
-                            }
-                        }
-                        a1 = group_total(L, a1);
-                        if constexpr (!SAME) a2 = group_total(L, a2);
-                        if constexpr (DUAL) a3 = group_total(L, a3);
-                        if constexpr (TRI) a4 = group_total(L, a4);
-                        if (L.gl == 0) {
-                            if constexpr (SAME) {
-                                out1[con[u]] = s1 * cf[u] * a1;
-                            } else {
-                                out1[con[u]] = s1 * cf[u] * (diag ? a1 : (0.5 * a1 + 0.5 * a2));
-                                if constexpr (DUAL) out2[con[u]] = s2 * cf[u] * a3;
-                                if constexpr (TRI) out3[con[u]] = cf[u] * a4;
-                            }
-                        }
-                    }
-                }
-            }
         }
     if (with_obj) {
         double v[2] = {p1, p2};
@@ -348,6 +285,78 @@ __global__ void __launch_bounds__(kBlock, MINB)
             if constexpr (DUAL) {
                 out2[V.obj_row] = o2;
                 if (obj2) *obj2 += o2;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+//  off-diagonal singleton constraints: one output per lower-triangular entry, entry-parallel
+// ---------------------------------------------------------------------------------------------------------------
+// A lane group walks CH consecutive entries of lowA (sorted by column, so the column-side rows U_j, W_j stay in
+// registers while the column repeats), gathers the row-side rows, takes the full dot products and writes the value to
+// the entry's constraint row -- every singleton row has exactly one writer, no reduction across entries.
+template <int MODE, int NP>
+__global__ void __launch_bounds__(kBlock, 4)
+    vc_low_kernel(VcDev V, int ld, int G, const double *__restrict__ U, const double *__restrict__ W, double s1, double s2,
+                  double *__restrict__ out1, double *__restrict__ out2, double *__restrict__ out3) {
+    constexpr bool SAME = (MODE == AUV_SAME);
+    constexpr bool TRI = (MODE == AUV_TRI);
+    constexpr bool DUAL = (MODE == AUV_DUAL) || TRI;
+    constexpr int CH = 8;
+    const Lanes L(G);
+    if (!L.valid) return;
+    const long long groups = (long long)gridDim.x * (kBlock / 32) * L.RW;
+    const long long g0 = ((long long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) * L.RW + L.grp;
+    for (long long base_e = V.l_lo + g0 * CH; base_e < V.l_hi; base_e += groups * CH) {
+        const int cnt = (int)min((long long)CH, V.l_hi - base_e);
+        int pj = -1;
+        d4 uj[NP], wj[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) uj[q] = wj[q] = kZero4;
+#pragma unroll 1
+        for (int t = 0; t < cnt; ++t) {
+            // one entry per trip (two per trip measured slower: 305 vs 278 us on the 2e6 entries of matrix completion)
+            const long long e = base_e + t;
+            const int i = V.l_row[e], j = V.l_col[e], con = V.l_con[e];
+            const double cf = V.l_coef[e];
+            d4 ui[NP], wi[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int col = 4 * L.gl + 32 * q;
+                const bool in = col < ld;
+                ui[q] = in ? ld4(U + (size_t)i * ld + col) : kZero4;
+                if constexpr (!SAME) wi[q] = in ? ld4(W + (size_t)i * ld + col) : kZero4;
+                if (j != pj) {
+                    uj[q] = in ? ld4(U + (size_t)j * ld + col) : kZero4;
+                    if constexpr (!SAME) wj[q] = in ? ld4(W + (size_t)j * ld + col) : kZero4;
+                }
+            }
+            pj = j;
+            double a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                if constexpr (SAME) {
+                    a1 += dot4(ui[q], uj[q]);
+                } else {
+                    a1 += dot4(ui[q], wj[q]);                           // U_i . W_j
+                    a2 += dot4(uj[q], wi[q]);                           // U_j . W_i
+                    if constexpr (DUAL) a3 += dot4(wi[q], wj[q]);       // W_i . W_j
+                    if constexpr (TRI) a4 += dot4(ui[q], uj[q]);        // U_i . U_j
+                }
+            }
+            a1 = group_total(L, a1);
+            if constexpr (!SAME) a2 = group_total(L, a2);
+            if constexpr (DUAL) a3 = group_total(L, a3);
+            if constexpr (TRI) a4 = group_total(L, a4);
+            if (L.gl == 0) {
+                if constexpr (SAME) {
+                    out1[con] = s1 * cf * a1;
+                } else {
+                    out1[con] = s1 * cf * ((i == j) ? a1 : (0.5 * a1 + 0.5 * a2));
+                    if constexpr (DUAL) out2[con] = s2 * cf * a3;
+                    if constexpr (TRI) out3[con] = cf * a4;
+                }
             }
         }
     }
@@ -386,6 +395,30 @@ void auv_launch(Ctx &c, const VcDev &V, int ld, bool with_obj, const double *U, 
     vc_auv_kernel<MODE, NP, UN, MINB, PL><<<vc_grid(c, V.n, G, MINB), kBlock, 0, c.stream>>>(V, ld, G, with_obj, U, W, s1, s2, o1, o2, o3, obj1, obj2, c.rs);
 }
 
+template <int MODE, int NP>
+void low_launch(Ctx &c, const VcDev &V, int ld, const double *U, const double *W, double s1, double s2, double *o1, double *o2,
+                double *o3) {
+    const int G = vc_lanes(ld);
+    const long long groups_needed = (V.l_hi - V.l_lo + 7) / 8;
+    const long long per_block = (long long)(32 / G) * (kBlock / 32);
+    long long g = (groups_needed + per_block - 1) / per_block;
+    g = std::min<long long>(g, (long long)c.num_sms * 8);
+    vc_low_kernel<MODE, NP><<<(int)std::max<long long>(g, 1), kBlock, 0, c.stream>>>(V, ld, G, U, W, s1, s2, o1, o2, o3);
+}
+
+template <int MODE>
+void low_dispatch(Ctx &c, int np, const VcDev &V, int ld, const double *U, const double *W, double s1, double s2, double *o1,
+                  double *o2, double *o3) {
+    switch (np) {
+    case 1: low_launch<MODE, 1>(c, V, ld, U, W, s1, s2, o1, o2, o3); break;
+    case 2: low_launch<MODE, 2>(c, V, ld, U, W, s1, s2, o1, o2, o3); break;
+    case 3: low_launch<MODE, 3>(c, V, ld, U, W, s1, s2, o1, o2, o3); break;
+    case 4: low_launch<MODE, 4>(c, V, ld, U, W, s1, s2, o1, o2, o3); break;
+    case 6: low_launch<MODE, 6>(c, V, ld, U, W, s1, s2, o1, o2, o3); break;
+    default: low_launch<MODE, 8>(c, V, ld, U, W, s1, s2, o1, o2, o3); break;
+    }
+}
+
 template <int MODE>
 void auv_dispatch(Ctx &c, int np, int un, const VcDev &V, int ld, bool with_obj, const double *U, const double *W, double s1,
                   double s2, double *o1, double *o2, double *o3, double *obj1, double *obj2) {
@@ -415,10 +448,14 @@ void auv_dispatch(Ctx &c, int np, int un, const VcDev &V, int ld, bool with_obj,
 
 int vc_max_ld() { return 256; }
 
-// loads in flight per lane: one while the gathered factor fits comfortably in L2, four beyond (LORADS_B200_VC_UN overrides)
+// loads in flight per lane: one while the gathered factor fits comfortably in L2 AND there are enough rows to fill the
+// machine with warps (one gather per lane, many resident warps measured fastest there); four when the factor spills
+// out of L2 (DRAM latency) or when the block is so small that a row group per row leaves most warp slots empty
+// (n = 5000: 1000 warps on 148 SMs) and the parallelism has to come from inside the row.  LORADS_B200_VC_UN overrides.
 static int vc_unroll(long long n, int ld) {
     static const int forced = getenv("LORADS_B200_VC_UN") ? atoi(getenv("LORADS_B200_VC_UN")) : 0;
     if (forced > 0) return forced;
+    if (n < 30000) return 4;
     return ((double)n * ld * 8.0 > 48e6) ? 4 : 1;
 }
 
@@ -457,15 +494,31 @@ void launch_vc_auv(Ctx &c, AuvMode mode, const VcDev &V, int ld, bool with_obj, 
     const int np = vc_passes(ld);
     if (np == 0) throw std::runtime_error("rank above 256 is not supported by the A(UV^T) kernel");
     const int un = vc_unroll(V.n, ld);
-    switch (mode) {
-    case AUV_SAME: auv_dispatch<AUV_SAME>(c, np, un, V, ld, with_obj, U, W, s1, s2, out1, out2, out3, obj1, obj2); break;
-    case AUV_PAIR: auv_dispatch<AUV_PAIR>(c, np, un, V, ld, with_obj, U, W, s1, s2, out1, out2, out3, obj1, obj2); break;
-    case AUV_DUAL: auv_dispatch<AUV_DUAL>(c, np, un, V, ld, with_obj, U, W, s1, s2, out1, out2, out3, obj1, obj2); break;
-    case AUV_TRI: auv_dispatch<AUV_TRI>(c, np, un, V, ld, with_obj, U, W, s1, s2, out1, out2, out3, obj1, obj2); break;
-    default: throw std::invalid_argument("vertex-centric A(UV^T): unsupported mode");
+    // row-centric part: objective row and the diagonal singleton constraints (skipped when the cone has neither)
+    if (V.n > 0 && (with_obj || V.d_con)) {
+        switch (mode) {
+        case AUV_SAME: auv_dispatch<AUV_SAME>(c, np, un, V, ld, with_obj, U, W, s1, s2, out1, out2, out3, obj1, obj2); break;
+        case AUV_PAIR: auv_dispatch<AUV_PAIR>(c, np, un, V, ld, with_obj, U, W, s1, s2, out1, out2, out3, obj1, obj2); break;
+        case AUV_DUAL: auv_dispatch<AUV_DUAL>(c, np, un, V, ld, with_obj, U, W, s1, s2, out1, out2, out3, obj1, obj2); break;
+        case AUV_TRI: auv_dispatch<AUV_TRI>(c, np, un, V, ld, with_obj, U, W, s1, s2, out1, out2, out3, obj1, obj2); break;
+        default: throw std::invalid_argument("vertex-centric A(UV^T): unsupported mode");
+        }
+        c.launches++;
+        LB2_CUDA(cudaGetLastError());
     }
-    c.launches++;
-    LB2_CUDA(cudaGetLastError());
+    // entry-parallel part: the off-diagonal singleton constraints
+    if (V.l_hi > V.l_lo) {
+        switch (mode) {
+        case AUV_SAME: low_dispatch<AUV_SAME>(c, np, V, ld, U, W, s1, s2, out1, out2, out3); break;
+        case AUV_PAIR: low_dispatch<AUV_PAIR>(c, np, V, ld, U, W, s1, s2, out1, out2, out3); break;
+        case AUV_DUAL: low_dispatch<AUV_DUAL>(c, np, V, ld, U, W, s1, s2, out1, out2, out3); break;
+        case AUV_TRI: low_dispatch<AUV_TRI>(c, np, V, ld, U, W, s1, s2, out1, out2, out3); break;
+        default: throw std::invalid_argument("vertex-centric A(UV^T): unsupported mode");
+        }
+        c.launches++;
+        LB2_CUDA(cudaGetLastError());
+    }
+    return;
 }
 
 }  // namespace lb2

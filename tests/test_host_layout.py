@@ -43,6 +43,7 @@ def vc_values(lay, U, V):
         out[d[has]] = lay["vc_d_coef"][has] * np.einsum("ij,ij->i", U[has], V[has])
     if lay["vc_l_row"].size:
         j = np.repeat(np.arange(n), np.diff(lay["vc_l_ptr"]))
+        assert np.array_equal(j, lay["vc_l_col"])            # flat list in (col,row) order + its column pointers
         i = lay["vc_l_row"].astype(np.int64)
         z = 0.5 * (np.einsum("ij,ij->i", U[i], V[j]) + np.einsum("ij,ij->i", U[j], V[i]))
         assert np.all(out[lay["vc_l_con"]] == 0.0)
