@@ -256,9 +256,8 @@ int lb2_comm_init(lb2_solver *s, const void *id128, int rank, int world) {
     int rc = g_nccl.init_rank(&s->impl.nccl, world, id, rank);
     if (rc != 0) throw CudaError("ncclCommInitRank failed");
     s->impl.world = world; s->impl.myrank = rank;
-    // sharded runs use the Gram-table L-BFGS: one all-reduce of 8 scalars per iteration instead of five
-    // sequential scalar all-reduces (LORADS_B200_EXACT_LBFGS=1 keeps the two-loop recursion)
-    if (getenv("LORADS_B200_EXACT_LBFGS") == nullptr) s->impl.vf_lbfgs = true;
+    // the Gram-table L-BFGS (default, solver.cu Solver::create) needs one all-reduce of 8 scalars per iteration instead
+    // of five sequential scalar all-reduces
     // Two schemes (solver.hpp): factor columns (default) or row slabs / cone blocks (LORADS_B200_SHARD=rows, the scheme
     // north_star names).  Both are built, tested against the oracle on two GPUs and measured at 2 / 4 / 8 GPUs; on the
     // BASELINE workloads (random sparse graphs: every rank needs every row of the gathered factor) the row scheme pays

@@ -139,7 +139,9 @@ struct Solver {
     DBuf<int> aug_pos;            // scatter list of the diagonal entries of freshly appended factor columns
     DBuf<double> aug_val;
     int lbfgs_len = 2, lb_head = 0;
-    bool vf_lbfgs = false;     // vector-free (Gram) L-BFGS for history length 2
+    bool vf_lbfgs = true;      // vector-free (Gram-table) L-BFGS for history length 2
+    // the pair kernel works on double2: an odd vector length (LP block) and longer histories use the plain recursion
+    bool use_vf() const { return vf_lbfgs && lbfgs_len == 2 && (vn & 1) == 0; }
     bool vf_valid = false;     // the G-dots in the Gram table belong to the current gradient
     // scalars
     DBuf<double> S;

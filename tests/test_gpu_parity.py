@@ -104,7 +104,11 @@ def test_golden_whole_solve(golden):
         assert abs(res["pObj"] - ref["pobj"]) <= 1e-6 * scale and abs(res["dObj"] - ref["dobj"]) <= 1e-6 * scale
         assert abs(res["dInfeasL1"] - ref["dinf"]) <= 1e-6
     else:
-        assert abs(res["pObj"] - ref["pobj"]) <= 3e-5 * scale and abs(res["dObj"] - ref["dobj"]) <= 3e-5 * scale
+        # long solves: tests/test_reference_sensitivity.py shows the reference moving by up to 1.1e-5 against itself; each
+        # run stops anywhere inside its own relative gap, so the dual objectives may differ by the two gaps on top
+        assert abs(res["pObj"] - ref["pobj"]) <= 3e-5 * scale
+        gap_room = (res["pdGap"] + ref["gap"]) * (1 + abs(ref["pobj"]) + abs(ref["dobj"]))
+        assert abs(res["dObj"] - ref["dobj"]) <= 3e-5 * scale + gap_room
 
 
 # ---------------------------------------------------------------------------------------------------
