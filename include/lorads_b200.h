@@ -238,9 +238,10 @@ int lb2_alm_run_host(lb2_solver *s, const double *R_in, const double *lambda_in,
 /* Times `reps` back-to-back launches of one hot kernel with CUDA events on the solver's stream (cone 0).
  * which: 0 A(UV^T) dual pass (R,D)+(D,D) with objective, 1 A(RR^T) constraints only, 2 S = C + A^*(w),
  *        3 Y = 2 S R (+ sum Y.Y), 4 one fused BLAS-1 pass (axpby + dot) over the factor vector,
+ *        99 a one-thread kernel (what the timing method itself costs per launch),
  *        10 / 11 / 12 the collectives of a sharded step (all-gather of a factor vector, all-reduce of the three m-vectors of
  *        the fused A() pass, all-reduce of the scalar table); every rank has to make the same call.
- * flush_l2 != 0: a buffer three times the size of the L2 is overwritten before every launch and each launch is timed
+ * flush_l2 != 0: a buffer three times the size of the L2 is read before every launch and each launch is timed
  * on its own (cold-cache figure); 0: back-to-back launches.  ms = average milliseconds per launch. */
 int lb2_bench_kernel(lb2_solver *s, int which, lb2_int reps, int flush_l2, double *ms);
 

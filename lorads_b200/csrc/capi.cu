@@ -608,6 +608,8 @@ int lb2_bench_kernel(lb2_solver *s, int which, lb2_int reps, int flush_l2, doubl
         case 4: launch_axpby_dot(S.ctx, S.N, S.Dtemp.p, coef_const(1.0), S.G.p, coef_const(-0.5), S.V.p, S.R.p, S.S.p, SL_T1, false); break;
         // the collectives of a sharded step (no-ops on one GPU): all-gather of the direction, all-reduce of the
         // three m-vectors of the fused A() pass, all-reduce of the dot table + gradient sums
+        // calibration: a one-thread kernel, to measure what the timing method itself costs per launch
+        case 99: launch_recip(S.ctx, S.S.p, SL_T1); break;
         case 10: S.allgather_owned(S.Dtemp.p); break;
         case 11: S.allreduce(S.q12.p, (long long)(S.q3.p - S.q1.p) + S.m + 1); break;
         case 12: S.allreduce(S.S.p + SL_VF_D, (kNumSlots - SL_VF_D) + 2 * (S.nCones + 1)); break;
@@ -617,11 +619,12 @@ int lb2_bench_kernel(lb2_solver *s, int which, lb2_int reps, int flush_l2, doubl
     for (int w = 0; w < 3; ++w) once();
     double total = 0.0;
     if (flush_l2) {
-        // every launch starts from a cold L2: a 384 MB buffer (3x the 126 MB L2) is overwritten before each timed launch
+        // every launch starts from a cold L2: a 384 MB buffer (3x the 126 MB L2) is READ before each timed launch (clean
+        // lines only -- see launch_l2_flush_read)
         const size_t fl = (size_t)48 << 20;
-        if (S.flush_buf.n < fl) S.flush_buf.alloc(fl, false);
+        if (S.flush_buf.n < fl) S.flush_buf.alloc(fl, true);
         for (lb2_int k = 0; k < reps; ++k) {
-            LB2_CUDA(cudaMemsetAsync(S.flush_buf.p, (int)(k & 1), fl * sizeof(double), S.ctx.stream));
+            launch_l2_flush_read(S.ctx, S.flush_buf.p, fl, S.S.p + SL_T1);
             LB2_CUDA(cudaEventRecord(e0, S.ctx.stream));
             once();
             LB2_CUDA(cudaEventRecord(e1, S.ctx.stream));

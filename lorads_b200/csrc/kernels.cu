@@ -1139,9 +1139,12 @@ __global__ void __launch_bounds__(kBlock) colsum_kernel(long long n, int ld, con
 
 void launch_colsum(Ctx &c, long long n, int ld, const double *X, double *out, double *scratch) {
     if (ld > 256) throw std::runtime_error("rank above 256 is not supported by the column-sum kernel yet");
-    long long blocks = (n + 7) / 8;
+    // 64 rows per CTA at least: the last CTA adds one partial per CTA and column serially, which dominated on small
+    // blocks (n = 5000: 592 partials per column for 100 KB of data)
+    long long blocks = (n + 63) / 64;
     const long long cap = (long long)c.num_sms * 4;
     if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
     colsum_kernel<<<(unsigned)blocks, kBlock, 0, c.stream>>>(n, ld, X, out, scratch, c.ticket);
     LB2_LAUNCH_CHECK(c);
 }

@@ -240,6 +240,8 @@ void launch_relayout(Ctx &c, long long n, int r_old, int ld_old, int ld_new, con
 // row-major n x ld device layout; padding columns are zero-filled on the way in.
 void launch_cm_to_rm(Ctx &c, long long n, int r_own, int ld, const double *src, double *dst);
 void launch_rm_to_cm(Ctx &c, long long n, int r_own, int ld, const double *src, double *dst);
+// cold-cache timing helper: reads `n` doubles (n * 8 bytes >> L2) so that the L2 holds only clean lines of `buf`
+void launch_l2_flush_read(Ctx &c, const double *buf, size_t n, double *sink);
 // val[e] *= f for the objective entries (tag == -1) of a vertex-centric adjacency
 void launch_scale_tagged(Ctx &c, long long n, const int *tag, double *val, double f);
 // R += (*tau_p) * D with the same fma as launch_alm_step (rows not owned under row sharding)

@@ -428,6 +428,7 @@ void auv_dispatch(Ctx &c, int np, int un, const VcDev &V, int ld, bool with_obj,
         static const int minb = getenv("LORADS_B200_VC_MINB_AUV") ? atoi(getenv("LORADS_B200_VC_MINB_AUV")) : 0;
         if (ld <= 4) auv_launch<MODE, 1, 1, 3, 4>(c, V, ld, with_obj, U, W, s1, s2, o1, o2, o3, obj1, obj2);
         else if (ld <= 8) auv_launch<MODE, 1, 1, 3, 2>(c, V, ld, with_obj, U, W, s1, s2, o1, o2, o3, obj1, obj2);
+        else if (un >= 4 && minb == 4) auv_launch<MODE, 1, 4, 4>(c, V, ld, with_obj, U, W, s1, s2, o1, o2, o3, obj1, obj2);
         else if (un >= 4) LB2_VC_AUV(1, 4);
         else if (un == 2) LB2_VC_AUV(1, 2);
         else if (minb == 5) auv_launch<MODE, 1, 1, 5>(c, V, ld, with_obj, U, W, s1, s2, o1, o2, o3, obj1, obj2);
@@ -448,15 +449,15 @@ void auv_dispatch(Ctx &c, int np, int un, const VcDev &V, int ld, bool with_obj,
 
 int vc_max_ld() { return 256; }
 
-// loads in flight per lane: one while the gathered factor fits comfortably in L2 AND there are enough rows to fill the
-// machine with warps (one gather per lane, many resident warps measured fastest there); four when the factor spills
-// out of L2 (DRAM latency) or when the block is so small that a row group per row leaves most warp slots empty
+// loads in flight per lane: one gather per lane and as many resident warps as fit measured fastest from n = 1e5
+// (L2 resident) to n = 1e6 (SpMM 624 vs 752 us with four in flight: the extra registers cost more warps than the
+// unrolling gains); four only when the block is so small that a row group per row leaves most warp slots empty
 // (n = 5000: 1000 warps on 148 SMs) and the parallelism has to come from inside the row.  LORADS_B200_VC_UN overrides.
 static int vc_unroll(long long n, int ld) {
+    (void)ld;
     static const int forced = getenv("LORADS_B200_VC_UN") ? atoi(getenv("LORADS_B200_VC_UN")) : 0;
     if (forced > 0) return forced;
-    if (n < 30000) return 4;
-    return ((double)n * ld * 8.0 > 48e6) ? 4 : 1;
+    return n < 30000 ? 4 : 1;
 }
 
 void launch_vc_spmm(Ctx &c, const VcDev &V, int ld, bool useC, const double *w, const int *wmap, const double *Sres,
@@ -471,6 +472,7 @@ void launch_vc_spmm(Ctx &c, const VcDev &V, int ld, bool useC, const double *w, 
         static const int minb = getenv("LORADS_B200_VC_MINB") ? atoi(getenv("LORADS_B200_VC_MINB")) : 0;
         if (ld <= 4) spmm_launch<1, 1, 4, 4>(c, V, ld, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, red, cs, c1);
         else if (ld <= 8) spmm_launch<1, 1, 4, 2>(c, V, ld, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, red, cs, c1);
+        else if (un >= 4 && minb == 4) spmm_launch<1, 4, 4>(c, V, ld, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, red, cs, c1);
         else if (un >= 4) LB2_VC_SPMM(1, 4);
         else if (un == 2) LB2_VC_SPMM(1, 2);
         else if (minb == 6) spmm_launch<1, 1, 6>(c, V, ld, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, red, cs, c1);
