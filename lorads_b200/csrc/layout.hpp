@@ -18,6 +18,7 @@
 #include <cstdint>
 #include <numeric>
 #include <stdexcept>
+#include <string>
 #include <thread>
 #include <chrono>
 #include <cstdio>
@@ -608,6 +609,25 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
         };
         by_work(V.order, [&](int64_t i) { return V.u_ptr[i + 1] - V.u_ptr[i]; });
         by_work(V.order_l, [&](int64_t i) { return V.u_ptr[i + 1] - V.u_mid[i]; });     // objective entries of the row
+        // Bounds of everything the gather kernels index with (compute-sanitizer is not available on the target pool, so the
+        // layout is proved in range here, once, on the host): neighbours and rows inside the block, constraint tags
+        // inside the compact constraint range, residual tags inside the pattern, monotone pointers.
+        {
+            auto bad = [](const char *what) { throw std::logic_error(std::string("vertex-centric layout out of range: ") + what); };
+            const int64_t nu = (int64_t)V.u_col.size();
+            if (V.u_ptr[0] != 0 || V.u_ptr[n] != nu) bad("adjacency pointers");
+            for (int64_t i = 0; i < n; ++i)
+                if (V.u_ptr[i] > V.u_mid[i] || V.u_mid[i] > V.u_ptr[i + 1]) bad("row split");
+            for (int64_t e = 0; e < nu; ++e) {
+                if (V.u_col[e] < 0 || V.u_col[e] >= n) bad("neighbour index");
+                const int32_t t = V.u_tag[e];
+                if (t >= L.n_act || (t <= -2 && -2 - (int64_t)t >= np)) bad("entry tag");
+            }
+            for (size_t q = 0; q < V.l_row.size(); ++q)
+                if (V.l_row[q] < V.l_col[q] || V.l_row[q] >= n || V.l_col[q] < 0 || V.l_con[q] < 0 || V.l_con[q] >= L.n_act) bad("lower-triangular entry");
+            for (int64_t i = 0; i < n; ++i)
+                if (V.d_con[i] >= L.n_act || V.order[i] < 0 || V.order[i] >= n || V.order_l[i] < 0 || V.order_l[i] >= n) bad("row table");
+        }
         // the fast path pays off when singleton constraints carry most of the constraint non-zeros
         V.on = L.nnzA == 0 || 2 * V.n_single >= L.n_act;
         if (const char *e = getenv("LORADS_B200_VC")) V.on = atoi(e) != 0;
