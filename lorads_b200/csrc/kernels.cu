@@ -1194,8 +1194,9 @@ void launch_alm_step(Ctx &c, long long n, const double *tau_p, const double *G, 
 __global__ void __launch_bounds__(kBlock) cg_update_kernel(long long n, double *__restrict__ x, double *__restrict__ r,
                                                            const double *__restrict__ p, const double *__restrict__ Q,
                                                            double *S, int slot_num, int slot_den, int slot_rr,
-                                                           ReduceScratch rs) {
-    const double alpha = S[slot_num] / S[slot_den];
+                                                           int slot_beta, ReduceScratch rs) {
+    const double rr_old = S[slot_num];
+    const double alpha = rr_old / S[slot_den];
     double acc = 0.0;
     for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n; q += (long long)gridDim.x * kBlock) {
         x[q] = fma(alpha, p[q], x[q]);
@@ -1204,12 +1205,15 @@ __global__ void __launch_bounds__(kBlock) cg_update_kernel(long long n, double *
         acc = fma(rv, rv, acc);
     }
     double v[1] = {acc};
-    if (grid_reduce<1>(v, rs) && threadIdx.x == 0) S[slot_rr] = v[0];
+    if (grid_reduce<1>(v, rs) && threadIdx.x == 0) {
+        S[slot_rr] = v[0];
+        if (slot_beta >= 0) S[slot_beta] = v[0] / rr_old;      // beta of the next direction (lorads_cgs.c:226-228)
+    }
 }
 
 void launch_cg_update(Ctx &c, long long n, double *x, double *r, const double *p, const double *Q, double *S,
-                      int slot_num, int slot_den, int slot_rr) {
-    cg_update_kernel<<<grid_for(n, 8, c), kBlock, 0, c.stream>>>(n, x, r, p, Q, S, slot_num, slot_den, slot_rr, c.rs);
+                      int slot_num, int slot_den, int slot_rr, int slot_beta) {
+    cg_update_kernel<<<grid_for(n, 8, c), kBlock, 0, c.stream>>>(n, x, r, p, Q, S, slot_num, slot_den, slot_rr, slot_beta, c.rs);
     LB2_LAUNCH_CHECK(c);
 }
 

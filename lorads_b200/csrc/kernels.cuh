@@ -161,8 +161,9 @@ void launch_neg_if_nonneg(Ctx &c, long long n, double *D, const double *G, const
 // tau is read from *tau_p (a device scalar slot) so that the launch can live in a replayed CUDA graph
 void launch_alm_step(Ctx &c, long long n, const double *tau_p, const double *G, const double *D, double *R, double *y, double *s);
 // x += alpha*p ; r -= alpha*Q ; S[slot_rr] = sum r*r  with alpha = S[slot_num]/S[slot_den]  (lorads_cgs.c:183-189)
+// slot_beta >= 0: S[slot_beta] = (new sum r*r) / S[slot_num], the beta of the next search direction
 void launch_cg_update(Ctx &c, long long n, double *x, double *r, const double *p, const double *Q, double *S,
-                      int slot_num, int slot_den, int slot_rr);
+                      int slot_num, int slot_den, int slot_rr, int slot_beta = -1);
 
 // ---- vector-free L-BFGS (history length 2): all inner products of the two-loop recursion come from a small Gram
 // table, so the recursion needs two passes over the factor vectors instead of five, and one reduction.

@@ -50,6 +50,8 @@ Solver::~Solver() {
     drop_graphs();
     if (push_host) cudaFreeHost(push_host);
     if (S_host) cudaFreeHost(S_host);
+    if (side_event) cudaEventDestroy(side_event);
+    if (side_stream) cudaStreamDestroy(side_stream);
     if (ctx.stream) cudaStreamDestroy(ctx.stream);
 }
 
@@ -594,6 +596,16 @@ void Solver::get_factor(char which, long long c, double *colMajor) const {
 }
 
 void Solver::sync() { LB2_CUDA(cudaStreamSynchronize(ctx.stream)); }
+
+void Solver::read_slots_side() {
+    if (!side_stream) {
+        LB2_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+        LB2_CUDA(cudaEventCreateWithFlags(&side_event, cudaEventDisableTiming));
+    }
+    LB2_CUDA(cudaEventRecord(side_event, ctx.stream));
+    LB2_CUDA(cudaStreamWaitEvent(side_stream, side_event, 0));
+    LB2_CUDA(cudaMemcpyAsync(S_host, S.p, sizeof(double) * (kNumSlots + 2 * (nCones + 1)), cudaMemcpyDeviceToHost, side_stream));
+}
 
 void Solver::read_slots() {
     LB2_CUDA(cudaMemcpyAsync(S_host, S.p, sizeof(double) * (kNumSlots + 2 * (nCones + 1)), cudaMemcpyDeviceToHost, ctx.stream));
@@ -1237,12 +1249,26 @@ void Solver::update_sdp_var_one(long long c, double *upd, const double *noupd, d
         allgather_cone(K, p0);
         cg_matvec(K, p0, noupd, Q0, p0, S.p + SL_CG_RED);       // Q = A p, S[SL_CG_RED+1] = <p,Q>
         if (world > 1) allreduce(S.p + SL_CG_RED, 2);
-        launch_cg_update(ctx, nk, x, r, p, cg_Q.p + off, S.p, rrA, SL_CG_RED + 1, rrB);
+        // single GPU, no restart due: beta is formed on the device by the update kernel and p = r + beta p is enqueued
+        // BEFORE the scalar read-back, so the round trip overlaps it (same IEEE division and FMA as the host path; when
+        // the solve stops here the extra p is never used)
+        const bool early_p = (world == 1) && (k % 20 != 0);
+        launch_cg_update(ctx, nk, x, r, p, cg_Q.p + off, S.p, rrA, SL_CG_RED + 1, rrB, early_p ? SL_CG_BETA : -1);
         if (world > 1) allreduce(S.p + rrB, 1);
-        read_slots();
+        if (early_p) {
+            read_slots_side();       // scalars as of the update kernel, copied on the side stream ...
+            launch_axpby_dot(ctx, nk, p, coef_slot(SL_CG_BETA), p, coef_const(1.0), r, nullptr, S.p, SL_T1, false);
+            LB2_CUDA(cudaStreamSynchronize(side_stream));      // ... while the direction update runs
+        } else read_slots();
         double rrNew = S_host[rrB];
         const double resi = std::sqrt(rrNew);
         if (resi / bNorm < tol) break;
+        if (early_p) {
+            rr = rrNew;
+            std::swap(rrA, rrB);
+            if (resi != resi) printf("File [%30s] Line [%d]\n", "lorads_b200 cg", (int)k);
+            continue;
+        }
         double beta;
         if (k % 20 == 0) {
             // restart (also at k = 0, lorads_cgs.c:195): r = b - A x, p = q = r, then beta = <r,r>/<r,r>

@@ -21,6 +21,7 @@ enum Slot : int {
     SL_PINF = 17, SL_DG = 19, SL_OBJ = 20, SL_DOBJ = 21,
     SL_CG_RED = 24,       // 24 = sum Q.Q (unused), 25 = p.Q
     SL_CG_RR_A = 26, SL_CG_RR_B = 27, SL_CG_BN = 28,
+    SL_CG_BETA = 31,      // beta = <r,r>_new / <r,r>_old of the CG, computed by the update kernel
     SL_NEGALPHA0 = 32,    // 32..47  -alpha of the L-BFGS two-loop, per history node
     SL_BETA0 = 48,        // 48..63  beta = 1/<y,s> per history node
     SL_VF_D = 64,         // 64..71 Gram dots of the vector-free L-BFGS (see launch_lbfgs_pair)
@@ -224,6 +225,11 @@ struct Solver {
     void upload_factor(double *dst, const ConeDev &K, const double *colMajor);
     void download_factor(const double *src, const ConeDev &K, double *colMajor) const;
     void read_slots();          // S -> S_host (synchronises the stream)
+    // S -> S_host as of the work enqueued so far, on a second stream: kernels enqueued afterwards on the main stream keep
+    // running while the host waits for the scalars
+    void read_slots_side();
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t side_event = nullptr;
     void sync();
     void allreduce(double *p, long long count);
     // operators
