@@ -291,6 +291,142 @@ __global__ void __launch_bounds__(kBlock, MINB)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+//  narrow factors (ld <= 8: low rank, or the column shards of a factor): entry-parallel lanes
+// ---------------------------------------------------------------------------------------------------------------
+// A whole row is one or two 32-byte loads, so a lane per ROW (the geometry above with G = 1, 2) leaves every lane
+// chasing its own index stream with uncoalesced loads.  Here eight lanes share a row instead: lane gl takes entries
+// gl, gl + 8, ... (the eight index loads of a trip are one coalesced access), gathers the WHOLE row of its entry and
+// keeps a partial accumulator of its own; the eight partials are added once per row (SpMM) or never (the objective of
+// A(UV^T) is linear in them).  NQ = ld / 4.
+template <int NQ>
+__global__ void __launch_bounds__(kBlock, 4)
+    vc_spmm_narrow_kernel(VcDev V, int ld, bool useC, const double *__restrict__ w, const int *__restrict__ wmap,
+                          const double *__restrict__ Sres, const double *__restrict__ X, double a, double b,
+                          const double *__restrict__ Z, const double *__restrict__ Z2, double *__restrict__ Y, ReduceScratch rs,
+                          double *red, const double *__restrict__ cs, double c1) {
+    const int lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
+    const long long wg = (long long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * (kBlock / 32);
+    const bool dynamic = (w != nullptr) || (Sres != nullptr);
+    double ryy = 0.0, ryz = 0.0;
+    for (long long base = wg * 4; base < V.n; base += nw * 4) {        // warp-uniform trip count: full-mask shuffles below
+        const long long slot = base + g;
+        const int i = slot < V.n ? V.order[slot] : -1;
+        d4 acc[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) acc[q] = kZero4;
+        if (i >= 0) {
+            const int ea = dynamic ? V.u_ptr[i] : V.u_mid[i];
+            const int eb = useC ? V.u_ptr[i + 1] : V.u_mid[i];
+            for (int e = ea + gl; e < eb; e += 8) {
+                const int j = V.u_col[e], t = V.u_tag[e];
+                double sv = V.u_val[e];
+                if (t >= 0) sv = w ? w[wmap ? wmap[t] : t] * sv : 0.0;
+                else if (t <= -2) sv = Sres ? Sres[-2 - t] : 0.0;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) fma4(acc[q], sv, ld4(X + (size_t)j * ld + 4 * q));
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                acc[q].a += __shfl_xor_sync(0xffffffffu, acc[q].a, o, 8);
+                acc[q].b += __shfl_xor_sync(0xffffffffu, acc[q].b, o, 8);
+                acc[q].c += __shfl_xor_sync(0xffffffffu, acc[q].c, o, 8);
+                acc[q].d += __shfl_xor_sync(0xffffffffu, acc[q].d, o, 8);
+            }
+        if (i >= 0 && gl < NQ) {          // lane q of the group finishes columns 4q .. 4q+3
+            const int col = 4 * gl;
+            d4 r = acc[0];
+#pragma unroll
+            for (int q = 1; q < NQ; ++q) if (gl == q) r = acc[q];
+            if (cs) { r.a += c1 * cs[col]; r.b += c1 * cs[col + 1]; r.c += c1 * cs[col + 2]; r.d += c1 * cs[col + 3]; }
+            d4 y = {a * r.a, a * r.b, a * r.c, a * r.d};
+            if (Z) {
+                const d4 z = ld4c(Z + (size_t)i * ld + col);
+                y.a = fma(b, z.a, y.a); y.b = fma(b, z.b, y.b); y.c = fma(b, z.c, y.c); y.d = fma(b, z.d, y.d);
+            }
+            st4(Y + (size_t)i * ld + col, y);
+            ryy = fma(y.a, y.a, ryy); ryy = fma(y.b, y.b, ryy); ryy = fma(y.c, y.c, ryy); ryy = fma(y.d, y.d, ryy);
+            if (Z2) {
+                const d4 z2 = ld4c(Z2 + (size_t)i * ld + col);
+                ryz = fma(y.a, z2.a, ryz); ryz = fma(y.b, z2.b, ryz); ryz = fma(y.c, z2.c, ryz); ryz = fma(y.d, z2.d, ryz);
+            }
+        }
+    }
+    if (red) {
+        double v[2] = {ryy, ryz};
+        if (grid_reduce<2>(v, rs) && threadIdx.x == 0) { red[0] = v[0]; red[1] = v[1]; }
+    }
+}
+
+template <int MODE, int NQ>
+__global__ void __launch_bounds__(kBlock, 4)
+    vc_auv_narrow_kernel(VcDev V, int ld, bool with_obj, const double *__restrict__ U, const double *__restrict__ W, double s1,
+                         double s2, double *__restrict__ out1, double *__restrict__ out2, double *__restrict__ out3, double *obj1,
+                         double *obj2, ReduceScratch rs) {
+    constexpr bool SAME = (MODE == AUV_SAME);
+    constexpr bool TRI = (MODE == AUV_TRI);
+    constexpr bool DUAL = (MODE == AUV_DUAL) || TRI;
+    const int lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
+    const long long wg = (long long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * (kBlock / 32);
+    const double *__restrict__ W2 = SAME ? U : W;
+    double p1 = 0.0, p2 = 0.0;
+    for (long long slot = wg * 4 + g; slot < V.n; slot += nw * 4) {
+        const int j = V.order_l[slot];
+        const int ca = with_obj ? V.u_mid[j] : 0, cb = with_obj ? V.u_ptr[j + 1] : 0;
+        const int dc = V.d_con ? V.d_con[j] : -1;
+        if (ca == cb && dc < 0) continue;
+        d4 uj[NQ], wj[NQ], t[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            uj[q] = ld4(U + (size_t)j * ld + 4 * q);
+            wj[q] = SAME ? uj[q] : ld4(W + (size_t)j * ld + 4 * q);
+            t[q] = kZero4;
+        }
+        for (int e = ca + gl; e < cb; e += 8) {
+            const int i = V.u_col[e];
+            const double cv = V.u_val[e];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) fma4(t[q], cv, ld4(W2 + (size_t)i * ld + 4 * q));
+        }
+        // <U_j, sum_lanes t> = sum_lanes <U_j, t_lane>: no reduction across the lanes of the row
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            p1 += dot4(uj[q], t[q]);
+            if constexpr (DUAL) p2 += dot4(wj[q], t[q]);
+        }
+        if (dc >= 0 && gl == 0) {
+            double a1 = 0.0, a3 = 0.0, a4 = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                a1 += dot4(uj[q], wj[q]);
+                if constexpr (DUAL) a3 += dot4(wj[q], wj[q]);
+                if constexpr (TRI) a4 += dot4(uj[q], uj[q]);
+            }
+            const double cf = V.d_coef[j];
+            out1[dc] = s1 * cf * a1;
+            if constexpr (DUAL) out2[dc] = s2 * cf * a3;
+            if constexpr (TRI) out3[dc] = cf * a4;
+        }
+    }
+    if (with_obj) {
+        double v[2] = {p1, p2};
+        if (grid_reduce<2>(v, rs) && threadIdx.x == 0) {
+            const double o1 = s1 * v[0], o2 = s2 * v[1];
+            out1[V.obj_row] = o1;
+            if (obj1) *obj1 += o1;
+            if constexpr (DUAL) {
+                out2[V.obj_row] = o2;
+                if (obj2) *obj2 += o2;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 //  off-diagonal singleton constraints: one output per lower-triangular entry, entry-parallel
 // ---------------------------------------------------------------------------------------------------------------
 // A lane group walks CH consecutive entries of lowA (sorted by column, so the column-side rows U_j, W_j stay in
@@ -466,6 +602,17 @@ void launch_vc_spmm(Ctx &c, const VcDev &V, int ld, bool useC, const double *w, 
     const int np = vc_passes(ld);
     if (np == 0) throw std::runtime_error("rank above 256 is not supported by the SpMM kernel");
     const int un = vc_unroll(V.n, ld);
+    static const bool narrow_on = getenv("LORADS_B200_NO_NARROW") == nullptr;
+    // measured at n = 1e5 (profiles/r02_kernels_narrow_factors_cfg2.log): ld = 4: 20.5 vs 28.7 us; ld = 8: 28.1 vs 25.7 us
+    if (ld <= 4 && narrow_on) {
+        const long long blocks = std::min<long long>((V.n + 31) / 32, (long long)c.num_sms * 4);
+        const int grid = (int)std::max<long long>(1, std::min<long long>(blocks, kVcMaxGrid));
+        if (ld <= 4) vc_spmm_narrow_kernel<1><<<grid, kBlock, 0, c.stream>>>(V, ld, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, c.rs, red, cs, c1);
+        else vc_spmm_narrow_kernel<2><<<grid, kBlock, 0, c.stream>>>(V, ld, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, c.rs, red, cs, c1);
+        c.launches++;
+        LB2_CUDA(cudaGetLastError());
+        return;
+    }
 #define LB2_VC_SPMM(NP_, UN_) spmm_launch<NP_, UN_>(c, V, ld, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, red, cs, c1)
     switch (np) {
     case 1: {
@@ -497,7 +644,25 @@ void launch_vc_auv(Ctx &c, AuvMode mode, const VcDev &V, int ld, bool with_obj, 
     if (np == 0) throw std::runtime_error("rank above 256 is not supported by the A(UV^T) kernel");
     const int un = vc_unroll(V.n, ld);
     // row-centric part: objective row and the diagonal singleton constraints (skipped when the cone has neither)
-    if (V.n > 0 && (with_obj || V.d_con)) {
+    static const bool narrow_on = getenv("LORADS_B200_NO_NARROW") == nullptr;
+    // (ld = 4 with the objective row: 18.5 vs 22.6 us; constraints only, or ld = 8: the lane-per-row path stays faster)
+    if (V.n > 0 && with_obj && ld <= 4 && narrow_on) {
+        const long long blocks = std::min<long long>((V.n + 31) / 32, (long long)c.num_sms * 4);
+        const int grid = (int)std::max<long long>(1, std::min<long long>(blocks, kVcMaxGrid));
+#define LB2_VC_AUV_NARROW(M_)                                                                                                   \
+        if (ld <= 4) vc_auv_narrow_kernel<M_, 1><<<grid, kBlock, 0, c.stream>>>(V, ld, with_obj, U, W, s1, s2, out1, out2, out3, obj1, obj2, c.rs); \
+        else vc_auv_narrow_kernel<M_, 2><<<grid, kBlock, 0, c.stream>>>(V, ld, with_obj, U, W, s1, s2, out1, out2, out3, obj1, obj2, c.rs);
+        switch (mode) {
+        case AUV_SAME: LB2_VC_AUV_NARROW(AUV_SAME) break;
+        case AUV_PAIR: LB2_VC_AUV_NARROW(AUV_PAIR) break;
+        case AUV_DUAL: LB2_VC_AUV_NARROW(AUV_DUAL) break;
+        case AUV_TRI: LB2_VC_AUV_NARROW(AUV_TRI) break;
+        default: throw std::invalid_argument("vertex-centric A(UV^T): unsupported mode");
+        }
+#undef LB2_VC_AUV_NARROW
+        c.launches++;
+        LB2_CUDA(cudaGetLastError());
+    } else if (V.n > 0 && (with_obj || V.d_con)) {
         switch (mode) {
         case AUV_SAME: auv_dispatch<AUV_SAME>(c, np, un, V, ld, with_obj, U, W, s1, s2, out1, out2, out3, obj1, obj2); break;
         case AUV_PAIR: auv_dispatch<AUV_PAIR>(c, np, un, V, ld, with_obj, U, W, s1, s2, out1, out2, out3, obj1, obj2); break;
