@@ -604,7 +604,8 @@ void launch_vc_spmm(Ctx &c, const VcDev &V, int ld, bool useC, const double *w, 
     const int un = vc_unroll(V.n, ld);
     static const bool narrow_on = getenv("LORADS_B200_NO_NARROW") == nullptr;
     // measured at n = 1e5 (profiles/r02_kernels_narrow_factors_cfg2.log): ld = 4: 20.5 vs 28.7 us; ld = 8: 28.1 vs 25.7 us
-    if (ld <= 4 && narrow_on) {
+    // (n = 1e6, index arrays streamed from DRAM, rows in natural order: it loses, 170 vs 134 us -- lane-per-row path there)
+    if (ld <= 4 && narrow_on && V.n <= 250000) {
         const long long blocks = std::min<long long>((V.n + 31) / 32, (long long)c.num_sms * 4);
         const int grid = (int)std::max<long long>(1, std::min<long long>(blocks, kVcMaxGrid));
         if (ld <= 4) vc_spmm_narrow_kernel<1><<<grid, kBlock, 0, c.stream>>>(V, ld, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, c.rs, red, cs, c1);
@@ -646,7 +647,7 @@ void launch_vc_auv(Ctx &c, AuvMode mode, const VcDev &V, int ld, bool with_obj, 
     // row-centric part: objective row and the diagonal singleton constraints (skipped when the cone has neither)
     static const bool narrow_on = getenv("LORADS_B200_NO_NARROW") == nullptr;
     // (ld = 4 with the objective row: 18.5 vs 22.6 us; constraints only, or ld = 8: the lane-per-row path stays faster)
-    if (V.n > 0 && with_obj && ld <= 4 && narrow_on) {
+    if (V.n > 0 && with_obj && ld <= 4 && narrow_on && V.n <= 250000) {
         const long long blocks = std::min<long long>((V.n + 31) / 32, (long long)c.num_sms * 4);
         const int grid = (int)std::max<long long>(1, std::min<long long>(blocks, kVcMaxGrid));
 #define LB2_VC_AUV_NARROW(M_)                                                                                                   \
