@@ -102,54 +102,73 @@ void Solver::bcast_ranges(double *X, long long lo, long long hi) {
 // Exchange buffers for the peer-memory all-reduce: allocate, publish through CUDA IPC (handles travel by
 // ncclAllGather), map every peer.  Any failure leaves p2p_on = false and the NCCL path in charge.
 static void setup_p2p(Solver &S) {
-    // Opt-in (LORADS_B200_P2P=1): at 2 GPUs NCCL's own small-message path measured 2 % FASTER per ALM step than this
-    // one-kernel exchange (4548 vs 4447 it/s, same box), and much faster for the 1.6 MB m-vectors (18 vs 33 us).
-    if (getenv("LORADS_B200_P2P") == nullptr || !g_nccl.allgather) return;
+    // Default from 4 GPUs up (LORADS_B200_P2P=0 / 1 overrides): measured on 8 GPUs the one-shot exchange takes 12 us
+    // for the scalar table against 23 us for NCCL and the MaxCut n = 1e5 step drops from 0.203 to 0.141 ms; at 2 GPUs
+    // NCCL's own small-message path was 2 % faster per step.  The m-vectors always stay on NCCL (faster above ~1 MB).
+    const char *env = getenv("LORADS_B200_P2P");
+    const bool want = env ? (atoi(env) != 0) : (S.world >= 4);
+    if (!want || !g_nccl.allgather) return;
     const int W = S.world;
     const size_t cap = (((size_t)S.m + 2) & ~(size_t)1) * 2;          // q1 | q2 in one message
+    struct Handles { cudaIpcMemHandle_t x, f; int ok; };
+    Handles mine;
+    std::memset(&mine, 0, sizeof(mine));
+    // step 1 (may fail locally): buffers and their IPC handles
     try {
         S.p2p_x.alloc(2 * (size_t)W * cap);
         S.p2p_f.alloc(2 * (size_t)W);
         S.p2p_epoch.alloc(1);
         S.p2p_ticket.alloc(2);
-        struct Handles { cudaIpcMemHandle_t x, f; };
-        Handles mine;
         LB2_CUDA(cudaIpcGetMemHandle(&mine.x, S.p2p_x.p));
         LB2_CUDA(cudaIpcGetMemHandle(&mine.f, S.p2p_f.p));
+        mine.ok = 1;
+    } catch (const std::exception &e) {
+        cudaGetLastError();
+        mine.ok = 0;
+        fprintf(stderr, "lorads_b200: peer-memory all-reduce unavailable on rank %d (%s); using NCCL\n", S.myrank, e.what());
+    }
+    // step 2 (every rank, whatever happened in step 1: nobody is left waiting in the collective): exchange the handles
+    std::vector<Handles> all((size_t)W);
+    {
         DBuf<unsigned char> dsend, drecv;
         dsend.alloc(sizeof(Handles)); drecv.alloc(sizeof(Handles) * (size_t)W);
         LB2_CUDA(cudaMemcpy(dsend.p, &mine, sizeof(Handles), cudaMemcpyHostToDevice));
         if (g_nccl.allgather(dsend.p, drecv.p, sizeof(Handles), 0 /* ncclInt8 */, S.nccl, S.ctx.stream) != 0)
             throw CudaError("ncclAllGather failed");
         LB2_CUDA(cudaStreamSynchronize(S.ctx.stream));
-        std::vector<Handles> all((size_t)W);
         LB2_CUDA(cudaMemcpy(all.data(), drecv.p, sizeof(Handles) * (size_t)W, cudaMemcpyDeviceToHost));
-        std::vector<double *> px((size_t)W);
-        std::vector<unsigned long long *> pf((size_t)W);
-        for (int r = 0; r < W; ++r) {
-            if (r == S.myrank) { px[(size_t)r] = S.p2p_x.p; pf[(size_t)r] = S.p2p_f.p; continue; }
-            void *a = nullptr, *b = nullptr;
-            LB2_CUDA(cudaIpcOpenMemHandle(&a, all[(size_t)r].x, cudaIpcMemLazyEnablePeerAccess));
-            S.p2p_opened.push_back(a);
-            LB2_CUDA(cudaIpcOpenMemHandle(&b, all[(size_t)r].f, cudaIpcMemLazyEnablePeerAccess));
-            S.p2p_opened.push_back(b);
-            px[(size_t)r] = (double *)a; pf[(size_t)r] = (unsigned long long *)b;
+    }
+    bool everybody = true;
+    for (int r = 0; r < W; ++r) everybody = everybody && all[(size_t)r].ok == 1;
+    // step 3: map the peers (only when every rank has buffers)
+    bool mapped = everybody;
+    if (everybody) {
+        try {
+            std::vector<double *> px((size_t)W);
+            std::vector<unsigned long long *> pf((size_t)W);
+            for (int r = 0; r < W; ++r) {
+                if (r == S.myrank) { px[(size_t)r] = S.p2p_x.p; pf[(size_t)r] = S.p2p_f.p; continue; }
+                void *a = nullptr, *b = nullptr;
+                LB2_CUDA(cudaIpcOpenMemHandle(&a, all[(size_t)r].x, cudaIpcMemLazyEnablePeerAccess));
+                S.p2p_opened.push_back(a);
+                LB2_CUDA(cudaIpcOpenMemHandle(&b, all[(size_t)r].f, cudaIpcMemLazyEnablePeerAccess));
+                S.p2p_opened.push_back(b);
+                px[(size_t)r] = (double *)a; pf[(size_t)r] = (unsigned long long *)b;
+            }
+            S.p2p_peer_x.upload(px); S.p2p_peer_f.upload(pf);
+            S.p2p.world = W; S.p2p.rank = S.myrank; S.p2p.cap = cap;
+            S.p2p.peer_x = S.p2p_peer_x.p; S.p2p.peer_f = S.p2p_peer_f.p;
+            S.p2p.x = S.p2p_x.p; S.p2p.f = S.p2p_f.p; S.p2p.epoch = S.p2p_epoch.p; S.p2p.ticket = S.p2p_ticket.p;
+        } catch (const std::exception &e) {
+            cudaGetLastError();
+            mapped = false;
+            fprintf(stderr, "lorads_b200: peer mapping failed on rank %d (%s); using NCCL\n", S.myrank, e.what());
         }
-        S.p2p_peer_x.upload(px); S.p2p_peer_f.upload(pf);
-        S.p2p.world = W; S.p2p.rank = S.myrank; S.p2p.cap = cap;
-        S.p2p.peer_x = S.p2p_peer_x.p; S.p2p.peer_f = S.p2p_peer_f.p;
-        S.p2p.x = S.p2p_x.p; S.p2p.f = S.p2p_f.p; S.p2p.epoch = S.p2p_epoch.p; S.p2p.ticket = S.p2p_ticket.p;
-        S.p2p_on = true;
-    } catch (const std::exception &e) {
-        cudaGetLastError();
-        S.p2p_on = false;
-        fprintf(stderr, "lorads_b200: peer-memory all-reduce unavailable on rank %d (%s); using NCCL\n", S.myrank, e.what());
     }
     // Agreement + barrier in one NCCL all-reduce: the exchange is used only if EVERY rank mapped its peers, and nobody
     // pushes before every rank has zeroed its flags.
-    const bool mine_ok = S.p2p_on;
     S.p2p_on = false;
-    const double flag = mine_ok ? 1.0 : 0.0;
+    const double flag = mapped ? 1.0 : 0.0;
     LB2_CUDA(cudaMemcpy(S.S.p + SL_T1, &flag, sizeof(double), cudaMemcpyHostToDevice));
     S.allreduce(S.S.p + SL_T1, 1);
     double sum = 0.0;
