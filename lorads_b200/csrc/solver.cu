@@ -597,6 +597,23 @@ void Solver::get_factor(char which, long long c, double *colMajor) const {
 
 void Solver::sync() { LB2_CUDA(cudaStreamSynchronize(ctx.stream)); }
 
+// Host wait on the per-iteration round trips.  cudaStreamSynchronize follows the context's scheduling flag, and the
+// default ("auto") turns into a blocking wait with tens of microseconds of wake-up latency when the process sees few
+// CPU cores (containers, eight ranks on one node): the step time then varied by +-25 % from box to box with identical
+// kernel and collective times.  Polling the stream keeps the latency at one driver call on every box.
+// LORADS_B200_BLOCKING_SYNC=1 restores the blocking wait.
+static void spin_sync(cudaStream_t s) {
+    static const bool blocking = getenv("LORADS_B200_BLOCKING_SYNC") != nullptr;
+    if (blocking) { LB2_CUDA(cudaStreamSynchronize(s)); return; }
+    cudaError_t e;
+    while ((e = cudaStreamQuery(s)) == cudaErrorNotReady) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    LB2_CUDA(e);
+}
+
 void Solver::read_slots_side() {
     if (!side_stream) {
         LB2_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
@@ -609,7 +626,7 @@ void Solver::read_slots_side() {
 
 void Solver::read_slots() {
     LB2_CUDA(cudaMemcpyAsync(S_host, S.p, sizeof(double) * (kNumSlots + 2 * (nCones + 1)), cudaMemcpyDeviceToHost, ctx.stream));
-    LB2_CUDA(cudaStreamSynchronize(ctx.stream));
+    spin_sync(ctx.stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1165,7 +1182,7 @@ void Solver::iter_back_front(double rho, double tau, long long next_counter) {
     LB2_CUDA(cudaGraphLaunch(it->second.exec, ctx.stream));
     ctx.launches += it->second.launches;
     lb_head = (lb_head + 1) % lbfgs_len;
-    LB2_CUDA(cudaStreamSynchronize(ctx.stream));
+    spin_sync(ctx.stream);
 }
 
 int Solver::alm_inner_front(double rho, long long counter, double *tau, double *p12, long long *rootNum) {
@@ -1258,7 +1275,7 @@ void Solver::update_sdp_var_one(long long c, double *upd, const double *noupd, d
         if (early_p) {
             read_slots_side();       // scalars as of the update kernel, copied on the side stream ...
             launch_axpby_dot(ctx, nk, p, coef_slot(SL_CG_BETA), p, coef_const(1.0), r, nullptr, S.p, SL_T1, false);
-            LB2_CUDA(cudaStreamSynchronize(side_stream));      // ... while the direction update runs
+            spin_sync(side_stream);      // ... while the direction update runs
         } else read_slots();
         double rrNew = S_host[rrB];
         const double resi = std::sqrt(rrNew);
