@@ -179,6 +179,15 @@ def kernel_bytes(S) -> dict:
     }
 
 
+def shard_description(world, rows):
+    if world <= 1:
+        return ""
+    if rows:
+        return (f"row slabs of the factors over {world} GPUs (cone blocks / rows with their pattern entries): NCCL all-reduce of the "
+                "m-vectors per A() evaluation, scalar all-reduce per dot table, all-gather of the new direction")
+    return f"factor columns sharded over {world} GPUs, NCCL all-reduce per A() evaluation and per dot"
+
+
 def workload_config(rank_r, world, mode):
     """The `config` object of the JSON line: identical for our arm and the reference arm."""
     return {"workload": f"MaxCut SDP n=m={WORKLOAD['n']} edges={WORKLOAD['edges']} seed={WORKLOAD['seed']} rank={rank_r} ({WORKLOAD['label']}); one step = one ALM inner iteration, lorads_alm.c:1073-1146",
@@ -229,7 +238,7 @@ def run_reference(args):
     inst = make_instance()
     # bounded sample: at most 60 timed and 10 warm-up iterations of the reference (0.33 s each on one core)
     steps = max(1, min(args.steps, 60))
-    warm = max(0, min(args.warmup, 10))
+    warm = min(max(3, args.warmup), 10)          # our arm always warms up at least 3 steps
     t0 = time.time()
     out = cpu_reference_rate(inst, warm + steps)
     if out is None:
@@ -240,7 +249,8 @@ def run_reference(args):
         "impl": "reference", "metric": "alm_inner_iterations_per_second", "value": rate, "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 / rate, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(r, 1, ""),
+        # the same config object as our arm prints at this N (the reference itself runs on the host cores of rank 0)
+        "config": workload_config(r, args.gpus, shard_description(args.gpus, os.environ.get("LORADS_B200_SHARD") == "rows")),
         "cpu_baseline": {"value": rate, "unit": "iterations/s", "cores": 1, "kind": "reference",
                          "sample": f"{warm + steps} inner iterations of the untouched reference (oracle/_ref, -DMAC_INT64, OpenBLAS 1 thread) from the srand(925) start, {sec:.1f} s; host has {os.cpu_count()} cores, the reference is single-threaded"},
         "e2e": {"value": rate, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -287,12 +297,7 @@ def run_ours(args):
     t_setup = time.time() - t_setup
     rho = S.dinfo(6)
     n, r, m = S.dim(0), S.rank(0), S.m
-    shard_desc = ""
-    if world > 1:
-        shard_desc = (f"row slabs of the factors over {world} GPUs (cone blocks / rows with their pattern entries): NCCL all-reduce of the "
-                      "m-vectors per A() evaluation, scalar all-reduce per dot table, all-gather of the new direction"
-                      if S.info(28) == 1 else
-                      f"factor columns sharded over {world} GPUs, NCCL all-reduce per A() evaluation and per dot")
+    shard_desc = shard_description(world, S.info(28) == 1)
 
     def barrier():
         if dist is not None:

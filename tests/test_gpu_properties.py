@@ -94,3 +94,28 @@ def test_inner_iterations_decrease_the_merit(big):
         assert root != 0 and 0.0 <= o["tau"] <= 1.0
         lags.append(o["lag_norm_sq"])
     assert lags[-1] < lag0
+
+
+@pytest.mark.parametrize("case", ["theta", "mcomp", "maxcut"])
+def test_reopt_path_reaches_the_same_optimum(case):
+    """A solve pushed into the re-optimisation loop (reopt -> objScale_dualvar, lorads_solver.c:1040-1052, main.c:386-435)
+    by a tiny ADMM iteration limit has to land on the optimum of the default solve: the objective rescaling touches every
+    copy of C the kernels read (pattern values, item weights, the vertex-centric adjacency, the rank-one coefficient)."""
+    from lorads_b200.capi import Solver, default_params
+    inst = {"theta": lambda: sdpa.lovasz_theta(60, 300, 5), "mcomp": lambda: sdpa.matrix_completion(60, 50, 700, 3, 7),
+            "maxcut": lambda: sdpa.maxcut(120, 600, 1)}[case]()
+    ref = Solver(inst).solve(default_params())
+    p = default_params()
+    p.maxALMIter = 6          # leave phase 1 early ...
+    p.maxADMMIter = 20        # ... and phase 2 before it converges, so that reopt has to finish the job
+    res = Solver(inst).solve(p)
+    assert ref["status"] in (1, 2)
+    if case == "theta":
+        # the hard instance may run out of its (tiny) iteration budget; an inconsistent rescaling would be off by the
+        # reopt factor 5, not by a percent
+        assert res["status"] in (1, 2, 3)
+        assert abs(res["pObj"] - ref["pObj"]) <= 1e-2 * (1 + abs(ref["pObj"]))
+    else:
+        assert res["status"] in (1, 2)
+        assert res["pInfeasL1"] <= 1e-5 and res["pdGap"] <= 5e-5
+        assert abs(res["pObj"] - ref["pObj"]) <= 1e-4 * (1 + abs(ref["pObj"]))
