@@ -124,9 +124,13 @@ int lb2_init_vars(lb2_solver *s, lb2_int lbfgsListLength, double initRho);
 /* LORADSDestroy* (lorads_solver.c:81,265,280,500,677). */
 void lb2_destroy(lb2_solver *s);
 
-/* Multi-GPU: factor columns are sharded over `world` ranks (one process per GPU); `ncclUniqueId` is the
- * 128-byte NCCL id produced on rank 0 and broadcast by the caller (e.g. torch.distributed over gloo/nccl).
- * Call between lb2_determine_rank and lb2_init_vars. */
+/* Multi-GPU: one process per GPU; `id128` is the 128-byte NCCL id produced on rank 0 (lb2_comm_unique_id) and broadcast
+ * by the caller (e.g. torch.distributed over gloo/nccl).  Call after lb2_preprocess / lb2_determine_rank and before
+ * lb2_init_vars.  The solve is sharded by factor columns (default) or, with LORADS_B200_SHARD=rows in the environment, by
+ * row slabs / cone blocks (the independent cone loops of lorads_alg_common.c:78-84,105-112 and lorads_alm.c:46-53 go to
+ * different ranks, a huge block is split by rows); one all-reduce of the m-vector per A() evaluation
+ * (LORADSInitConstrValSum, lorads_alg_common.c:134-142) and one scalar all-reduce per dot table in both schemes.
+ * An LP block together with sharding returns LB2_ERR_UNSUPPORTED. */
 int lb2_comm_unique_id(void *id128);
 int lb2_comm_init(lb2_solver *s, const void *id128, int rank, int world);
 
