@@ -90,16 +90,29 @@ struct ReduceScratch {
 };
 
 // Returns true in every thread of the LAST block; there thread 0 holds the NV totals in v[].
+// All NV values travel through one shared-memory exchange (two barriers per phase instead of two per value): warp sums,
+// then thread k adds the eight warp partials of value k in warp order -- the same additions in the same order as
+// block_sum, so results are bit-identical to the one-value-at-a-time form.
 template <int NV>
 __device__ __forceinline__ bool grid_reduce(double (&v)[NV], ReduceScratch rs) {
-    __shared__ double sm[8];
+    static_assert(NV <= 32, "grid_reduce: at most 32 values");
+    __shared__ double sm[NV][kBlock / 32];
     __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-        double t = block_sum(v[k], sm);
-        if (threadIdx.x == 0) rs.partials[(size_t)blockIdx.x * NV + k] = t;
+        const double t = warp_sum(v[k]);
+        if (lane == 0) sm[k][w] = t;
     }
-    __threadfence();
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < kBlock / 32; ++q) t += sm[threadIdx.x][q];
+        rs.partials[(size_t)blockIdx.x * NV + threadIdx.x] = t;
+        __threadfence();
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         unsigned int ticket = atomicAdd(rs.counter, 1u);
         is_last = (ticket == gridDim.x - 1);
@@ -111,9 +124,22 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], ReduceScratch rs) {
     for (int k = 0; k < NV; ++k) {
         double t = 0.0;
         for (unsigned int b = threadIdx.x; b < gridDim.x; b += kBlock) t += __ldcg(rs.partials + (size_t)b * NV + k);
-        v[k] = block_sum(t, sm);
+        t = warp_sum(t);
+        if (lane == 0) sm[k][w] = t;
     }
-    if (threadIdx.x == 0) *rs.counter = 0u;
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < kBlock / 32; ++q) t += sm[threadIdx.x][q];
+        sm[threadIdx.x][0] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v[k] = sm[k][0];
+        *rs.counter = 0u;
+    }
     return true;
 }
 
