@@ -1174,11 +1174,38 @@ void launch_neg_if_nonneg(Ctx &c, long long n, double *D, const double *G, const
     LB2_LAUNCH_CHECK(c);
 }
 
+// m-vector update of the same point of the iteration (see launch_alm_m_update): carried by extra CTAs of the step
+// kernel, so that the two element-wise passes cost one launch
+struct MUpdate {
+    long long m = 0;
+    const double *q1 = nullptr, *q2 = nullptr, *lam = nullptr, *b = nullptr, *rho_p = nullptr;
+    double *s = nullptr, *M1 = nullptr;
+};
+
+__device__ __forceinline__ void m_update_body(const MUpdate &u, const double *tau_p, long long first, long long stride) {
+    const double tau = u.q1 ? *tau_p : 0.0, rho = *u.rho_p;
+    const double t2 = tau * tau;
+    for (long long i = first; i < u.m; i += stride) {
+        double sv = u.s[i];
+        if (u.q1) {
+            sv = fma(tau, u.q1[i], sv);
+            sv = fma(t2, u.q2[i], sv);
+            u.s[i] = sv;
+        }
+        u.M1[i] = fma(rho, sv, fma(-rho, u.b[i], -u.lam[i]));
+    }
+}
+
 __global__ void __launch_bounds__(kBlock) alm_step_kernel(long long n, const double *tau_p, const double *__restrict__ G,
                                                           const double *__restrict__ D, double *__restrict__ R,
-                                                          double *__restrict__ y, double *__restrict__ s) {
+                                                          double *__restrict__ y, double *__restrict__ s, int vec_blocks,
+                                                          MUpdate mu) {
+    if ((int)blockIdx.x >= vec_blocks) {
+        m_update_body(mu, tau_p, (long long)(blockIdx.x - vec_blocks) * kBlock + threadIdx.x, (long long)(gridDim.x - vec_blocks) * kBlock);
+        return;
+    }
     const double tau = *tau_p;
-    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n; q += (long long)gridDim.x * kBlock) {
+    for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < n; q += (long long)vec_blocks * kBlock) {
         const double d = D[q];
         y[q] = -G[q];
         s[q] = tau * d;
@@ -1187,7 +1214,19 @@ __global__ void __launch_bounds__(kBlock) alm_step_kernel(long long n, const dou
 }
 
 void launch_alm_step(Ctx &c, long long n, const double *tau_p, const double *G, const double *D, double *R, double *y, double *s) {
-    alm_step_kernel<<<grid_for(n, 4, c), kBlock, 0, c.stream>>>(n, tau_p, G, D, R, y, s);
+    const int vb = grid_for(n, 4, c);
+    alm_step_kernel<<<vb, kBlock, 0, c.stream>>>(n, tau_p, G, D, R, y, s, vb, MUpdate{});
+    LB2_LAUNCH_CHECK(c);
+}
+
+void launch_alm_step_m(Ctx &c, long long n, const double *tau_p, const double *G, const double *D, double *R, double *y, double *s,
+                       long long m, const double *q1, const double *q2, double *sm, const double *lam, const double *b,
+                       const double *rho_p, double *M1) {
+    const int vb = grid_for(n, 4, c);
+    const int mb = grid_for(m, 4, c);
+    MUpdate mu;
+    mu.m = m; mu.q1 = q1; mu.q2 = q2; mu.lam = lam; mu.b = b; mu.rho_p = rho_p; mu.s = sm; mu.M1 = M1;
+    alm_step_kernel<<<vb + mb, kBlock, 0, c.stream>>>(n, tau_p, G, D, R, y, s, vb, mu);
     LB2_LAUNCH_CHECK(c);
 }
 

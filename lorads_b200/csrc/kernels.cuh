@@ -160,6 +160,11 @@ void launch_neg_if_nonneg(Ctx &c, long long n, double *D, const double *G, const
 // y = -G ; s = tau*D ; R += tau*D         (SetyAsNegGrad :583, ALMupdateVar :619, first half of setlbfgsHisTwo :657)
 // tau is read from *tau_p (a device scalar slot) so that the launch can live in a replayed CUDA graph
 void launch_alm_step(Ctx &c, long long n, const double *tau_p, const double *G, const double *D, double *R, double *y, double *s);
+// the same plus launch_alm_m_update(m, tau_p, q1, q2, sm, lam, b, rho_p, M1) in ONE launch (extra CTAs; both passes are
+// element-wise and independent, same arithmetic as the two separate kernels)
+void launch_alm_step_m(Ctx &c, long long n, const double *tau_p, const double *G, const double *D, double *R, double *y, double *s,
+                       long long m, const double *q1, const double *q2, double *sm, const double *lam, const double *b,
+                       const double *rho_p, double *M1);
 // x += alpha*p ; r -= alpha*Q ; S[slot_rr] = sum r*r  with alpha = S[slot_num]/S[slot_den]  (lorads_cgs.c:183-189)
 // slot_beta >= 0: S[slot_beta] = (new sum r*r) / S[slot_num], the beta of the next search direction
 void launch_cg_update(Ctx &c, long long n, double *x, double *r, const double *p, const double *Q, double *S,

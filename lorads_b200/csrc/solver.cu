@@ -1087,13 +1087,14 @@ long long Solver::finish_front(double rho, double *tau, double *p12) {
 void Solver::enqueue_back(double rho, double tau, bool front_follows) {
     (void)rho; (void)tau;     // both are read from the scalar slots S[SL_RHO], S[SL_TAU] (push_scalars)
     const int head = lb_head;
-    launch_alm_step(ctx, vn, S.p + SL_TAU, G.p + vo, U.p + vo, R.p + vo, lb_y[head].p + vo, lb_s[head].p + vo);
+    // variable step + m-vector update (s += tau q1 + tau^2 q2, M1 = -lambda - rho b + rho s) in one launch
+    launch_alm_step_m(ctx, vn, S.p + SL_TAU, G.p + vo, U.p + vo, R.p + vo, lb_y[head].p + vo, lb_s[head].p + vo, m, q1.p, q2.p,
+                      s.p, lam.p, b.p, S.p + SL_RHO, M1.p);
     if (shard_rows()) {
         // R is replicated: the rows owned elsewhere take the same fused multiply-add from the gathered direction
         launch_axpy_slot(ctx, vo, S.p + SL_TAU, U.p, R.p);
         launch_axpy_slot(ctx, N - (vo + vn), S.p + SL_TAU, U.p + vo + vn, R.p + vo + vn);
     }
-    launch_alm_m_update(ctx, m, S.p + SL_TAU, q1.p, q2.p, s.p, lam.p, b.p, S.p + SL_RHO, M1.p);
     grad_from_M1(*this);
     // setlbfgsHisTwo, lorads_alm.c:657-678: y += G_new, beta = 1/<y,s>, advance the ring
     if (use_vf()) {
