@@ -1256,12 +1256,20 @@ void launch_cg_update(Ctx &c, long long n, double *x, double *r, const double *p
     LB2_LAUNCH_CHECK(c);
 }
 
+// Last block of the kernel that ends an iteration: publish the scalar slots to pinned host memory (Ctx::mirror), so that
+// the host reads them right after the stream drains without a copy node in between.
+__device__ __forceinline__ void mirror_slots(const double *S, double *mirror, int mirror_n) {
+    if (!mirror) return;
+    __syncthreads();
+    for (int t = threadIdx.x; t < mirror_n; t += kBlock) mirror[t] = __ldcg(S + t);
+}
+
 __global__ void __launch_bounds__(kBlock) linesearch_dots_kernel(long long m, const double *__restrict__ b,
                                                                  const double *__restrict__ s,
                                                                  const double *__restrict__ lam, const double *rho_p,
                                                                  const double *__restrict__ q1,
                                                                  const double *__restrict__ q2, double *S, int slot,
-                                                                 ReduceScratch rs) {
+                                                                 ReduceScratch rs, double *mirror, int mirror_n) {
     const double rhoInv = 1.0 / (*rho_p);
     double v[5] = {0, 0, 0, 0, 0};
     for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < m; i += (long long)gridDim.x * kBlock) {
@@ -1273,8 +1281,10 @@ __global__ void __launch_bounds__(kBlock) linesearch_dots_kernel(long long m, co
         v[3] = fma(a, a, v[3]);
         v[4] = fma(q0, a, v[4]);
     }
-    if (grid_reduce<5>(v, rs) && threadIdx.x == 0)
+    if (!grid_reduce<5>(v, rs)) return;
+    if (threadIdx.x == 0)
         for (int k = 0; k < 5; ++k) S[slot + k] = v[k];
+    mirror_slots(S, mirror, mirror_n);
 }
 
 // The same sums when the exact constraint values arrive in `src` (third output of the gather pass): s := src, the
@@ -1284,7 +1294,8 @@ __global__ void __launch_bounds__(kBlock) linesearch_resid_kernel(long long m, c
                                                                   const double *__restrict__ lam, const double *rho_p,
                                                                   const double *__restrict__ q1,
                                                                   const double *__restrict__ q2, double *S, int slot,
-                                                                  int pinf_slot, ReduceScratch rs) {
+                                                                  int pinf_slot, ReduceScratch rs, double *mirror,
+                                                                  int mirror_n) {
     const double rhoInv = 1.0 / (*rho_p);
     double v[6] = {0, 0, 0, 0, 0, 0};
     for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < m; i += (long long)gridDim.x * kBlock) {
@@ -1300,21 +1311,23 @@ __global__ void __launch_bounds__(kBlock) linesearch_resid_kernel(long long m, c
         v[4] = fma(q0, a, v[4]);
         v[5] = fma(d, d, v[5]);
     }
-    if (grid_reduce<6>(v, rs) && threadIdx.x == 0) {
+    if (!grid_reduce<6>(v, rs)) return;
+    if (threadIdx.x == 0) {
         for (int k = 0; k < 5; ++k) S[slot + k] = v[k];
         S[pinf_slot] = v[5];
     }
+    mirror_slots(S, mirror, mirror_n);
 }
 
 void launch_linesearch_resid(Ctx &c, long long m, const double *b, const double *src, double *s, const double *lam,
                              const double *rho_p, const double *q1, const double *q2, double *S, int slot, int pinf_slot) {
-    linesearch_resid_kernel<<<grid_for(m, 4, c), kBlock, 0, c.stream>>>(m, b, src, s, lam, rho_p, q1, q2, S, slot, pinf_slot, c.rs);
+    linesearch_resid_kernel<<<grid_for(m, 4, c), kBlock, 0, c.stream>>>(m, b, src, s, lam, rho_p, q1, q2, S, slot, pinf_slot, c.rs, c.mirror, c.mirror_n);
     LB2_LAUNCH_CHECK(c);
 }
 
 void launch_linesearch_dots(Ctx &c, long long m, const double *b, const double *s, const double *lam, const double *rho_p,
                             const double *q1, const double *q2, double *S, int slot) {
-    linesearch_dots_kernel<<<grid_for(m, 4, c), kBlock, 0, c.stream>>>(m, b, s, lam, rho_p, q1, q2, S, slot, c.rs);
+    linesearch_dots_kernel<<<grid_for(m, 4, c), kBlock, 0, c.stream>>>(m, b, s, lam, rho_p, q1, q2, S, slot, c.rs, c.mirror, c.mirror_n);
     LB2_LAUNCH_CHECK(c);
 }
 

@@ -13,6 +13,10 @@ struct Ctx {
     size_t dense_part_cap = 0;         // capacity of dense_part in doubles
     int num_sms = 148;
     long long launches = 0;
+    // When set, the kernel that ends an iteration (the line-search sums) copies the first mirror_n scalar slots into
+    // this pinned host buffer from its last block, replacing a device-to-host copy node behind it.
+    double *mirror = nullptr;
+    int mirror_n = 0;
 };
 
 // ------------------------------------------------------------------------------------------------

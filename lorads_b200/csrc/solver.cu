@@ -1142,11 +1142,12 @@ void Solver::finish_back(double *lagNormSq, double *pinf1) {
 }
 
 void Solver::iter_back_front(double rho, double tau, long long next_counter) {
-    push_scalars(tau, rho);
     const size_t slot_bytes = sizeof(double) * (kNumSlots + 2 * (nCones + 1));
     // NCCL all-reduces are captured into the graph too (validated at 2 ranks); LORADS_B200_NO_GRAPH_NCCL=1 opts out
     static const bool graph_nccl = getenv("LORADS_B200_NO_GRAPH_NCCL") == nullptr;
+    static const bool mirror_scalars = getenv("LORADS_B200_NO_MIRROR") == nullptr;
     if (!use_graphs || (world > 1 && !graph_nccl)) {
+        push_scalars(tau, rho);
         enqueue_back(rho, tau, next_counter >= 0);
         if (next_counter >= 0) enqueue_front(rho, next_counter);
         read_slots();
@@ -1163,10 +1164,19 @@ void Solver::iter_back_front(double rho, double tau, long long next_counter) {
         cudaGraph_t graph = nullptr;
         LB2_CUDA(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal));
         try {
+            // first node: tau, rho from the pinned pair the host fills before every replay; last kernel: the line-search
+            // sums, whose final block mirrors the scalar slots into pinned host memory (no copy node behind it)
+            LB2_CUDA(cudaMemcpyAsync(S.p + SL_TAU, push_host, 2 * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
             enqueue_back(rho, tau, next_counter >= 0);
+            if (next_counter >= 0 && mirror_scalars) {
+                ctx.mirror = S_host; ctx.mirror_n = (int)(slot_bytes / sizeof(double));
+            }
             if (next_counter >= 0) enqueue_front(rho, next_counter);
-            LB2_CUDA(cudaMemcpyAsync(S_host, S.p, slot_bytes, cudaMemcpyDeviceToHost, ctx.stream));
+            const bool mirrored = ctx.mirror != nullptr;
+            ctx.mirror = nullptr; ctx.mirror_n = 0;
+            if (!mirrored) LB2_CUDA(cudaMemcpyAsync(S_host, S.p, slot_bytes, cudaMemcpyDeviceToHost, ctx.stream));
         } catch (...) {
+            ctx.mirror = nullptr; ctx.mirror_n = 0;
             cudaStreamEndCapture(ctx.stream, &graph);
             if (graph) cudaGraphDestroy(graph);
             throw;
@@ -1180,6 +1190,7 @@ void Solver::iter_back_front(double rho, double tau, long long next_counter) {
         it = iter_graphs.emplace(key, g).first;
     }
     // ... and replay them as one graph launch
+    push_host[0] = tau; push_host[1] = rho;
     LB2_CUDA(cudaGraphLaunch(it->second.exec, ctx.stream));
     ctx.launches += it->second.launches;
     lb_head = (lb_head + 1) % lbfgs_len;
