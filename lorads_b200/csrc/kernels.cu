@@ -584,14 +584,17 @@ __global__ void __launch_bounds__(kBlock) dense_uvt_dmma_kernel(long long n, int
 // Split-K symmetric product: CTA (x = 64-row block, y = split) accumulates its share of column blocks with DMMA
 // (warp w owns rows 8w..8w+7 and every 8-column sub-tile of X) and writes a partial n x ldp block; the finish
 // kernel adds the partials in split order and applies the epilogue (deterministic).
-constexpr int kSymRows = 64, kSymMaxSub = 12;   // ld <= 96 on this path
-__global__ void __launch_bounds__(kBlock) dense_symm_dmma_kernel(long long n, int ld, int ldp, const double *__restrict__ Sp,
+// Factors wider than 96 columns are covered by column panels of pw <= 96 columns (col0 = first column of the panel),
+// one launch per panel; every output element still sums the same products in the same order.
+constexpr int kSymRows = 64, kSymMaxSub = 12;   // <= 96 columns per panel
+__global__ void __launch_bounds__(kBlock) dense_symm_dmma_kernel(long long n, int ld, int ldp, int col0, int pw,
+                                                                 const double *__restrict__ Sp,
                                                                  const double *__restrict__ X, double *__restrict__ part,
                                                                  int jb_per_split) {
     extern __shared__ double sm[];
     double *St = sm;                                   // kSymRows x (kDT + 1)
-    double *Xt = sm + kSymRows * (kDT + 1);            // kDT x (ldp + 1)
-    const int ldx = ldp + 1, nsub = ldp / 8;
+    double *Xt = sm + kSymRows * (kDT + 1);            // kDT x (pw + 1)
+    const int ldx = pw + 1, nsub = pw / 8;
     const long long i0 = (long long)blockIdx.x * kSymRows;
     const int nb = (int)((n + kDT - 1) / kDT);
     const int jb0 = blockIdx.y * jb_per_split, jb1 = min(nb, jb0 + jb_per_split);
@@ -646,9 +649,9 @@ __global__ void __launch_bounds__(kBlock) dense_symm_dmma_kernel(long long n, in
         const long long j0 = (long long)jb * kDT;
         __syncthreads();
         stash(jb);
-        for (int q = threadIdx.x; q < kDT * ldp; q += kBlock) {
-            const int rr = q / ldp, cc = q % ldp;
-            Xt[rr * ldx + cc] = ((j0 + rr) < n && cc < ld) ? X[(j0 + rr) * ld + cc] : 0.0;
+        for (int q = threadIdx.x; q < kDT * pw; q += kBlock) {
+            const int rr = q / pw, cc = q % pw;
+            Xt[rr * ldx + cc] = ((j0 + rr) < n && col0 + cc < ld) ? X[(j0 + rr) * ld + col0 + cc] : 0.0;
         }
         __syncthreads();
         if (jb + 1 < jb1) fetch(jb + 1);
@@ -663,7 +666,7 @@ __global__ void __launch_bounds__(kBlock) dense_symm_dmma_kernel(long long n, in
     }
     const long long gi = i0 + 8 * w + fr;
     if (gi < n) {
-        double *dst = part + ((size_t)blockIdx.y * n + gi) * ldp + 2 * fk;
+        double *dst = part + ((size_t)blockIdx.y * n + gi) * ldp + col0 + 2 * fk;
 #pragma unroll
         for (int q = 0; q < kSymMaxSub; ++q)
             if (q < nsub) { dst[8 * q] = acc[q][0]; dst[8 * q + 1] = acc[q][1]; }
@@ -828,7 +831,7 @@ __global__ void __launch_bounds__(kBlock) dense_symm_kernel(long long n, int r, 
 void launch_dense_symm(Ctx &c, long long n, int r, int ld, const double *Sp, const double *X, double a, double b,
                        const double *Z, const double *Z2, double *Y, double *red) {
     if (ld > 256) throw std::runtime_error("rank above 256 is not supported by the dense symm kernel yet");
-    if (ld <= 8 * kSymMaxSub && c.dense_part) {
+    if (c.dense_part) {
         // FP64 tensor-core path: split-K grid of (64-row blocks) x (splits), partials added in a fixed order
         const int ldp = ((ld + 7) / 8) * 8;
         const int nb = (int)((n + kDT - 1) / kDT), nrb = (int)((n + kSymRows - 1) / kSymRows);
@@ -840,10 +843,17 @@ void launch_dense_symm(Ctx &c, long long n, int r, int ld, const double *Sp, con
             nsplit = (nb + jbps - 1) / jbps;
             // (a register-tiled DFMA version of this kernel measured 136 us / 414 us at n = 3000, ld = 20 / 68 against
             //  90 us / 119 us for DMMA on the B200: the FP64 tensor pipe is the faster FP64 path on this part)
-            const size_t smem = sizeof(double) * (kSymRows * (kDT + 1) + kDT * (ldp + 1));
+            // column panels of (almost) equal width, each at most 8 * kSymMaxSub columns
+            const int npanel = (ldp + 8 * kSymMaxSub - 1) / (8 * kSymMaxSub);
+            const int pw_max = ((ldp / 8 + npanel - 1) / npanel) * 8;
+            const size_t smem = sizeof(double) * (kSymRows * (kDT + 1) + kDT * (pw_max + 1));
             LB2_CUDA(cudaFuncSetAttribute(dense_symm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            dense_symm_dmma_kernel<<<dim3(nrb, nsplit), kBlock, smem, c.stream>>>(n, ld, ldp, Sp, X, c.dense_part, jbps);
-            LB2_LAUNCH_CHECK(c);
+            for (int col0 = 0; col0 < ldp; col0 += pw_max) {
+                const int pw = std::min(pw_max, ldp - col0);
+                dense_symm_dmma_kernel<<<dim3(nrb, nsplit), kBlock, smem, c.stream>>>(n, ld, ldp, col0, pw, Sp, X, c.dense_part,
+                                                                                       jbps);
+                LB2_LAUNCH_CHECK(c);
+            }
             dense_symm_finish_kernel<<<grid_for(n * ld, 1, c), kBlock, 0, c.stream>>>(n, r, ld, ldp, nsplit, c.dense_part, a, b, Z, Z2,
                                                                                    Y, c.rs, red);
             LB2_LAUNCH_CHECK(c);
@@ -1745,24 +1755,32 @@ __device__ __forceinline__ void lp_update_one(const LpDev &L, int j, int lane, d
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kBlock) lp_sweep_kernel(LpDev L, double rho, const double *__restrict__ b,
-                                                          const double *__restrict__ lam, double *cvs, double *x, double *u,
-                                                          double *v) {
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int lv = 0; lv < L.n_lvl; ++lv) {
-        for (int q = L.lvl_ptr[lv] + w; q < L.lvl_ptr[lv + 1]; q += kBlock / 32) {
+// One launch covers the levels [lv_lo, lv_hi).  A wide level is a launch of its own over many CTAs (its columns share no
+// row, so any assignment of columns to warps gives the same values); runs of narrow levels share a one-CTA launch with a
+// block barrier between levels.  The segments are built on the host (Solver::set_lp).
+__global__ void __launch_bounds__(kBlock) lp_sweep_kernel(LpDev L, int lv_lo, int lv_hi, double rho,
+                                                          const double *__restrict__ b, const double *__restrict__ lam,
+                                                          double *cvs, double *x, double *u, double *v) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5), nw = gridDim.x * (kBlock / 32);
+    for (int lv = lv_lo; lv < lv_hi; ++lv) {
+        for (int q = L.lvl_ptr[lv] + w; q < L.lvl_ptr[lv + 1]; q += nw) {
             const int j = L.lvl_col[q];
             lp_update_one(L, j, lane, rho, b, lam, cvs, x, u, v);
             lp_update_one(L, j, lane, rho, b, lam, cvs, x, v, u);
         }
-        __syncthreads();
+        if (lv + 1 < lv_hi) __syncthreads();      // more than one level only in one-CTA launches
     }
 }
 
-void launch_lp_sweep(Ctx &c, const LpDev &L, double rho, const double *b, const double *lam, double *cvs, double *x,
-                     double *u, double *v) {
-    lp_sweep_kernel<<<1, kBlock, 0, c.stream>>>(L, rho, b, lam, cvs, x, u, v);
-    LB2_LAUNCH_CHECK(c);
+void launch_lp_sweep(Ctx &c, const LpDev &L, const LpSeg *segs, int n_segs, double rho, const double *b, const double *lam,
+                     double *cvs, double *x, double *u, double *v) {
+    for (int k = 0; k < n_segs; ++k) {
+        const LpSeg &g = segs[k];
+        if (g.blocks > 1 && g.lv_hi - g.lv_lo != 1) throw std::logic_error("LP sweep: a multi-CTA segment must be one level");
+        lp_sweep_kernel<<<g.blocks, kBlock, 0, c.stream>>>(L, g.lv_lo, g.lv_hi, rho, b, lam, cvs, x, u, v);
+        LB2_LAUNCH_CHECK(c);
+    }
 }
 
 __global__ void __launch_bounds__(kBlock) lp_dinf_kernel(LpDev L, const double *__restrict__ w, double *S, int slot, ReduceScratch rs) {

@@ -237,8 +237,9 @@ void launch_lp_grad(Ctx &c, const LpDev &L, const double *w, const double *r, do
 // One Gauss-Seidel sweep over the LP columns, u_j then v_j, with constrValSum kept current
 // (LORADSUpdateSDPLPVar + LORADSUpdateLPVarOne, lorads_alg_common.c:225-249, lorads_admm.c:595-628);
 // x[j] is the product currently represented in constrValSum for column j (constrValLP[j] = a_j x[j]).
-void launch_lp_sweep(Ctx &c, const LpDev &L, double rho, const double *b, const double *lam, double *cvs, double *x,
-                     double *u, double *v);
+struct LpSeg { int lv_lo, lv_hi, blocks; };     // levels [lv_lo, lv_hi) in one launch of `blocks` CTAs
+void launch_lp_sweep(Ctx &c, const LpDev &L, const LpSeg *segs, int n_segs, double rho, const double *b, const double *lam,
+                     double *cvs, double *x, double *u, double *v);
 // S[slot] = sum_j |min(c_j + a_j^T w, 0)|   (calculate_dual_infeasibility_solver, lorads_solver.c:1015-1023; w = -lambda)
 void launch_lp_dinf(Ctx &c, const LpDev &L, const double *w, double *S, int slot);
 

@@ -184,6 +184,15 @@ void Solver::build_lp() {
         std::vector<int> cur(lptr.begin(), lptr.end() - 1);
         for (long long j = 0; j < nLp; ++j) lcol[(size_t)cur[(size_t)level[(size_t)j]]++] = (int)j;
     }
+    // launches of the sweep: a level of 64 columns or more (over eight per warp of one CTA) gets its own multi-CTA launch,
+    // runs of narrower levels share a one-CTA launch
+    lp_segs.clear();
+    for (int l = 0; l < n_lvl; ++l) {
+        const int cols = lptr[(size_t)l + 1] - lptr[(size_t)l];
+        if (cols >= 64) lp_segs.push_back(LpSeg{l, l + 1, std::min((cols + 7) / 8, 8 * ctx.num_sms)});
+        else if (!lp_segs.empty() && lp_segs.back().blocks == 1) lp_segs.back().lv_hi = l + 1;
+        else lp_segs.push_back(LpSeg{l, l + 1, 1});
+    }
     lp_c.upload(lp_c_h); lp_rbeg.upload(rbeg); lp_rcol.upload(rcol); lp_rval.upload(rval);
     lp_cbeg.upload(cbeg); lp_crow.upload(crow); lp_cval.upload(cval); lp_nrm2sq.upload(n2);
     lp_lvl_ptr.upload(lptr); lp_lvl_col.upload(lcol);
@@ -1337,7 +1346,7 @@ void Solver::update_sdp_var(double rho, double tol, long long maxit) {
         }
     }
     // LORADSUpdateSDPLPVar, lorads_alg_common.c:225-249: the LP columns follow the cones in the same sweep
-    if (nLp > 0) launch_lp_sweep(ctx, lp, rho, b.p, lam.p, s.p, lp_x.p, U.p + N, V.p + N);
+    if (nLp > 0) launch_lp_sweep(ctx, lp, lp_segs.data(), (int)lp_segs.size(), rho, b.p, lam.p, s.p, lp_x.p, U.p + N, V.p + N);
 }
 
 void Solver::get_lp_vec(char which, double *out) {

@@ -109,6 +109,7 @@ struct Solver {
     std::vector<double> lp_c_h;
     DBuf<double> lp_c, lp_rval, lp_cval, lp_nrm2sq, lp_x;
     DBuf<int> lp_rbeg, lp_rcol, lp_cbeg, lp_crow, lp_lvl_ptr, lp_lvl_col;
+    std::vector<LpSeg> lp_segs;     // launches of the Gauss-Seidel sweep (kernels.cuh)
     LpDev lp;
     void set_lp(long long nLpCols, const lb2_int *beg, const lb2_int *idx, const double *elem);
     void build_lp();
