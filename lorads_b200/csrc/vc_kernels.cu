@@ -517,6 +517,20 @@ inline int vc_grid(const Ctx &c, long long n, int G, int per_sm) {
     return (int)std::max<long long>(g, 1);
 }
 
+// Resident CTAs per SM asked of the compiler for factors wider than 32 columns (NP >= 2 passes): 0 = the budget of the
+// one-pass kernels (48 / 64 registers, accumulators partly in local memory), 3 and 2 = 80 / 128 registers.  Measured at
+// n = 1e5 (scripts/wide_minb.py, profiles/r02_wide_factor_register_budget.log; us hot, settings 0 / 3 / 2):
+//   ld  64: TRI  99 /  99 /  94   SpMM  81 / 101 /  96
+//   ld  96: TRI 174 / 187 / 163   SpMM 139 / 176 / 126
+//   ld 128: TRI 263 / 285 / 312   SpMM 219 / 158 / 199
+// The defaults below take the fastest of each row; LORADS_B200_VC_WIDE_MINB (read at every launch, so that one process
+// can compare the settings) overrides them.  A() values and the SpMM are bit-identical across the settings; the
+// objective sum follows the persistent grid and moves in the last bit.
+static int vc_wide_minb(int dflt) {
+    const char *e = getenv("LORADS_B200_VC_WIDE_MINB");
+    return e ? atoi(e) : dflt;
+}
+
 template <int NP, int UN, int MINB = (UN == 1 ? 5 : 3), int PL = 1>
 void spmm_launch(Ctx &c, const VcDev &V, int ld, bool useC, const double *w, const int *wmap, const double *Sres, const double *X,
                  double a, double b, const double *Z, const double *Z2, double *Y, double *red, const double *cs, double c1) {
@@ -572,12 +586,17 @@ void auv_dispatch(Ctx &c, int np, int un, const VcDev &V, int ld, bool with_obj,
         else LB2_VC_AUV(1, 1);
         break;
     }
-    case 2: LB2_VC_AUV(2, 1); break;
-    case 3: LB2_VC_AUV(3, 1); break;
-    case 4: LB2_VC_AUV(4, 1); break;
+#define LB2_VC_AUV_WIDE(NP_)                                                                                                    \
+    if (wide == 2) auv_launch<MODE, NP_, 1, 2>(c, V, ld, with_obj, U, W, s1, s2, o1, o2, o3, obj1, obj2);                         \
+    else if (wide == 3) auv_launch<MODE, NP_, 1, 3>(c, V, ld, with_obj, U, W, s1, s2, o1, o2, o3, obj1, obj2);                    \
+    else LB2_VC_AUV(NP_, 1);
+    case 2: { const int wide = vc_wide_minb(2); LB2_VC_AUV_WIDE(2) break; }
+    case 3: { const int wide = vc_wide_minb(2); LB2_VC_AUV_WIDE(3) break; }
+    case 4: { const int wide = vc_wide_minb(0); LB2_VC_AUV_WIDE(4) break; }
     case 6: LB2_VC_AUV(6, 1); break;
     default: LB2_VC_AUV(8, 1); break;
     }
+#undef LB2_VC_AUV_WIDE
 #undef LB2_VC_AUV
 }
 
@@ -628,12 +647,17 @@ void launch_vc_spmm(Ctx &c, const VcDev &V, int ld, bool useC, const double *w, 
         else LB2_VC_SPMM(1, 1);
         break;
     }
-    case 2: LB2_VC_SPMM(2, 1); break;
-    case 3: LB2_VC_SPMM(3, 1); break;
-    case 4: LB2_VC_SPMM(4, 1); break;
+#define LB2_VC_SPMM_WIDE(NP_)                                                                                                   \
+    if (wide == 2) spmm_launch<NP_, 1, 2>(c, V, ld, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, red, cs, c1);                          \
+    else if (wide == 3) spmm_launch<NP_, 1, 3>(c, V, ld, useC, w, wmap, Sres, X, a, b, Z, Z2, Y, red, cs, c1);                     \
+    else LB2_VC_SPMM(NP_, 1);
+    case 2: { const int wide = vc_wide_minb(0); LB2_VC_SPMM_WIDE(2) break; }
+    case 3: { const int wide = vc_wide_minb(2); LB2_VC_SPMM_WIDE(3) break; }
+    case 4: { const int wide = vc_wide_minb(3); LB2_VC_SPMM_WIDE(4) break; }
     case 6: LB2_VC_SPMM(6, 1); break;
     default: LB2_VC_SPMM(8, 1); break;
     }
+#undef LB2_VC_SPMM_WIDE
 #undef LB2_VC_SPMM
     c.launches++;
     LB2_CUDA(cudaGetLastError());
