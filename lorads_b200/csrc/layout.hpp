@@ -493,22 +493,40 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
     // ----------------------------- vertex-centric class split -----------------------------
     {
         VcLayout &V = L.vc;
+        // Two constructions of the class-split adjacency that must give identical arrays: "rows" (default) walks the
+        // symmetric adjacency of P row by row, threads over row ranges, and classifies every pattern position through T
+        // and an objective look-up; "sort" (LORADS_B200_VC_BUILD=sort) builds entry lists per class and scatters them
+        // into a symmetric CSR.  tests/test_host_layout.py compares the two on every instance shape of the suite.
+        const char *build_env = getenv("LORADS_B200_VC_BUILD");
+        bool by_rows = !(build_env && std::string(build_env) == "sort");
+        std::vector<int32_t> obj_k;           // objective entry at a pattern position (-1: none)
+        if (by_rows) {
+            obj_k.assign(np, -1);
+            for (int64_t k = beg[0]; k < beg[1] && by_rows; ++k) {
+                if (obj_k[epos[k]] >= 0) by_rows = false;          // repeated objective entry: the list construction keeps both
+                else obj_k[epos[k]] = (int32_t)k;
+            }
+        }
         // lower-triangular entries (row >= col) of the three classes, each list in (col,row) order
         struct Ent { int32_t row, col, tag; double val; };
         std::vector<Ent> dyn, sta;
         // objective: entries of column 0 are already in (col,row) order
-        sta.reserve(beg[1] - beg[0]);
-        for (int64_t k = beg[0]; k < beg[1]; ++k) sta.push_back({erow[k], ecol[k], -1, sval[k]});
+        if (!by_rows) {
+            sta.reserve(beg[1] - beg[0]);
+            for (int64_t k = beg[0]; k < beg[1]; ++k) sta.push_back({erow[k], ecol[k], -1, sval[k]});
+        }
         // singleton constraints
         V.d_con.assign(n, -1); V.d_coef.assign(n, 0.0);
         std::vector<Ent> low;
+        std::vector<uint8_t> single(L.n_act, 0);
         V.n_single = 0;
         for (int64_t a = 0; a < L.n_act; ++a) {
             const int64_t i = L.act_idx[a];
             if (beg[i + 2] - beg[i + 1] != 1) continue;
             const int64_t k = beg[i + 1];
             V.n_single++;
-            dyn.push_back({erow[k], ecol[k], (int32_t)a, sval[k]});
+            single[a] = 1;
+            if (!by_rows) dyn.push_back({erow[k], ecol[k], (int32_t)a, sval[k]});
             if (erow[k] == ecol[k] && V.d_con[erow[k]] < 0) { V.d_con[erow[k]] = (int32_t)a; V.d_coef[erow[k]] = sval[k]; }
             else low.push_back({erow[k], ecol[k], (int32_t)a, (erow[k] == ecol[k]) ? sval[k] : 2.0 * sval[k]});
         }
@@ -561,9 +579,51 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
                     V.Tr_con[q] = (int32_t)a; V.Tr_val[q] = sval[k];
                 }
             }
-            for (int64_t p = 0; p < np; ++p)
-                if (V.Tr_ptr[p + 1] > V.Tr_ptr[p]) dyn.push_back({L.P_row[p], L.P_col[p], (int32_t)(-2 - p), 0.0});
+            if (!by_rows)
+                for (int64_t p = 0; p < np; ++p)
+                    if (V.Tr_ptr[p + 1] > V.Tr_ptr[p]) dyn.push_back({L.P_row[p], L.P_col[p], (int32_t)(-2 - p), 0.0});
         }
+        pt.lap("vc: entry classes");
+        if (by_rows) {
+            // Row i of adj lists its pattern positions by ascending neighbour -- the order the symmetric CSR of the list
+            // construction produces.  At one position the singleton constraints come in ascending compact index (the order
+            // of T), then the residual entry; the objective entry of the position goes to the second half of the row.
+            std::vector<int32_t> nd(n), ns(n);
+            auto walk = [&](int64_t i, auto dyn_entry, auto sta_entry) {
+                for (int32_t e = L.adj_ptr[i]; e < L.adj_ptr[i + 1]; ++e) {
+                    const int32_t p = L.adj_pos[e], nb = L.adj_col[e];
+                    for (int32_t q = L.T_ptr[p]; q < L.T_ptr[p + 1]; ++q)
+                        if (single[L.T_con[q]]) dyn_entry(nb, L.T_con[q], L.T_val[q]);
+                    if (V.Tr_ptr[p + 1] > V.Tr_ptr[p]) dyn_entry(nb, (int32_t)(-2 - p), 0.0);
+                    if (obj_k[p] >= 0) sta_entry(nb, sval[obj_k[p]]);
+                }
+            };
+            parallel_chunks(n, nthreads, [&](int64_t i0, int64_t i1) {
+                for (int64_t i = i0; i < i1; ++i) {
+                    int32_t d = 0, t = 0;
+                    walk(i, [&](int32_t, int32_t, double) { ++d; }, [&](int32_t, double) { ++t; });
+                    nd[i] = d; ns[i] = t;
+                }
+            });
+            int64_t total = 0;
+            for (int64_t i = 0; i < n; ++i) total += (int64_t)nd[i] + ns[i];
+            if (total > (int64_t)2000000000) throw std::runtime_error("adjacency exceeds 2^31 entries");
+            V.u_ptr.assign(n + 1, 0); V.u_mid.assign(n, 0);
+            for (int64_t i = 0; i < n; ++i) {
+                V.u_mid[i] = V.u_ptr[i] + nd[i];
+                V.u_ptr[i + 1] = V.u_mid[i] + ns[i];
+            }
+            V.u_col.resize(total); V.u_tag.resize(total); V.u_val.resize(total);
+            parallel_chunks(n, nthreads, [&](int64_t i0, int64_t i1) {
+                for (int64_t i = i0; i < i1; ++i) {
+                    int64_t wd = V.u_ptr[i], ws = V.u_mid[i];
+                    walk(i,
+                         [&](int32_t nb, int32_t tag, double val) { V.u_col[wd] = nb; V.u_tag[wd] = tag; V.u_val[wd] = val; ++wd; },
+                         [&](int32_t nb, double val) { V.u_col[ws] = nb; V.u_tag[ws] = -1; V.u_val[ws] = val; ++ws; });
+                }
+            });
+            pt.lap("vc: adjacency by rows");
+        } else {
         if (!std::is_sorted(dyn.begin(), dyn.end(), by_pos)) std::stable_sort(dyn.begin(), dyn.end(), by_pos);
         // symmetric adjacency: per row the weight-dependent entries, then the objective entries
         std::vector<int32_t> dptr, sptr, dslot, sslot;
@@ -594,6 +654,8 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
             }
             V.u_ptr[n] = (int32_t)w;
         }
+        pt.lap("vc: adjacency by sorted lists");
+        }
         // rows by decreasing work (stable counting sort).  Sorting pays while the factors are L2 resident; on very
         // large blocks the scattered row order costs more DRAM locality than the balance gains (measured, n = 1e6)
         auto by_work = [&](std::vector<int32_t> &out, auto work) {
@@ -609,6 +671,7 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
         };
         by_work(V.order, [&](int64_t i) { return V.u_ptr[i + 1] - V.u_ptr[i]; });
         by_work(V.order_l, [&](int64_t i) { return V.u_ptr[i + 1] - V.u_mid[i]; });     // objective entries of the row
+        pt.lap("vc: row orders");
         // Bounds of everything the gather kernels index with (compute-sanitizer is not available on the target pool, so the
         // layout is proved in range here, once, on the host): neighbours and rows inside the block, constraint tags
         // inside the compact constraint range, residual tags inside the pattern, monotone pointers.
@@ -632,7 +695,7 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
         V.on = L.nnzA == 0 || 2 * V.n_single >= L.n_act;
         if (const char *e = getenv("LORADS_B200_VC")) V.on = atoi(e) != 0;
     }
-    pt.lap("vertex-centric split");
+    pt.lap("vc: bounds proof");
     return L;
 }
 

@@ -210,3 +210,65 @@ def test_layout_edge_shapes_against_the_restatement(case):
     Y += lay["c_rank1"] * V.sum(axis=0)[None, :]
     assert rel_err(Y, O.wsum_mulrk(w, True, "V")) < TOL
     check_vc(lay, U, V, w, O.auv("U", "V"), ref_obj, O.wsum_mulrk(w, True, "V"), inst.m)
+
+
+def _with_extra_constraints(inst, extra, seed):
+    """Appends constraints given as lists of (row, col, value) to the single cone of `inst`: repeated singleton
+    constraints on one position, multi-entry (residual) constraints that share positions with singletons."""
+    cone = inst.cones[0]
+    n = cone.n
+    beg, idx, elem = list(cone.beg), list(cone.idx), list(cone.elem)
+    for entries in extra:
+        for (i, j, v) in sorted(entries, key=lambda e: (min(e[0], e[1]), max(e[0], e[1]))):
+            r, c = max(i, j), min(i, j)
+            idx.append(c * n - c * (c - 1) // 2 + (r - c))      # packed lower-triangular index, column-major
+            elem.append(v)
+        beg.append(len(idx))
+    rng = np.random.default_rng(seed)
+    out = sdpa.Instance(m=inst.m + len(extra), cones=[sdpa.Cone(n=n, beg=np.array(beg), idx=np.array(idx), elem=np.array(elem))],
+                        b=np.concatenate([inst.b, rng.standard_normal(len(extra))]))
+    return out
+
+
+def _vc_build_cases():
+    cases = {k: f for k, f in EDGE.items() if k not in ("theta_dense", "tiny_dense")}
+    cases["two_block_cone1"] = None
+    base = sdpa.maxcut(200, 500, 77)
+    cases["repeated_singletons_and_residuals"] = lambda: _with_extra_constraints(base, [
+        [(3, 3, 2.0)], [(3, 3, -1.0)],                       # two more singleton constraints on a diagonal position
+        [(7, 2, 0.5)], [(7, 2, 1.5)],                        # two singleton constraints on one off-diagonal position
+        [(7, 2, 1.0), (9, 9, 2.0), (11, 4, -3.0)],           # residual constraint sharing positions with singletons
+        [(5, 5, 1.0), (6, 6, 1.0)], [(20, 1, 1.0), (20, 1, 2.0)],   # residual; a constraint listing one position twice
+    ], 5)
+    return cases
+
+
+@pytest.mark.parametrize("case", sorted(_vc_build_cases()))
+def test_vc_adjacency_constructions_agree(case, monkeypatch):
+    """The class-split adjacency is built by walking the pattern adjacency row by row (default, threaded); the
+    construction from sorted entry lists (LORADS_B200_VC_BUILD=sort) must give the very same arrays, entry for entry --
+    the order inside a row fixes the order of the floating-point sums of the gather kernels."""
+    if case == "two_block_cone1":
+        import sys
+        from conftest import GOLDEN_DIR
+        sys.path.insert(0, GOLDEN_DIR)
+        from make_golden import build_instance
+        inst = build_instance("two_block", dict(n1=25, e1=70, n2=140, e2=600))
+        cones = [(inst.cones[1], inst.m), (inst.cones[0], inst.m)]
+    else:
+        inst = _vc_build_cases()[case]()
+        cones = [(inst.cones[0], inst.m)]
+    for cone, m in cones:
+        for threads in ("1", "5"):
+            monkeypatch.setenv("LORADS_B200_PRESOLVE_THREADS", threads)
+            monkeypatch.delenv("LORADS_B200_VC_BUILD", raising=False)
+            a = capi.host_layout(cone, m)
+            monkeypatch.setenv("LORADS_B200_VC_BUILD", "sort")
+            b = capi.host_layout(cone, m)
+            assert a.keys() == b.keys()
+            assert a["dense_path"] or any(k.startswith("vc_") for k in a)
+            for k in a:
+                if isinstance(a[k], np.ndarray):
+                    assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), k
+                else:
+                    assert a[k] == b[k], k
