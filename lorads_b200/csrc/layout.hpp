@@ -588,14 +588,35 @@ inline ConeLayout build_cone_layout(int64_t n, int64_t m, const int64_t *beg_in,
             // Row i of adj lists its pattern positions by ascending neighbour -- the order the symmetric CSR of the list
             // construction produces.  At one position the singleton constraints come in ascending compact index (the order
             // of T), then the residual entry; the objective entry of the position goes to the second half of the row.
+            // One record per pattern position, filled in a sequential sweep, so that the row walk below costs one
+            // random access per adjacency slot: number of weight-dependent entries (nd >> 1), objective flag (nd & 1),
+            // tag / value of the weight-dependent entry when there is exactly one (the common case).
+            struct PosRec { double dval, oval; int32_t tag, nd; };
+            std::vector<PosRec> rec(np);
+            parallel_chunks(np, nthreads, [&](int64_t p0, int64_t p1) {
+                for (int64_t p = p0; p < p1; ++p) {
+                    PosRec r{0.0, 0.0, 0, 0};
+                    int32_t cnt = 0;
+                    for (int32_t q = L.T_ptr[p]; q < L.T_ptr[p + 1]; ++q)
+                        if (single[L.T_con[q]]) { if (cnt++ == 0) { r.tag = L.T_con[q]; r.dval = L.T_val[q]; } }
+                    if (V.Tr_ptr[p + 1] > V.Tr_ptr[p]) { if (cnt++ == 0) { r.tag = (int32_t)(-2 - p); r.dval = 0.0; } }
+                    r.nd = cnt << 1;
+                    if (obj_k[p] >= 0) { r.nd |= 1; r.oval = sval[obj_k[p]]; }
+                    rec[p] = r;
+                }
+            });
             std::vector<int32_t> nd(n), ns(n);
             auto walk = [&](int64_t i, auto dyn_entry, auto sta_entry) {
                 for (int32_t e = L.adj_ptr[i]; e < L.adj_ptr[i + 1]; ++e) {
                     const int32_t p = L.adj_pos[e], nb = L.adj_col[e];
-                    for (int32_t q = L.T_ptr[p]; q < L.T_ptr[p + 1]; ++q)
-                        if (single[L.T_con[q]]) dyn_entry(nb, L.T_con[q], L.T_val[q]);
-                    if (V.Tr_ptr[p + 1] > V.Tr_ptr[p]) dyn_entry(nb, (int32_t)(-2 - p), 0.0);
-                    if (obj_k[p] >= 0) sta_entry(nb, sval[obj_k[p]]);
+                    const PosRec &r = rec[p];
+                    if ((r.nd >> 1) == 1) dyn_entry(nb, r.tag, r.dval);
+                    else if ((r.nd >> 1) > 1) {
+                        for (int32_t q = L.T_ptr[p]; q < L.T_ptr[p + 1]; ++q)
+                            if (single[L.T_con[q]]) dyn_entry(nb, L.T_con[q], L.T_val[q]);
+                        if (V.Tr_ptr[p + 1] > V.Tr_ptr[p]) dyn_entry(nb, (int32_t)(-2 - p), 0.0);
+                    }
+                    if (r.nd & 1) sta_entry(nb, r.oval);
                 }
             };
             parallel_chunks(n, nthreads, [&](int64_t i0, int64_t i1) {
