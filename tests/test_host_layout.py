@@ -272,3 +272,53 @@ def test_vc_adjacency_constructions_agree(case, monkeypatch):
                     assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), k
                 else:
                     assert a[k] == b[k], k
+
+
+def _dense_reference(cone, m, U, V, w):
+    """A(sym(UV^T)), <C, sym(UV^T)> and (C + A^*(w)) V from dense symmetric matrices built straight from the reader
+    arrays (column 0 = C, column i = A_i; packed lower-triangular indices)."""
+    n = cone.n
+    Z = 0.5 * (U @ V.T + V @ U.T)
+    mats = []
+    for c in range(m + 1):
+        k = np.arange(cone.beg[c], cone.beg[c + 1])
+        i, j = sdpa.unpack_idx(n, np.asarray(cone.idx)[k].astype(np.int64))
+        A = np.zeros((n, n))
+        np.add.at(A, (i, j), np.asarray(cone.elem)[k])
+        A = A + np.tril(A, -1).T
+        mats.append(A)
+    auv = np.array([float((A * Z).sum()) for A in mats[1:]])
+    obj = float((mats[0] * Z).sum())
+    S = mats[0] + sum(wi * A for wi, A in zip(w, mats[1:]))
+    return auv, obj, S @ V
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_vc_layout_on_random_mixed_constraints(seed):
+    """Singleton constraints (several on one position), multi-entry constraints sharing positions with them and with the
+    objective: the class-split layout evaluated in numpy against dense matrices built from the same reader arrays."""
+    rng = np.random.default_rng(100 + seed)
+    base = sdpa.maxcut(120, 300, 60 + seed)
+    cone = base.cones[0]
+    i0, j0 = sdpa.unpack_idx(cone.n, np.asarray(cone.idx[cone.beg[0]:cone.beg[1]]).astype(np.int64))
+    extra = []
+    for _ in range(30):
+        cnt = int(rng.integers(1, 5))
+        pick = rng.integers(0, i0.size, size=cnt)
+        ent = {(int(i0[p]), int(j0[p])): float(rng.standard_normal()) for p in pick}      # distinct positions of C's pattern
+        if rng.random() < 0.3:
+            a, b = sorted(rng.integers(0, cone.n, size=2))
+            ent[(int(b), int(a))] = float(rng.standard_normal())                           # a position outside C's pattern
+        extra.append([(i, j, v) for (i, j), v in ent.items()])
+    inst = _with_extra_constraints(base, extra, seed)
+    cone = inst.cones[0]
+    lay = capi.host_layout(cone, inst.m)
+    assert not lay["dense_path"] and lay["vc_nnz_res"] > 0 and lay["vc_l_row"].size > 0
+    U, V = rng.standard_normal((cone.n, 6)), rng.standard_normal((cone.n, 6))
+    w = rng.standard_normal(inst.m)
+    auv, obj, SV = _dense_reference(cone, inst.m, U, V, w)
+    check_vc(lay, U, V, w, auv, obj, SV, inst.m)
+    compact = item_values(lay, "A", U, V)
+    full = np.zeros(inst.m)
+    full[lay["act_idx"]] = compact
+    assert rel_err(full, auv) < TOL
